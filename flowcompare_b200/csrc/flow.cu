@@ -1,0 +1,352 @@
+// The conditional normalizing flow: `Flow.log_prob` of reference models/transform.py:70-76 over the
+// transform list of model_initialization.py:134-152, as a stream of fused GEMM / attention launches.
+//
+// Per coupling layer (attention configs), with M = B*N rows:
+//   pre-attention MLP (reference models/cif_block.py:14-20, models/nets.py:19-30)   4 GEMMs (GELU/residual fused)
+//   LayerNorm row statistics (models/perceiver.py:26-35)                            1 small kernel
+//   to_q with LayerNorm folded into the epilogue (perceiver.py:109)                 1 GEMM
+//   to_kv on the context (perceiver.py:110)                                         1 GEMM
+//   softmax(q k^T / 8) v, flash style (perceiver.py:111-113)                        1 kernel
+//   coupling MLP; attention out-projection (perceiver.py:95-96) and the concat with x1 / extra
+//   context (transform.py:49-50, affine_coupling.py:34-35) folded into its first layer           4 GEMMs
+//     last GEMM's epilogue = sigmoid scale, y2 = x2*s + t in place, sum log s -> partial log-det
+//   ActNorm + LinearLU folded into one 300x300 GEMM (act_norm.py:37-43, permuters.py:164-169)     1 GEMM
+// The running log-det never leaves fp32 registers/partials until the final reduction.
+#include "model.cuh"
+#include <new>
+
+namespace {
+
+__global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
+                                 long long M, int cols) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * cols) return;
+    const long long r = i / cols; const int c = (int)(i % cols);
+    dst[r * ldd + c] = src[r * lds + c];
+}
+
+// one warp per row: mean and 1/sqrt(var + eps) (biased variance, two passes in registers)
+__global__ void ln_stats_kernel(const float* __restrict__ h, int ldh, int M, int width, float eps,
+                                float* __restrict__ mu, float* __restrict__ rstd) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* p = h + (size_t)row * ldh;
+    float v[16];
+    float s = 0.f;
+    const int per = (width + 31) / 32;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        v[i] = 0.f;
+        if (i < per) { const int c = i * 32 + lane; if (c < width) { v[i] = p[c]; s += v[i]; } }
+    }
+    s = fc_warp_sum(s);
+    const float m = s / (float)width;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (i < per) { const int c = i * 32 + lane; if (c < width) { const float d = v[i] - m; q = fmaf(d, d, q); } }
+    q = fc_warp_sum(q);
+    if (lane == 0) { mu[row] = m; rstd[row] = rsqrtf(q / (float)width + eps); }
+}
+
+// cbA[b] = [extra_b (if extra) | ctx_b (if global)], zero padded to lda
+__global__ void build_cb_input_kernel(const float* __restrict__ extra, const float* __restrict__ ctx, int E,
+                                      int has_extra, int is_global, int B, int lda, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * lda) return;
+    const int b = i / lda, c = i % lda;
+    float v = 0.f;
+    if (has_extra && c == 0) v = extra[b];
+    else if (is_global) { const int e = c - has_extra; if (e >= 0 && e < E) v = ctx[(size_t)b * E + e]; }
+    out[i] = v;
+}
+
+// log_prob[row] = sum(augment partials) + sum(coupling partials) + const + sum_d(-0.5 z_d^2 - 0.5 log 2pi)
+// (reference models/distributions.py:192-195 for the base density).  One warp per row.
+__global__ void finalize_kernel(const float* __restrict__ z, int ldz, int D, const float* __restrict__ apart,
+                                int n_apart, const float* __restrict__ cpart, int n_cpart, int M, float ldj_const,
+                                float* __restrict__ log_prob) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* p = z + (size_t)row * ldz;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) { const float v = p[c]; s += -0.91893853320467274178f - 0.5f * v * v; }
+    s = fc_warp_sum(s);
+    if (lane == 0) {
+        float acc = 0.f;
+        for (int i = 0; i < n_apart; ++i) acc += apart[(size_t)i * M + row];
+        for (int i = 0; i < n_cpart; ++i) acc += cpart[(size_t)i * M + row];
+        log_prob[row] = (acc + ldj_const) + s;
+    }
+}
+
+}  // namespace
+
+int fc_launch_ln_stats(const float* h, int ldh, int M, int width, float eps, float* mu, float* rstd, cudaStream_t s) {
+    FC_REQUIRE(width <= 512);
+    const int wpb = 8;
+    ln_stats_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, s>>>(h, ldh, M, width, eps, mu, rstd);
+    fc_count_launch();
+    FC_LAUNCH_OK();
+    return FC_OK;
+}
+
+static int gemm_plain(const FcLinear& l, const float* A1, int lda1, const float* A2, int lda2, const float* bias,
+                      int bias_ld, int bias_group, const float* res, int ldres, int act, float* C, int ldc, int M,
+                      int precision, cudaStream_t stream) {
+    GemmArgs g = fc_gemm_args_zero();
+    g.A1 = A1; g.lda1 = lda1; g.K1 = l.K1; g.A2 = A2; g.lda2 = lda2; g.K2 = l.K2;
+    g.Wt = l.w; g.ldw = l.ldw;
+    if (bias) { g.bias = bias; g.bias_ld = bias_ld; g.bias_group = bias_group; }
+    else { g.bias = l.b; }
+    g.res = res; g.ldres = ldres; g.act = act; g.C = C; g.ldc = ldc; g.M = M; g.N = l.N;
+    g.precision = precision;
+    return fc_launch_gemm(g, stream);
+}
+
+int fc_run_mlp_hidden(const FcMlp& m, const FcMlpIn& in, int M, float* bufA, float* bufB, int ldh, int precision,
+                      cudaStream_t stream, float** last) {
+    // reference models/nets.py:19-30: x = act(in(x)); even hidden i: res = x, x = act(layer(x));
+    // odd i: x = act(res + layer(x))
+    int rc = gemm_plain(m.in, in.A1, in.lda1, in.A2, in.lda2, in.bias, in.bias_ld, in.bias_group, nullptr, 0,
+                        FC_ACT_GELU, bufA, ldh, M, precision, stream);
+    if (rc) return rc;
+    float* cur = bufA; float* other = bufB;
+    for (int i = 0; i < m.n_hidden; ++i) {
+        if ((i & 1) == 0) {
+            rc = gemm_plain(m.hidden[i], cur, ldh, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_GELU, other, ldh, M,
+                            precision, stream);
+        } else {
+            // residual source is `other` (the activation before the previous layer); write in place over it
+            rc = gemm_plain(m.hidden[i], cur, ldh, nullptr, 0, nullptr, 0, 0, other, ldh, FC_ACT_GELU, other, ldh, M,
+                            precision, stream);
+        }
+        if (rc) return rc;
+        float* t = cur; cur = other; other = t;
+    }
+    *last = cur;
+    return FC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ create
+static FcAttn read_attn(FcCursor& c, const fc_flow& f) {
+    FcAttn a;
+    a.csum = c.ptr(c.next(), f.inner);
+    a.qbias = c.ptr(c.next(), f.inner);
+    a.q = c.linear(f.attn_in, 0, f.inner, /*has_bias=*/false);
+    a.kv = c.linear(f.E, 0, 2 * f.inner, /*has_bias=*/false);
+    if (!a.csum || !a.qbias) c.ok = false;
+    return a;
+}
+
+extern "C" int fc_flow_create(const int32_t* header, int n_header, const int64_t* table, int n_table,
+                              const float* arena, int64_t arena_floats, fc_flow** out) {
+    FC_REQUIRE(header && table && arena && out && n_header >= 19);
+    if (header[0] != FC_FLOW_MAGIC || header[1] != FC_ARENA_VERSION) return FC_ERR_MODEL;
+    if (reinterpret_cast<uintptr_t>(arena) & 15) return FC_ERR_MODEL;
+    fc_flow* f = new (std::nothrow) fc_flow();
+    if (!f) return FC_ERR_MODEL;
+    f->L = header[2]; f->D = header[3]; f->d_in = header[4]; f->half = header[5]; f->extra = header[6];
+    f->is_global = header[7]; f->E = header[8]; f->inner = header[9]; f->attn_in = header[10];
+    f->hid = header[11]; f->n_hid = header[12]; f->pre_hid = header[13]; f->n_pre_hid = header[14];
+    f->aug_hid = header[15]; f->n_aug_hid = header[16]; f->augpre_hid = header[17]; f->n_augpre_hid = header[18];
+    f->arena = arena; f->arena_floats = arena_floats;
+    bool dims_ok = f->L >= 1 && f->D >= 2 && f->D <= 512 && f->d_in >= 1 && f->d_in < f->D && f->half == f->D / 2 &&
+                   f->inner == 64 && f->attn_in <= 512 && f->hid <= 512 && f->pre_hid <= 512 && f->aug_hid <= 512 &&
+                   f->augpre_hid <= 512 && f->hid == f->aug_hid && (f->D % 2) == 0 && ((f->D - f->d_in) % 2) == 0;
+    if (!dims_ok) { delete f; return FC_ERR_UNSUPPORTED; }
+    f->layers = new (std::nothrow) FcFlowLayer[f->L];
+    if (!f->layers) { delete f; return FC_ERR_MODEL; }
+
+    FcCursor c{table, n_table, 0, arena, arena_floats, true};
+    const int64_t cbits = c.next();
+    memcpy(&f->ldj_const, &cbits, sizeof(double));
+    const int attn_k2 = f->is_global ? 0 : f->inner;
+    if (!f->is_global) {
+        f->augpre = c.mlp(f->d_in, 0, f->augpre_hid, f->n_augpre_hid, f->attn_in);
+        f->augattn = read_attn(c, *f);
+    }
+    f->aug = c.mlp(f->d_in, attn_k2, f->aug_hid, f->n_aug_hid, 2 * (f->D - f->d_in));
+    f->has_cb = f->extra || f->is_global;
+    if (f->has_cb) f->cb = c.linear(f->extra + (f->is_global ? f->E : 0), 0, (f->L + 1) * f->hid);
+    for (int l = 0; l < f->L; ++l) {
+        FcFlowLayer& y = f->layers[l];
+        if (!f->is_global) {
+            y.pre = c.mlp(f->half, 0, f->pre_hid, f->n_pre_hid, f->attn_in);
+            y.attn = read_attn(c, *f);
+        }
+        y.cpl = c.mlp(f->half, attn_k2, f->hid, f->n_hid, 2 * (f->D - f->half));
+        y.has_lu = (l != f->L - 1);
+        if (y.has_lu) y.lu = c.linear(f->D, 0, f->D);
+    }
+    if (!c.ok || c.pos != n_table) { fc_flow_destroy(f); return FC_ERR_MODEL; }
+    *out = f;
+    return FC_OK;
+}
+
+extern "C" void fc_flow_destroy(fc_flow* f) {
+    if (!f) return;
+    delete[] f->layers;
+    delete f;
+}
+
+// ------------------------------------------------------------------------------------------ workspace
+namespace {
+struct FlowWs {
+    float *lat0, *lat1, *hA, *hB, *hC, *q, *o, *mu, *rstd, *cpart, *apart, *kv, *cb, *cbA;
+    int ldx, ldh, n_cpart, n_apart, cb_ld, cbA_ld;
+    int64_t total_bytes;
+};
+
+FlowWs carve_flow_ws(const fc_flow* f, int B, int N, int Nc, void* base) {
+    FlowWs w{};
+    const int64_t M = (int64_t)B * N;
+    w.ldx = fc_round_up(f->D, 4);
+    w.ldh = 512;
+    w.n_cpart = fc_gemm_n_tiles(2 * (f->D - f->half));
+    w.n_apart = fc_gemm_n_tiles(2 * (f->D - f->d_in));
+    w.cb_ld = (f->L + 1) * f->hid;
+    w.cbA_ld = fc_round_up(f->extra + (f->is_global ? f->E : 0), 4);
+    if (w.cbA_ld == 0) w.cbA_ld = 4;
+    int64_t off = 0;
+    auto take = [&](int64_t floats) { float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+                                      off += fc_round_up_ll(floats * 4, 256); return p; };
+    w.lat0 = take(M * w.ldx); w.lat1 = take(M * w.ldx);
+    w.hA = take(M * w.ldh); w.hB = take(M * w.ldh); w.hC = take(M * w.ldh);
+    w.q = take(M * 64); w.o = take(M * 64);
+    w.mu = take(M); w.rstd = take(M);
+    w.cpart = take(M * w.n_cpart); w.apart = take(M * w.n_apart);
+    w.kv = take((int64_t)B * Nc * 128);
+    w.cb = take((int64_t)B * w.cb_ld);
+    w.cbA = take((int64_t)B * w.cbA_ld);
+    w.total_bytes = off;
+    return w;
+}
+}  // namespace
+
+extern "C" int64_t fc_flow_workspace_bytes(const fc_flow* f, int B, int N, int Nc) {
+    if (!f || B <= 0 || N <= 0 || Nc <= 0) return FC_ERR_INVALID_ARG;
+    return carve_flow_ws(f, B, N, Nc, nullptr).total_bytes;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+static int run_attention_block(const fc_flow* f, const FcMlp& pre, const FcAttn& at, const float* lat, int ldx, int K_in,
+                               const float* context, int B, int N, int Nc, FlowWs& w, int precision, cudaStream_t s) {
+    const int M = B * N;
+    FcMlpIn in{lat, ldx, nullptr, 0, nullptr, 0, 0};
+    (void)K_in;
+    float* last = nullptr;
+    int rc = fc_run_mlp_hidden(pre, in, M, w.hA, w.hB, w.ldh, precision, s, &last);
+    if (rc) return rc;
+    float* h4 = (last == w.hA) ? w.hB : w.hA;
+    rc = gemm_plain(pre.out, last, w.ldh, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, h4, w.ldh, M, precision, s);
+    if (rc) return rc;
+    rc = fc_launch_ln_stats(h4, w.ldh, M, f->attn_in, 1e-5f, w.mu, w.rstd, s);
+    if (rc) return rc;
+    {
+        GemmArgs g = fc_gemm_args_zero();
+        g.A1 = h4; g.lda1 = w.ldh; g.K1 = f->attn_in; g.Wt = at.q.w; g.ldw = at.q.ldw; g.bias = at.qbias;
+        g.C = w.q; g.ldc = 64; g.M = M; g.N = f->inner; g.epi = FC_EPI_LNQ; g.row_mu = w.mu; g.row_rstd = w.rstd;
+        g.csum = at.csum; g.precision = precision;
+        rc = fc_launch_gemm(g, s);
+        if (rc) return rc;
+    }
+    rc = gemm_plain(at.kv, context, f->E, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, w.kv, 128, B * Nc,
+                    precision, s);
+    if (rc) return rc;
+    // reference models/perceiver.py:104: scale = inner_dim ** -0.5
+    const float scale = 1.0f / sqrtf((float)f->inner);
+    return fc_launch_cross_attention(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
+}
+
+extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* context, const float* extra,
+                                const float* eps, float* log_prob_out, int B, int N, int Nc, void* workspace,
+                                int64_t workspace_bytes, int precision, fc_stream_t stream_) {
+    FC_REQUIRE(f && x && context && eps && log_prob_out && B > 0 && N > 0 && Nc > 0);
+    FC_REQUIRE((f->extra != 0) == (extra != nullptr));
+    FC_REQUIRE((int64_t)B * N < (1ll << 31) && (int64_t)B * Nc < (1ll << 31));
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return FC_ERR_WORKSPACE;
+    FlowWs w = carve_flow_ws(f, B, N, Nc, workspace);
+    if (w.total_bytes > workspace_bytes) return FC_ERR_WORKSPACE;
+    const int M = B * N;
+    int rc;
+
+    // x -> latent columns [0, d_in)
+    {
+        const long long tot = (long long)M * f->d_in;
+        copy_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(x, f->d_in, w.lat0, w.ldx, M, f->d_in);
+        fc_count_launch();
+        FC_LAUNCH_OK();
+    }
+    FC_CUDA_OK(cudaMemsetAsync(w.cpart, 0, (size_t)M * w.n_cpart * sizeof(float), s));
+    // per-cloud bias of every conditioner's first layer (extra context and/or global embedding)
+    if (f->has_cb) {
+        const int tot = B * w.cbA_ld;
+        build_cb_input_kernel<<<(tot + 255) / 256, 256, 0, s>>>(extra, context, f->E, f->extra, f->is_global, B, w.cbA_ld, w.cbA);
+        fc_count_launch();
+        FC_LAUNCH_OK();
+        rc = gemm_plain(f->cb, w.cbA, w.cbA_ld, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, w.cb, w.cb_ld, B,
+                        0 /* always exact fp32: tiny */, s);
+        if (rc) return rc;
+    }
+    auto cb_ptr = [&](int slot) -> const float* { return f->has_cb ? w.cb + (size_t)slot * f->hid : nullptr; };
+
+    // ---- transforms.0: augment (reference models/augmenter.py:15-19, :49-63)
+    if (!f->is_global) {
+        rc = run_attention_block(f, f->augpre, f->augattn, w.lat0, w.ldx, f->d_in, context, B, N, Nc, w, precision, s);
+        if (rc) return rc;
+    }
+    {
+        FcMlpIn in{w.lat0, w.ldx, f->is_global ? nullptr : w.o, 64, cb_ptr(0), w.cb_ld, N};
+        if (!f->has_cb) { in.bias = nullptr; in.bias_ld = 0; in.bias_group = 0; }
+        float* last = nullptr;
+        rc = fc_run_mlp_hidden(f->aug, in, M, w.hA, w.hB, w.ldh, precision, s, &last);
+        if (rc) return rc;
+        GemmArgs g = fc_gemm_args_zero();
+        g.A1 = last; g.lda1 = w.ldh; g.K1 = f->aug_hid; g.Wt = f->aug.out.w; g.ldw = f->aug.out.ldw; g.bias = f->aug.out.b;
+        g.M = M; g.N = f->aug.out.N; g.epi = FC_EPI_AUGMENT; g.x = w.lat0; g.ldx = w.ldx; g.col0 = f->d_in;
+        g.part = w.apart; g.eps = eps; g.ld_eps = f->D - f->d_in; g.precision = precision;
+        rc = fc_launch_gemm(g, s);
+        if (rc) return rc;
+    }
+
+    // ---- coupling layers
+    float* lat = w.lat0; float* lat_next = w.lat1;
+    for (int l = 0; l < f->L; ++l) {
+        const FcFlowLayer& y = f->layers[l];
+        if (!f->is_global) {
+            rc = run_attention_block(f, y.pre, y.attn, lat, w.ldx, f->half, context, B, N, Nc, w, precision, s);
+            if (rc) return rc;
+        }
+        FcMlpIn in{lat, w.ldx, f->is_global ? nullptr : w.o, 64, cb_ptr(l + 1), w.cb_ld, N};
+        if (!f->has_cb) { in.bias = nullptr; in.bias_ld = 0; in.bias_group = 0; }
+        float* last = nullptr;
+        rc = fc_run_mlp_hidden(y.cpl, in, M, w.hA, w.hB, w.ldh, precision, s, &last);
+        if (rc) return rc;
+        {
+            GemmArgs g = fc_gemm_args_zero();
+            g.A1 = last; g.lda1 = w.ldh; g.K1 = f->hid; g.Wt = y.cpl.out.w; g.ldw = y.cpl.out.ldw; g.bias = y.cpl.out.b;
+            g.M = M; g.N = y.cpl.out.N; g.epi = FC_EPI_COUPLING; g.x = lat; g.ldx = w.ldx; g.col0 = f->half;
+            g.part = w.cpart; g.precision = precision;
+            rc = fc_launch_gemm(g, s);
+            if (rc) return rc;
+        }
+        if (y.has_lu) {
+            rc = gemm_plain(y.lu, lat, w.ldx, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, lat_next, w.ldx, M,
+                            precision, s);
+            if (rc) return rc;
+            float* t = lat; lat = lat_next; lat_next = t;
+        }
+    }
+    {
+        const int wpb = 8;
+        finalize_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, s>>>(lat, w.ldx, f->D, w.apart, w.n_apart, w.cpart, w.n_cpart,
+                                                                 M, (float)f->ldj_const, log_prob_out);
+        fc_count_launch();
+        FC_LAUNCH_OK();
+    }
+    return FC_OK;
+}

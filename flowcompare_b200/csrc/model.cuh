@@ -1,0 +1,113 @@
+// Packed-model descriptions shared by flow.cu / embed.cu / api.cu.
+// Arena format: see DESIGN.md "arena format" and flowcompare_b200/packing.py (the two walk the
+// tensors in the same order; the table is a flat list of float offsets into the arena).
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+constexpr int FC_MAX_HIDDEN = 8;
+constexpr int32_t FC_FLOW_MAGIC = 0x46435F46;  // 'FC_F'
+constexpr int32_t FC_EMB_MAGIC = 0x46435F45;   // 'FC_E'
+constexpr int32_t FC_ARENA_VERSION = 1;
+
+struct FcLinear {
+    const float* w = nullptr;  // K-major [Kp][ldw]
+    const float* b = nullptr;  // [N] or null
+    int K1 = 0, K2 = 0, N = 0, ldw = 0;
+};
+
+struct FcMlp {
+    FcLinear in;
+    FcLinear hidden[FC_MAX_HIDDEN];
+    int n_hidden = 0;
+    FcLinear out;
+};
+
+struct FcAttn {
+    const float* csum = nullptr;   // [inner] column sums of Wq*diag(gamma)
+    const float* qbias = nullptr;  // [inner] Wq*beta
+    FcLinear q;                    // K=attn_in -> inner
+    FcLinear kv;                   // K=E -> 2*inner
+};
+
+struct FcFlowLayer {
+    FcMlp pre;      // pre-attention MLP (attention configs)
+    FcAttn attn;
+    FcMlp cpl;      // coupling conditioner; in.K2 = inner for attention configs
+    FcLinear lu;    // folded ActNorm + LinearLU (absent on the last layer)
+    bool has_lu = false;
+};
+
+struct fc_flow {
+    int L, D, d_in, half, extra, is_global, E, inner, attn_in, hid, n_hid, pre_hid, n_pre_hid,
+        aug_hid, n_aug_hid, augpre_hid, n_augpre_hid;
+    double ldj_const;            // sum over layers of ActNorm + LinearLU log-dets (exact, fp64 at pack time)
+    FcMlp augpre;
+    FcAttn augattn;
+    FcMlp aug;
+    bool has_cb = false;
+    FcLinear cb;                 // per-cloud bias GEMM: K = extra + (global ? E : 0), N = (L+1)*hid
+    FcFlowLayer* layers = nullptr;
+    const float* arena = nullptr;
+    int64_t arena_floats = 0;
+};
+
+struct FcEdgeConv { FcLinear pq; int Cin, Cout; };
+
+struct fc_embedder {
+    int kind;        // 0 DGCNN per-point, 1 DGCNN global, 2 PAConv
+    int d_in, k, E, out_hid, n_out_hid;
+    FcEdgeConv ec[4];
+    FcLinear conv5;
+    FcMlp out_mlp;
+    void* paconv = nullptr;  // PAConv description (paconv.cu)
+    const float* arena = nullptr;
+    int64_t arena_floats = 0;
+};
+
+// table cursor used by the *_create functions
+struct FcCursor {
+    const int64_t* table; int n; int pos; const float* arena; int64_t arena_floats; bool ok;
+    int64_t next() { if (pos >= n) { ok = false; return -1; } return table[pos++]; }
+    const float* ptr(int64_t off, int64_t count) {
+        if (off < 0) return nullptr;
+        if (off + count > arena_floats || (off & 3)) { ok = false; return nullptr; }
+        return arena + off;
+    }
+    FcLinear linear(int K1, int K2, int N, bool has_bias = true) {
+        FcLinear l; l.K1 = K1; l.K2 = K2; l.N = N; l.ldw = fc_gemm_ldw(N);
+        const int64_t kp = fc_gemm_kpad(K1) + (K2 ? fc_gemm_kpad(K2) : 0);
+        l.w = ptr(next(), kp * l.ldw);
+        const int64_t boff = next();
+        l.b = has_bias ? ptr(boff, N) : nullptr;
+        if (!l.w || (has_bias && !l.b)) ok = false;
+        return l;
+    }
+    FcMlp mlp(int K1, int K2, int hid, int n_hidden, int N_out) {
+        FcMlp m; m.n_hidden = n_hidden;
+        if (n_hidden > FC_MAX_HIDDEN) { ok = false; return m; }
+        m.in = linear(K1, K2, hid);
+        for (int i = 0; i < n_hidden; ++i) m.hidden[i] = linear(hid, 0, hid);
+        m.out = linear(hid, 0, N_out);
+        return m;
+    }
+};
+
+// misc kernels (flow.cu)
+int fc_launch_ln_stats(const float* h, int ldh, int M, int width, float eps, float* mu, float* rstd, cudaStream_t s);
+int fc_launch_cross_attention(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
+                              int B, int N, int Nc, int d, float scale, cudaStream_t stream);
+int fc_launch_edgeconv_gather_max(const float* PQ, int ldpq, const int32_t* idx, int B, int N, int k, int Cout,
+                                  float* out, int ldo, cudaStream_t stream);
+int fc_knn_launch(const float* q, int ldq, long long q_bstride, const float* t, int ldt, long long t_bstride,
+                  int B, int Nq, int Nt, int C, int k, int mode, int32_t* idx32, int64_t* idx64,
+                  cudaStream_t stream);
+
+// runs in/hidden layers of an MLP; returns the buffer holding the last hidden activation.
+// bufA/bufB: [M][ldh] scratch (ldh >= hidden width).  `in_bias`/group override the in-layer bias.
+struct FcMlpIn {
+    const float* A1; int lda1; const float* A2; int lda2;
+    const float* bias; int bias_ld; int bias_group;  // bias == nullptr -> use the packed in-layer bias
+};
+int fc_run_mlp_hidden(const FcMlp& m, const FcMlpIn& in, int M, float* bufA, float* bufB, int ldh,
+                      int precision, cudaStream_t stream, float** last);

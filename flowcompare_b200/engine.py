@@ -1,0 +1,300 @@
+"""Host side of the drop-in: mirrors the reference's `model_dict` / `inner_loop` interface.
+
+    models_dict = initialize_flow(config, device, 'test')      # reference, unchanged
+    models_dict = load_flow(checkpoint, models_dict)            # reference, unchanged
+    engine = FlowCompareB200(models_dict, config)               # packs the state_dicts once
+    loss, log_prob, bpd = engine.inner_loop(batch)              # == inner_loop(batch, models_dict, config)
+
+or `accelerate(models_dict, config)` which returns a models_dict whose 'flow' / 'input_embedder'
+entries are adapters with the reference call signatures (`flow.log_prob(x, context=, extra_context=)`,
+`input_embedder(extract_0)`), so the reference's own `inner_loop` / `test_flow.evaluate_on_test` run
+unmodified on top of the CUDA path.
+
+PyTorch is used for device memory and streams only; every computation is a call into
+`libflowcompare_b200.so`.  There is no CPU path: tensors must live on a CUDA device (host tensors are
+copied there), and a missing library raises.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from . import packing
+from .configs import derive
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t, device):
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+class FlowCompareB200:
+    """Per-point conditional log-likelihood engine (eval mode only).
+
+    Parameters: `models` -- the reference's `models_dict` ({'flow': Flow, 'input_embedder': Module}) or a
+    pair of state_dicts `(flow_sd, embedder_sd)`; `config` -- the reference config dict (YAML values).
+    `precision`: 'fp32' (exact FFMA GEMMs) or 'tf32x3' (tcgen05 tensor cores, 3xTF32 error-compensated).
+    """
+
+    def __init__(self, models, config, device="cuda:0", precision="fp32"):
+        self.lib = _lib.load()
+        self.config = derive(config)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.FlowCompareError("flowcompare_b200 runs on CUDA devices only (no CPU fallback)")
+        self.precision = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3}[precision]
+        if isinstance(models, dict):
+            for m in (models["flow"], models["input_embedder"]):
+                if getattr(m, "training", False):
+                    raise _lib.FlowCompareError("train-mode modules (BN / ActNorm data init) are out of scope: call .eval()")
+            flow_sd, emb_sd = models["flow"].state_dict(), models["input_embedder"].state_dict()
+        else:
+            flow_sd, emb_sd = models
+        self.d_in = self.config["input_dim"]
+        self.D = self.config["latent_dim"]
+        self.E = self.config["input_embedding_dim"]
+        self.is_global = bool(self.config["global"])
+        self.has_extra = bool(self.config["using_extra_context"])
+        self.k = self.config["n_neighbors"]
+        with torch.cuda.device(self.device):
+            self._flow = self._create(packing.pack_flow(flow_sd, self.config), self.lib.fc_flow_create, "fc_flow_create")
+            self._emb = self._create(packing.pack_embedder(emb_sd, self.config), self.lib.fc_embedder_create,
+                                     "fc_embedder_create")
+        self._ws = None
+        self._seed_counter = 0
+
+    # ------------------------------------------------------------------ lifecycle
+    def _create(self, packed, create_fn, what):
+        header, table, arena = packed
+        arena_dev = arena.to(self.device)
+        handle = _lib.c_vp()
+        rc = create_fn(header.ctypes.data, len(header), table.ctypes.data, len(table), arena_dev.data_ptr(),
+                       arena_dev.numel(), handle)
+        _lib.check(rc, what)
+        return {"handle": handle, "arena": arena_dev, "header": header, "table": table}
+
+    def close(self):
+        if getattr(self, "_flow", None):
+            self.lib.fc_flow_destroy(self._flow["handle"])
+            self._flow = None
+        if getattr(self, "_emb", None):
+            self.lib.fc_embedder_destroy(self._emb["handle"])
+            self._emb = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def weight_bytes(self):
+        return 4 * (self._flow["arena"].numel() + self._emb["arena"].numel())
+
+    def _workspace(self, nbytes):
+        if nbytes < 0:
+            _lib.check(int(nbytes), "workspace query")
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        base = self._ws.data_ptr()
+        return (base + 255) // 256 * 256
+
+    # ------------------------------------------------------------------ pieces
+    def embed(self, extract_0, return_knn=False):
+        """`input_embedder(extract_0)`: [B,Nc,>=input_dim] -> [B,Nc,E] (or [B,E] for the global embedder)."""
+        with torch.cuda.device(self.device):
+            pts = _f32c(extract_0[:, :, :self.d_in], self.device)
+            B, Nc = pts.shape[0], pts.shape[1]
+            out = torch.empty((B, self.E) if self.is_global else (B, Nc, self.E), dtype=torch.float32, device=self.device)
+            idx = None
+            if return_knn:
+                idx = torch.empty((4, B, Nc, self.k), dtype=torch.int32, device=self.device)
+            nbytes = self.lib.fc_embedder_workspace_bytes(self._emb["handle"], B, Nc)
+            ws = self._workspace(nbytes)
+            rc = self.lib.fc_embed(self._emb["handle"], pts.data_ptr(), out.data_ptr(), B, Nc, _ptr(idx), ws, nbytes,
+                                   self.precision, _stream())
+            _lib.check(rc, "fc_embed")
+        return (out, idx) if return_knn else out
+
+    def draw_eps(self, B, N, seed=None):
+        """Device-side N(0,1) draw for the augmentation noise (reference: models/distributions.py:148-153)."""
+        with torch.cuda.device(self.device):
+            eps = torch.empty((B, N, self.D - self.d_in), dtype=torch.float32, device=self.device)
+            if seed is None:
+                self._seed_counter += 1
+                seed = 0x5EED0000 + self._seed_counter
+            _lib.check(self.lib.fc_fill_normal(eps.data_ptr(), eps.numel(), seed, 0, _stream()), "fc_fill_normal")
+        return eps
+
+    def log_prob(self, x, context, extra_context=None, eps=None):
+        """`Flow.log_prob(x, context=, extra_context=)` (reference models/transform.py:70-76).
+
+        x [B,N,input_dim]; context [B,Nc,E] (or [B,E] / repeated [B,N,E] for the global embedder);
+        extra_context [B], [B,1] or the repeated [B,N,1] the reference passes; eps [B,N,latent-input_dim]
+        optional (default: drawn on the device)."""
+        with torch.cuda.device(self.device):
+            x = _f32c(x[..., :self.d_in], self.device)
+            B, N = x.shape[0], x.shape[1]
+            context = context.to(self.device)
+            if self.is_global and context.dim() == 3:
+                context = context[:, 0, :]
+            context = _f32c(context, self.device)
+            Nc = 1 if self.is_global else context.shape[1]
+            extra = None
+            if self.has_extra:
+                if extra_context is None:
+                    raise _lib.FlowCompareError("this config uses extra context (extra_z_value_context) but none was given")
+                extra = extra_context.to(self.device)
+                if extra.dim() == 3:
+                    extra = extra[:, 0, :]
+                extra = _f32c(extra.reshape(B), self.device)
+            eps = self.draw_eps(B, N) if eps is None else _f32c(eps, self.device)
+            assert eps.shape == (B, N, self.D - self.d_in), eps.shape
+            out = torch.empty((B, N), dtype=torch.float32, device=self.device)
+            nbytes = self.lib.fc_flow_workspace_bytes(self._flow["handle"], B, N, Nc)
+            ws = self._workspace(nbytes)
+            rc = self.lib.fc_flow_log_prob(self._flow["handle"], x.data_ptr(), context.data_ptr(), _ptr(extra),
+                                           eps.data_ptr(), out.data_ptr(), B, N, Nc, ws, nbytes, self.precision, _stream())
+            _lib.check(rc, "fc_flow_log_prob")
+        return out
+
+    # ------------------------------------------------------------------ whole path
+    def inner_loop(self, batch, eps=None):
+        """`inner_loop(batch, models_dict, config)` (reference model_initialization.py:206-228).
+        batch = (extract_0 [B,Nc,>=6], extract_1 [B,N,>=6], extra_context [B,1] | None).
+        Returns (loss, log_prob [B,N], bpd) as CUDA tensors."""
+        e0, e1, extra = batch
+        with torch.cuda.device(self.device):
+            e0 = _f32c(e0[:, :, :self.d_in], self.device)
+            e1 = _f32c(e1[:, :, :self.d_in], self.device)
+            B, Nc, N = e0.shape[0], e0.shape[1], e1.shape[1]
+            ex = None
+            if self.has_extra:
+                if extra is None:
+                    raise _lib.FlowCompareError("this config uses extra context but batch[2] is None")
+                ex = _f32c(extra.reshape(B), self.device)
+            eps = self.draw_eps(B, N) if eps is None else _f32c(eps, self.device)
+            lp = torch.empty((B, N), dtype=torch.float32, device=self.device)
+            stats = torch.empty(2, dtype=torch.float32, device=self.device)
+            nbytes = self.lib.fc_inner_loop_workspace_bytes(self._emb["handle"], self._flow["handle"], B, N, Nc)
+            ws = self._workspace(nbytes)
+            rc = self.lib.fc_inner_loop(self._emb["handle"], self._flow["handle"], e0.data_ptr(), e1.data_ptr(), _ptr(ex),
+                                        eps.data_ptr(), lp.data_ptr(), stats.data_ptr(), B, N, Nc, ws, nbytes,
+                                        self.precision, _stream())
+            _lib.check(rc, "fc_inner_loop")
+        return stats[0], lp, stats[1]
+
+    def inner_loop_host(self, e0, e1, extra, eps, out_log_prob=None, out_stats=None):
+        """Same path through `fc_inner_loop_host`: HOST (ideally pinned) fp32 contiguous buffers in and out,
+        copies on the current stream, synchronous on return.  Used by the end-to-end benchmark."""
+        for t in (e0, e1, eps):
+            assert t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
+        assert e0.shape[2] == self.d_in and e1.shape[2] == self.d_in
+        B, Nc, N = e0.shape[0], e0.shape[1], e1.shape[1]
+        if out_log_prob is None:
+            out_log_prob = torch.empty((B, N), dtype=torch.float32).pin_memory()
+        if out_stats is None:
+            out_stats = torch.empty(2, dtype=torch.float32).pin_memory()
+        with torch.cuda.device(self.device):
+            nbytes = self.lib.fc_inner_loop_host_workspace_bytes(self._emb["handle"], self._flow["handle"], B, N, Nc)
+            ws = self._workspace(nbytes)
+            rc = self.lib.fc_inner_loop_host(self._emb["handle"], self._flow["handle"], e0.data_ptr(), e1.data_ptr(),
+                                             _ptr(extra), eps.data_ptr(), out_log_prob.data_ptr(), out_stats.data_ptr(),
+                                             B, N, Nc, ws, nbytes, self.precision, _stream())
+            _lib.check(rc, "fc_inner_loop_host")
+        return out_stats[0], out_log_prob, out_stats[1]
+
+    # ------------------------------------------------------------------ consumers
+    def log_prob_to_change(self, log_prob_1_given_0, log_prob_0_given_0, multiple, hard_cutoff=None):
+        """`log_prob_to_change` (+ `clamp_infs`), reference test_flow.py:241-275."""
+        return log_prob_to_change(log_prob_1_given_0, log_prob_0_given_0, multiple, hard_cutoff)
+
+
+# ---------------------------------------------------------------------- free functions (op level)
+def knn(x, k):
+    """`knn(x, k)` of reference models/pytorch_gcn.py:13-20: x [B,C,N] CUDA -> idx [B,N,k] int64."""
+    lib = _lib.load()
+    assert x.is_cuda
+    pts = x.transpose(2, 1).to(torch.float32).contiguous()  # [B,N,C]
+    B, N, C = pts.shape
+    idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.fc_knn_self(pts.data_ptr(), C, B, N, C, k, 0, idx.data_ptr(), _stream()), "fc_knn_self")
+    return idx
+
+
+def get_knn(samples, context_cloud, n_neighbors):
+    """`get_knn(samples, context_cloud, n_neighbors)` of reference knn.py:79-90 ('torch' flavour):
+    [Nq,D], [Nt,D] CUDA -> [Nq,k] int64, ascending distance."""
+    lib = _lib.load()
+    assert samples.is_cuda and context_cloud.is_cuda
+    q = samples.to(torch.float32).contiguous()
+    t = context_cloud.to(torch.float32).contiguous()
+    idx = torch.empty((q.shape[0], n_neighbors), dtype=torch.int64, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(lib.fc_knn_query(q.data_ptr(), t.data_ptr(), q.shape[0], t.shape[0], q.shape[1], n_neighbors,
+                                    idx.data_ptr(), _stream()), "fc_knn_query")
+    return idx
+
+
+def log_prob_to_change(log_prob_1_given_0, log_prob_0_given_0, multiple, hard_cutoff=None):
+    """`log_prob_to_change` of reference test_flow.py:249-275 on CUDA tensors [B,N] (or [N])."""
+    lib = _lib.load()
+    a, c = log_prob_1_given_0, log_prob_0_given_0
+    assert a.is_cuda and c.is_cuda
+    squeeze = a.dim() == 1
+    a2 = a.reshape(-1, a.shape[-1]).to(torch.float32).contiguous()
+    c2 = c.reshape(-1, c.shape[-1]).to(torch.float32).contiguous()
+    out = torch.empty_like(a2)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.fc_change_score(a2.data_ptr(), c2.data_ptr(), out.data_ptr(), a2.shape[0], a2.shape[1],
+                                       float(multiple), 0 if hard_cutoff is None else 1,
+                                       0.0 if hard_cutoff is None else float(hard_cutoff), _stream()), "fc_change_score")
+    return out[0] if squeeze else out.reshape(a.shape)
+
+
+# ---------------------------------------------------------------------- drop-in adapters
+class _FlowAdapter:
+    """Stands in for `models.Flow` inside a models_dict: same `log_prob` signature."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.eps = None  # set to a tensor to inject the augmentation noise (parity tests)
+
+    def log_prob(self, x, context=None, extra_context=None):
+        return self.engine.log_prob(x, context, extra_context, eps=self.eps)
+
+    def eval(self):
+        return self
+
+
+class _EmbedderAdapter:
+    def __init__(self, engine):
+        self.engine = engine
+
+    def __call__(self, extract_0):
+        return self.engine.embed(extract_0)
+
+    def eval(self):
+        return self
+
+
+def accelerate(models_dict, config, device="cuda:0", precision="fp32"):
+    """Returns a models_dict the reference's own `inner_loop(batch, models_dict, config)` accepts
+    (model_initialization.py:206-228), backed by the CUDA path."""
+    engine = FlowCompareB200(models_dict, config, device=device, precision=precision)
+    return {"parameters": models_dict.get("parameters", []), "flow": _FlowAdapter(engine),
+            "input_embedder": _EmbedderAdapter(engine), "engine": engine}
+
+
+def inner_loop(batch, models_dict, config, eps=None):
+    """Same signature as the reference's `inner_loop`; `models_dict` must come from `accelerate`."""
+    return models_dict["engine"].inner_loop(batch, eps=eps)

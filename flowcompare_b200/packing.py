@@ -1,0 +1,269 @@
+"""Packs the reference's own `state_dict`s into the device arena the C-ABI library consumes.
+
+Input: `models_dict['flow'].state_dict()` / `models_dict['input_embedder'].state_dict()` exactly as
+`load_flow` produces them (reference model_initialization.py:18-23, key layout SURVEY.md A.5) -- no
+renames, no retraining.  Output per model: (header int32[], table int64[], arena fp32[]); the C++
+side (`csrc/flow.cu: fc_flow_create`, `csrc/embed.cu: fc_embedder_create`) walks the table in the same
+order as the code below.
+
+Pack-time algebra (all in fp64, rounded once to fp32) -- mathematically identical to the reference:
+  * every Linear weight is stored K-major `Wt[Kp][ldw]` (zero padded) so GEMM B-tiles load coalesced;
+  * LayerNorm (perceiver.py:26-35) is folded into `to_q`: Wq' = Wq*diag(gamma), csum = rowsum(Wq'),
+    qbias = Wq*beta, applied in the GEMM epilogue with the per-row (mu, rstd);
+  * the attention out-projection `lin` (perceiver.py:95-96) and the concat `[x1 | extra | attn]`
+    (transform.py:49-50, affine_coupling.py:34-35) are folded into the coupling MLP's first layer:
+    W_fold = W_in[:, attn] @ W_lin, b_fold = b_in + W_in[:, attn] @ b_lin, extra/global context -> per-cloud bias;
+  * ActNorm + LinearLU (act_norm.py:37-43, permuters.py:148-169) become one matrix
+    W' = L U diag(exp(-log_scale)), b' = -W' shift, and their log-dets one fp64 constant;
+  * the last Linear of the coupling / augment nets has its rows interleaved (s_raw_j, t_j) /
+    (mean_j, log_std_j) so the elementwise epilogue sees both halves in one register tile;
+  * eval-mode BatchNorm (pytorch_gcn.py:57-77) is folded into the EdgeConv [P | Q] weights.
+"""
+import struct
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .configs import derive
+
+FLOW_MAGIC = 0x46435F46
+EMB_MAGIC = 0x46435F45
+ARENA_VERSION = 1
+
+
+def gemm_ldw(n):
+    return 64 if n <= 64 else (n + 127) // 128 * 128
+
+
+def gemm_kpad(k):
+    return (k + 15) // 16 * 16
+
+
+class Arena:
+    def __init__(self):
+        self.chunks = []
+        self.size = 0
+        self.table = []
+
+    def add(self, t):
+        """Appends a tensor (flattened, fp32) at a 64-float aligned offset; returns the offset."""
+        t = t.detach().to(torch.float32).contiguous().reshape(-1)
+        off = self.size
+        pad = (-t.numel()) % 64
+        self.chunks.append(t)
+        if pad:
+            self.chunks.append(torch.zeros(pad))
+        self.size += t.numel() + pad
+        return off
+
+    def linear(self, W, b, K1, K2=0):
+        """W [N, K1+K2] (fp64 ok), b [N] or None -> table entries (w_off, b_off)."""
+        N = W.shape[0]
+        assert W.shape[1] == K1 + K2, (W.shape, K1, K2)
+        ldw = gemm_ldw(N)
+        kp1 = gemm_kpad(K1)
+        kp = kp1 + (gemm_kpad(K2) if K2 else 0)
+        Wt = torch.zeros(kp, ldw, dtype=torch.float64)
+        Wt[:K1, :N] = W[:, :K1].t()
+        if K2:
+            Wt[kp1:kp1 + K2, :N] = W[:, K1:].t()
+        self.table.append(self.add(Wt))
+        self.table.append(self.add(b) if b is not None else -1)
+
+    def vector(self, v):
+        self.table.append(self.add(v))
+
+    def finish(self):
+        return torch.cat(self.chunks) if self.chunks else torch.zeros(0), np.asarray(self.table, dtype=np.int64)
+
+
+def _d(sd, key):
+    return sd[key].detach().to(torch.float64).cpu()
+
+
+def _mlp_tensors(sd, prefix):
+    hidden = []
+    i = 0
+    while f"{prefix}.layers.{i}.weight" in sd:
+        hidden.append((_d(sd, f"{prefix}.layers.{i}.weight"), _d(sd, f"{prefix}.layers.{i}.bias")))
+        i += 1
+    return ((_d(sd, f"{prefix}.in_layer.weight"), _d(sd, f"{prefix}.in_layer.bias")), hidden,
+            (_d(sd, f"{prefix}.out_layer.weight"), _d(sd, f"{prefix}.out_layer.bias")))
+
+
+def _pack_plain_mlp(ar, sd, prefix, in_dim):
+    (w_in, b_in), hidden, (w_out, b_out) = _mlp_tensors(sd, prefix)
+    ar.linear(w_in, b_in, in_dim)
+    for w, b in hidden:
+        assert w.shape[0] == w.shape[1] == w_in.shape[0], "hidden widths must be uniform"
+        ar.linear(w, b, w.shape[1])
+    ar.linear(w_out, b_out, w_out.shape[1])
+    return w_in.shape[0], len(hidden)
+
+
+def _pack_attn(ar, sd, prefix):
+    wq = _d(sd, f"{prefix}.fn.attention.to_q.weight")
+    wkv = _d(sd, f"{prefix}.fn.attention.to_kv.weight")
+    gamma, beta = _d(sd, f"{prefix}.norm.weight"), _d(sd, f"{prefix}.norm.bias")
+    wq_f = (wq * gamma[None, :]).to(torch.float32).to(torch.float64)  # as stored
+    ar.vector(wq_f.sum(dim=1))          # csum
+    ar.vector(wq @ beta)                # qbias
+    ar.linear(wq_f, None, wq.shape[1])
+    ar.linear(wkv, None, wkv.shape[1])
+
+
+def _interleave_rows(w, b):
+    n = w.shape[0] // 2
+    idx = torch.stack((torch.arange(n), torch.arange(n) + n), dim=1).reshape(-1)
+    return w[idx], b[idx]
+
+
+def _conditioner_first_layer(sd, mlp_prefix, attn_prefix, k_x, ex, is_global, E):
+    """Folds [x | extra | attn/emb] first layer.  Returns (W_gemm [hid, k_x(+64)], b_fold [hid],
+    w_extra [hid, ex], W_emb [hid, E] or None)."""
+    w_in, b_in = _d(sd, f"{mlp_prefix}.in_layer.weight"), _d(sd, f"{mlp_prefix}.in_layer.bias")
+    w_x = w_in[:, :k_x]
+    w_e = w_in[:, k_x:k_x + ex]
+    w_c = w_in[:, k_x + ex:]
+    if attn_prefix is not None:
+        w_lin, b_lin = _d(sd, f"{attn_prefix}.fn.lin.weight"), _d(sd, f"{attn_prefix}.fn.lin.bias")
+        b_fold = b_in + w_c @ b_lin
+        if is_global:
+            # attention over N identical keys is uniform: out = lin(W_v ctx)  
+            wkv = _d(sd, f"{attn_prefix}.fn.attention.to_kv.weight")
+            w_v = wkv[wkv.shape[0] // 2:]
+            return w_x, b_fold, w_e, w_c @ w_lin @ w_v
+        return torch.cat((w_x, w_c @ w_lin), dim=1), b_fold, w_e, None
+    assert is_global and w_c.shape[1] == E
+    return w_x, b_in, w_e, w_c
+
+
+def pack_flow(flow_sd, config):
+    cfg = derive(config)
+    from .spec import _check_supported
+    _check_supported(cfg)
+    L, D, d_in, ex = cfg["n_flow_layers"], cfg["latent_dim"], cfg["input_dim"], cfg["extra_context_dim"]
+    half = D // 2
+    is_global = bool(cfg["global"])
+    E = cfg["input_embedding_dim"]
+    inner = cfg["cross_heads"] * cfg["cross_dim_head"]
+    assert inner == 64, "only inner_dim 64 (all shipped configs) is built"
+    ar = Arena()
+    ar.table.append(0)  # placeholder for the fp64 log-det constant
+    has_cb = bool(ex) or is_global
+    cb_cols, cb_bias = [], []
+
+    def pack_conditioner(mlp_prefix, attn_prefix, k_x, out_dim):
+        w_g, b_fold, w_e, w_emb = _conditioner_first_layer(flow_sd, mlp_prefix, attn_prefix, k_x, ex, is_global, E)
+        (_, _), hidden, (w_out, b_out) = _mlp_tensors(flow_sd, mlp_prefix)
+        hid = w_g.shape[0]
+        ar.linear(w_g, b_fold, k_x, w_g.shape[1] - k_x)
+        for w, b in hidden:
+            assert w.shape[0] == w.shape[1] == hid
+            ar.linear(w, b, hid)
+        assert w_out.shape[0] == out_dim
+        w_o, b_o = _interleave_rows(w_out, b_out)
+        ar.linear(w_o, b_o, hid)
+        if has_cb:
+            rows = [w_e] if ex else []
+            if is_global:
+                rows.append(w_emb)
+            cb_cols.append(torch.cat(rows, dim=1))  # [hid, Kcb]
+            cb_bias.append(b_fold)
+        return hid, len(hidden)
+
+    # transforms.0
+    augpre_hid = n_augpre = 0
+    if not is_global:
+        augpre_hid, n_augpre = _pack_plain_mlp(ar, flow_sd, "transforms.0.pre_attn_mlp", d_in)
+        _pack_attn(ar, flow_sd, "transforms.0.attn")
+    else:
+        augpre_hid, n_augpre = cfg["hidden_dims"][0], len(cfg["hidden_dims"]) - 1
+    aug_hid, n_aug = pack_conditioner("transforms.0.augment.noise_dist.net", "transforms.0.attn", d_in, 2 * (D - d_in))
+    cb_slot = len(ar.table)
+    if has_cb:
+        ar.table.extend([0, 0])  # patched below once every layer's columns are known
+    ldj_const = 0.0
+    t = 1
+    hid = n_hid = pre_hid = n_pre = 0
+    for layer in range(L):
+        p = f"transforms.{t}"
+        if not is_global:
+            pre_hid, n_pre = _pack_plain_mlp(ar, flow_sd, f"{p}.pre_conditioner.pre_attention_mlp", half)
+            _pack_attn(ar, flow_sd, f"{p}.pre_conditioner.attn")
+        hid, n_hid = pack_conditioner(f"{p}.transform.nn", None if is_global else f"{p}.pre_conditioner.attn",
+                                      half, 2 * (D - half))
+        t += 1
+        if layer != L - 1:
+            shift, log_scale = _d(flow_sd, f"transforms.{t}.shift")[0], _d(flow_sd, f"transforms.{t}.log_scale")[0]
+            t += 1
+            lo, up = _d(flow_sd, f"transforms.{t}.lower_entries"), _d(flow_sd, f"transforms.{t}.upper_entries")
+            dg = _d(flow_sd, f"transforms.{t}.unconstrained_upper_diag")
+            Lm = torch.eye(D, dtype=torch.float64)
+            il = np.tril_indices(D, k=-1)
+            Lm[il[0], il[1]] = lo
+            Um = torch.zeros(D, D, dtype=torch.float64)
+            iu = np.triu_indices(D, k=1)
+            Um[iu[0], iu[1]] = up
+            diag = F.softplus(dg) + cfg["linear_lu_eps"]
+            Um[range(D), range(D)] = diag
+            Wp = Lm @ Um @ torch.diag(torch.exp(-log_scale))
+            ar.linear(Wp, -(Wp @ shift), D)
+            ldj_const += float((-log_scale).sum() + torch.log(diag).sum())
+            t += 1
+    if not is_global:
+        pre_hid = pre_hid or cfg["pre_attention_mlp_hidden_dims"][0]
+    if has_cb:
+        Wcb = torch.cat(cb_cols, dim=0)  # [(L+1)*hid, Kcb]
+        bcb = torch.cat(cb_bias, dim=0)
+        saved = ar.table
+        ar.table = []
+        ar.linear(Wcb, bcb, Wcb.shape[1])
+        w_off, b_off = ar.table
+        ar.table = saved
+        ar.table[cb_slot], ar.table[cb_slot + 1] = w_off, b_off
+    assert hid == aug_hid, "coupling and augment conditioners must share the hidden width"
+    ar.table[0] = struct.unpack("<q", struct.pack("<d", ldj_const))[0]
+    arena, table = ar.finish()
+    header = np.asarray([FLOW_MAGIC, ARENA_VERSION, L, D, d_in, half, ex, int(is_global), E, inner,
+                         cfg["attn_input_dim"], hid, n_hid, pre_hid or 0, n_pre, aug_hid, n_aug,
+                         augpre_hid, n_augpre], dtype=np.int32)
+    return header, table, arena
+
+
+def _bn_fold(sd, prefix):
+    w, b = _d(sd, f"{prefix}.weight"), _d(sd, f"{prefix}.bias")
+    rm, rv = _d(sd, f"{prefix}.running_mean"), _d(sd, f"{prefix}.running_var")
+    a = w / torch.sqrt(rv + 1e-5)
+    return a, b - a * rm
+
+
+def pack_embedder(emb_sd, config):
+    cfg = derive(config)
+    name = cfg["input_embedder"]
+    if name == "PAConv":
+        from .paconv_packing import pack_paconv
+        return pack_paconv(emb_sd, cfg)
+    if name not in ("DGCNNembedder", "DGCNNembedderGlobal"):
+        raise NotImplementedError(name)
+    kind = 1 if name == "DGCNNembedderGlobal" else 0
+    ar = Arena()
+    cins = [cfg["input_dim"], 64, 64, 128]
+    for i in range(4):
+        W = _d(emb_sd, f"conv{i + 1}.0.weight")[:, :, 0, 0]
+        cin = cins[i]
+        assert W.shape[1] == 2 * cin, (W.shape, cin)
+        a, b = _bn_fold(emb_sd, f"bn{i + 1}")
+        w1, w2 = W[:, :cin], W[:, cin:]
+        Wpq = torch.cat((a[:, None] * w1, a[:, None] * (w2 - w1)), dim=0)
+        bpq = torch.cat((torch.zeros_like(b), b), dim=0)
+        ar.linear(Wpq, bpq, cin)
+    W5 = _d(emb_sd, "conv5.0.weight")[:, :, 0]
+    a5, b5 = _bn_fold(emb_sd, "bn5")
+    ar.linear(a5[:, None] * W5, b5, 512)
+    out_hid, n_out = _pack_plain_mlp(ar, emb_sd, "out_mlp", 1024 if kind == 1 else 512)
+    arena, table = ar.finish()
+    header = np.asarray([EMB_MAGIC, ARENA_VERSION, kind, cfg["input_dim"], cfg["n_neighbors"],
+                         cfg["input_embedding_dim"], out_hid, n_out], dtype=np.int32)
+    return header, table, arena

@@ -1,0 +1,163 @@
+/*
+ * flowcompare_b200 -- C ABI of the B200-native per-point conditional log-likelihood path.
+ *
+ * This is the drop-in boundary for the hot path of SamGalanakis/FlowCompare
+ * (reference `model_initialization.py:206-228` `inner_loop` and everything below it).
+ * The reference's own native boundary is a set of `extern "C"` launchers taking raw device
+ * pointers, explicit int dims and a `cudaStream_t`
+ * (e.g. `models/scene_seg_PAConv/lib/pointops/src/knnquery_heap/knnquery_heap_cuda_kernel.h:10-18`),
+ * wrapped by pybind (`lib/pointops/src/pointops_api.cpp:15-40`).  The entry points below keep that
+ * convention -- caller allocates every output, plain pointers + sizes, no torch types -- but
+ *   - return an int status (0 = FC_OK, negative = error) instead of `exit(-1)`
+ *     (reference `lib/pointops/src/grouping/grouping_cuda_kernel.cu:87-91`);
+ *   - never allocate: scratch memory is passed in (`*_workspace_bytes` queries);
+ *   - launch everything on the stream passed in (several reference kernels use the legacy
+ *     default stream, e.g. `lib/pointops/src/sampling/sampling_cuda_kernel.cu:40`).
+ *
+ * All pointers are DEVICE pointers unless the name ends in `_host`.  All matrices are row-major
+ * fp32; point clouds are [B, N, C] (point-major), the layout `inner_loop` receives.
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef FLOWCOMPARE_B200_H
+#define FLOWCOMPARE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fc_stream_t; /* a cudaStream_t */
+
+#if defined(__GNUC__)
+#define FC_API __attribute__((visibility("default")))
+#else
+#define FC_API
+#endif
+
+enum {
+    FC_OK = 0,
+    FC_ERR_INVALID_ARG = -1,
+    FC_ERR_CUDA = -2,       /* a CUDA runtime call failed; see fc_last_error() */
+    FC_ERR_LAUNCH = -3,     /* a kernel launch failed; see fc_last_error() */
+    FC_ERR_WORKSPACE = -4,  /* workspace too small / misaligned */
+    FC_ERR_UNSUPPORTED = -5,
+    FC_ERR_MODEL = -6       /* model description inconsistent */
+};
+
+FC_API int fc_version(void);
+/* Human-readable description of the last error raised on this thread ("" if none). */
+FC_API const char* fc_last_error(void);
+
+/* ------------------------------------------------------------------ kNN ------------------
+ * fc_knn_self replaces `knn(x, k)` of reference models/pytorch_gcn.py:13-20 (called from
+ * get_graph_feature :27): for every point the k nearest points of the SAME cloud (self included)
+ * in ascending squared distance.  x is [B, N, ldx] with the C feature columns used starting at
+ * column 0.  Arithmetic (the "canonical form" the bit-exact oracle oracle/knn_ref.c restates):
+ *   dot_ij = fmaf chain over c = 0..C-1;  xx_i likewise;  pd_ij = ((-xx_j) - (-2*dot_ij)) - xx_i
+ * (the reference's algebraic form, fixed summation order); the k LARGEST pd are selected, ties
+ * broken by LOWER index.  idx32 [B,N,k] and idx64 [B,N,k] are both optional (NULL to skip one).
+ * Requires 1 <= k <= 64 and k <= N.                                                           */
+FC_API int fc_knn_self(const float* x, int ldx, int B, int N, int C, int k,
+                int32_t* idx32, int64_t* idx64, fc_stream_t stream);
+
+/* fc_knn_query replaces `get_knn(samples, context_cloud, n_neighbors)` / `KNN_torch_fun` of
+ * reference knn.py:40-52,79-90: queries q [Nq, D], train t [Nt, D] -> idx64 [Nq, k], ascending
+ * diss_ij = (qq_i + tt_j) - 2*dot_ij, ties by lower index.  1 <= k <= 64, k <= Nt.            */
+FC_API int fc_knn_query(const float* q, const float* t, int Nq, int Nt, int D, int k,
+                 int64_t* idx64, fc_stream_t stream);
+
+/* ------------------------------------------------------------------ GEMM (test hook) ------
+ * C[M,N] = act(A[M,K] * Wt[K,N] + bias) with the library's fp32 GEMM; `Wt` is K-major
+ * ([Kp, ldw], Kp = K rounded up to 16, rows >= K zero, ldw >= N rounded up to 128 (64 if N<=64)).
+ * act: 0 none, 1 exact-erf GELU (reference models/nets.py:19-30 with nn.GELU), 2 LeakyReLU(0.2)
+ * (reference models/pytorch_gcn.py:63-77).  precision: 0 = fp32 FFMA, 1 = 3xTF32 tcgen05.      */
+FC_API int fc_gemm(const float* A, int lda, const float* Wt, int ldw, const float* bias,
+            float* C, int ldc, int M, int N, int K, int act, int precision, fc_stream_t stream);
+
+/* ------------------------------------------------------------------ EdgeConv --------------
+ * One DGCNN EdgeConv block, reference models/pytorch_gcn.py:23-47 + :63-74 + :86-100:
+ *   out_i = max_{j in idx_i} LeakyReLU_0.2( BN_eval( W * [x_j - x_i ; x_i] ) )
+ * computed in the factorised form out_i = LeakyReLU( max_j P_j + Q_i ), P = x*(a.W1)^T,
+ * Q = x*(a.(W2-W1))^T + b  (a, b = folded eval-mode BN).
+ * PQ is [B*N, ldpq] with P in columns [0,Cout) and Q in [Cout, 2Cout) (produced by fc_gemm);
+ * idx [B,N,k] int32 local indices; out [B*N, ldo] written at column 0..Cout-1.               */
+FC_API int fc_edgeconv_gather_max(const float* PQ, int ldpq, const int32_t* idx, int B, int N, int k,
+                           int Cout, float* out, int ldo, fc_stream_t stream);
+
+/* ------------------------------------------------------------------ cross attention -------
+ * softmax(q k^T * scale) v, single head, reference models/perceiver.py:108-115.
+ * q [B*N, ldq] (dim d), kv [B*Nc, ldkv] with k in columns [0,d) and v in [d,2d); out [B*N, ldo].
+ * Only d == 64 is supported.                                                                  */
+FC_API int fc_cross_attention(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
+                       int B, int N, int Nc, int d, float scale, fc_stream_t stream);
+
+/* ------------------------------------------------------------------ model handles ---------
+ * A model is described by (header int32[], table int64[], arena fp32[] on the device), produced by
+ * flowcompare_b200/packing.py from the reference's own `state_dict`s.  The arena
+ * stays owned by the caller and must outlive the handle.  See DESIGN.md "arena format".       */
+typedef struct fc_flow fc_flow;
+typedef struct fc_embedder fc_embedder;
+
+FC_API int fc_flow_create(const int32_t* header_host, int n_header, const int64_t* table_host, int n_table,
+                   const float* arena, int64_t arena_floats, fc_flow** out);
+FC_API void fc_flow_destroy(fc_flow* h);
+FC_API int64_t fc_flow_workspace_bytes(const fc_flow* h, int B, int N, int Nc);
+/* fc_flow_log_prob replaces `Flow.log_prob(x, context, extra_context)`, reference
+ * models/transform.py:70-76, for the transform list built by model_initialization.py:134-152.
+ *   x [B,N,input_dim]; context [B,Nc,E] (attention configs) or [B,E] (global embedder);
+ *   extra [B] or NULL; eps [B,N,latent-input_dim] = the N(0,1) draw of
+ *   models/distributions.py:148-153 made explicit; log_prob_out [B,N].
+ *   precision: 0 = fp32 FFMA GEMMs, 1 = 3xTF32 tcgen05 GEMMs.                                 */
+FC_API int fc_flow_log_prob(const fc_flow* h, const float* x, const float* context, const float* extra,
+                     const float* eps, float* log_prob_out, int B, int N, int Nc,
+                     void* workspace, int64_t workspace_bytes, int precision, fc_stream_t stream);
+
+FC_API int fc_embedder_create(const int32_t* header_host, int n_header, const int64_t* table_host, int n_table,
+                       const float* arena, int64_t arena_floats, fc_embedder** out);
+FC_API void fc_embedder_destroy(fc_embedder* h);
+FC_API int64_t fc_embedder_workspace_bytes(const fc_embedder* h, int B, int Nc);
+/* fc_embed replaces `input_embedder(extract_0)`: DGCNNembedder.forward (reference
+ * models/pytorch_gcn.py:81-107) -> out [B,Nc,E]; DGCNNembedderGlobal.forward (:143-188) -> out [B,E];
+ * PointNet2SSGSeg.forward (models/scene_seg_PAConv/model/pointnet2/pointnet2_paconv_seg.py:63-82)
+ * -> out [B,Nc,E].  pts [B,Nc,input_dim].  knn_idx_out: optional int32 [4,B,Nc,k] (DGCNN only).  */
+FC_API int fc_embed(const fc_embedder* h, const float* pts, float* out, int B, int Nc,
+             int32_t* knn_idx_out, void* workspace, int64_t workspace_bytes, int precision,
+             fc_stream_t stream);
+
+/* ------------------------------------------------------------------ whole path ------------
+ * fc_inner_loop replaces `inner_loop(batch, models_dict, config)`, reference
+ * model_initialization.py:206-228: embed extract_0, score extract_1.  Device buffers.
+ * Outputs: log_prob_out [B,N]; stats_out[2] = {loss = -mean(log_prob), bpd = loss*log2(e)/input_dim}. */
+FC_API int64_t fc_inner_loop_workspace_bytes(const fc_embedder* e, const fc_flow* f, int B, int N, int Nc);
+FC_API int fc_inner_loop(const fc_embedder* e, const fc_flow* f, const float* extract_0, const float* extract_1,
+                  const float* extra, const float* eps, float* log_prob_out, float* stats_out,
+                  int B, int N, int Nc, void* workspace, int64_t workspace_bytes, int precision,
+                  fc_stream_t stream);
+/* Same call with HOST buffers (pinned or pageable): copies inputs H2D, runs, copies log_prob and
+ * stats D2H on `stream`, and synchronises the stream before returning.  This is the call the
+ * end-to-end benchmark times.  The staging area is carved from `workspace`.                    */
+FC_API int64_t fc_inner_loop_host_workspace_bytes(const fc_embedder* e, const fc_flow* f, int B, int N, int Nc);
+FC_API int fc_inner_loop_host(const fc_embedder* e, const fc_flow* f, const float* extract_0_host,
+                       const float* extract_1_host, const float* extra_host, const float* eps_host,
+                       float* log_prob_out_host, float* stats_out_host, int B, int N, int Nc,
+                       void* workspace, int64_t workspace_bytes, int precision, fc_stream_t stream);
+
+/* ------------------------------------------------------------------ consumers -------------
+ * fc_change_score replaces `log_prob_to_change` + `clamp_infs`, reference test_flow.py:241-275:
+ * per cloud, clamp +-inf to the minimum finite value, mask = lp10 < mean(lp00) - multiple*std(lp00)
+ * (unbiased std) or lp10 < hard_cutoff when use_hard_cutoff != 0, change = 1-(lp10-min)/(max-min),
+ * zero outside the mask.  lp10, lp00, change_out: [B,N].                                       */
+FC_API int fc_change_score(const float* lp10, const float* lp00, float* change_out, int B, int N,
+                    float multiple, int use_hard_cutoff, float hard_cutoff, fc_stream_t stream);
+
+/* Standard-normal fill (Philox-4x32-10 + Box-Muller) for callers that do not inject eps.      */
+FC_API int fc_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, fc_stream_t stream);
+
+/* Number of kernels this library has launched in this process since load (bench bookkeeping). */
+FC_API int64_t fc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWCOMPARE_B200_H */

@@ -1,0 +1,171 @@
+"""CPU interpreter of the packed arena (test infrastructure).
+
+Walks (header, table, arena) exactly like csrc/flow.cu / csrc/embed.cu do and evaluates the same
+sequence of fused ops with torch on the CPU.  It exists so the pack-time algebra in
+flowcompare_b200/packing.py (LayerNorm fold, attention out-projection fold, ActNorm+LinearLU fold, row
+interleaving, BatchNorm fold, per-cloud bias) can be checked against the oracle WITHOUT a GPU.  It is
+not a fallback: nothing in flowcompare_b200/ imports it.
+"""
+import math
+import struct
+
+import torch
+import torch.nn.functional as F
+
+from flowcompare_b200.packing import gemm_kpad, gemm_ldw
+
+
+class Cursor:
+    def __init__(self, table, arena):
+        self.table, self.arena, self.pos = [int(v) for v in table], arena, 0
+
+    def next(self):
+        v = self.table[self.pos]
+        self.pos += 1
+        return v
+
+    def vec(self, n):
+        off = self.next()
+        return self.arena[off:off + n]
+
+    def linear(self, K1, K2, N, has_bias=True):
+        ldw = gemm_ldw(N)
+        kp1 = gemm_kpad(K1)
+        kp = kp1 + (gemm_kpad(K2) if K2 else 0)
+        off = self.next()
+        Wt = self.arena[off:off + kp * ldw].view(kp, ldw)
+        boff = self.next()
+        b = self.arena[boff:boff + N] if has_bias else None
+        return dict(Wt=Wt, b=b, K1=K1, K2=K2, N=N, kp1=kp1)
+
+    def mlp(self, K1, K2, hid, n_hidden, N_out):
+        return dict(inp=self.linear(K1, K2, hid), hidden=[self.linear(hid, 0, hid) for _ in range(n_hidden)],
+                    out=self.linear(hid, 0, N_out))
+
+
+def lin(l, A1, A2=None, bias=None):
+    y = A1[:, :l["K1"]] @ l["Wt"][:l["K1"], :l["N"]]
+    if l["K2"]:
+        y = y + A2[:, :l["K2"]] @ l["Wt"][l["kp1"]:l["kp1"] + l["K2"], :l["N"]]
+    b = bias if bias is not None else l["b"]
+    return y + b if b is not None else y
+
+
+def mlp_hidden(m, A1, A2=None, bias=None):
+    h = F.gelu(lin(m["inp"], A1, A2, bias))
+    res = None
+    for i, l in enumerate(m["hidden"]):
+        if i % 2 == 0:
+            res, h = h, F.gelu(lin(l, h))
+        else:
+            h = F.gelu(res + lin(l, h))
+    return h
+
+
+def read_attn(c, attn_in, E, inner):
+    return dict(csum=c.vec(inner), qbias=c.vec(inner), q=c.linear(attn_in, 0, inner, False),
+                kv=c.linear(E, 0, 2 * inner, False))
+
+
+def attention_block(pre, at, lat_cols, context, B, N, inner):
+    h = mlp_hidden(pre, lat_cols)
+    h4 = lin(pre["out"], h)
+    mu = h4.mean(-1, keepdim=True)
+    rstd = torch.rsqrt(((h4 - mu) ** 2).mean(-1, keepdim=True) + 1e-5)
+    acc = h4 @ at["q"]["Wt"][:h4.shape[1], :inner]
+    q = rstd * (acc - mu * at["csum"]) + at["qbias"]
+    kv = lin(at["kv"], context.reshape(-1, context.shape[-1]))
+    q = q.view(B, N, inner)
+    kv = kv.view(B, -1, 2 * inner)
+    w = torch.softmax(q @ kv[..., :inner].transpose(1, 2) * (inner ** -0.5), dim=-1)
+    return (w @ kv[..., inner:]).reshape(B * N, inner)
+
+
+def flow_log_prob(packed, x, context, extra, eps):
+    header, table, arena = packed
+    (_, _, L, D, d_in, half, ex, is_global, E, inner, attn_in, hid, n_hid, pre_hid, n_pre, aug_hid, n_aug,
+     augpre_hid, n_augpre) = [int(v) for v in header]
+    c = Cursor(table, arena)
+    ldj_const = struct.unpack("<d", struct.pack("<q", c.next()))[0]
+    B, N = x.shape[0], x.shape[1]
+    M = B * N
+    k2 = 0 if is_global else inner
+    if not is_global:
+        augpre = c.mlp(d_in, 0, augpre_hid, n_augpre, attn_in)
+        augattn = read_attn(c, attn_in, E, inner)
+    aug = c.mlp(d_in, k2, aug_hid, n_aug, 2 * (D - d_in))
+    has_cb = bool(ex) or bool(is_global)
+    cb = None
+    if has_cb:
+        cbl = c.linear(ex + (E if is_global else 0), 0, (L + 1) * hid)
+        parts = []
+        if ex:
+            parts.append(extra.reshape(B, 1))
+        if is_global:
+            parts.append(context.reshape(B, E))
+        cb = lin(cbl, torch.cat(parts, dim=1))  # [B, (L+1)*hid]
+
+    def cloud_bias(slot):
+        if cb is None:
+            return None
+        return cb[:, slot * hid:(slot + 1) * hid].repeat_interleave(N, dim=0)
+
+    lat = torch.zeros(M, D)
+    lat[:, :d_in] = x.reshape(M, d_in)
+    o = None
+    if not is_global:
+        o = attention_block(augpre, augattn, lat, context, B, N, inner)
+    h = mlp_hidden(aug, lat, o, cloud_bias(0))
+    st = lin(aug["out"], h)
+    mean, log_std = st[:, 0::2], st[:, 1::2]
+    e = eps.reshape(M, D - d_in)
+    lat[:, d_in:] = mean + torch.exp(log_std) * e
+    logp = (0.5 * e * e + log_std + 0.5 * math.log(2 * math.pi)).sum(-1)
+    for l in range(L):
+        if not is_global:
+            pre = c.mlp(half, 0, pre_hid, n_pre, attn_in)
+            at = read_attn(c, attn_in, E, inner)
+            o = attention_block(pre, at, lat, context, B, N, inner)
+        cpl = c.mlp(half, k2, hid, n_hid, 2 * (D - half))
+        h = mlp_hidden(cpl, lat, o, cloud_bias(l + 1))
+        st = lin(cpl["out"], h)
+        s_raw, t = st[:, 0::2], st[:, 1::2]
+        s = (2 * torch.sigmoid(s_raw) - 1) + 1
+        lat = torch.cat((lat[:, :half], lat[:, half:] * s + t), dim=1)
+        logp = logp + torch.log(s).sum(-1)
+        if l != L - 1:
+            lu = c.linear(D, 0, D)
+            lat = lin(lu, lat)
+    assert c.pos == len(c.table), (c.pos, len(c.table))
+    logp = logp + ldj_const + (-0.5 * math.log(2 * math.pi) - 0.5 * lat ** 2).sum(-1)
+    return logp.view(B, N)
+
+
+def dgcnn_embed(packed, pts, knn_fn):
+    """knn_fn(x [B,N,C], k) -> idx [B,N,k] (injected so the test can use the canonical-arithmetic oracle)."""
+    header, table, arena = packed
+    _, _, kind, d_in, k, E, out_hid, n_out = [int(v) for v in header]
+    c = Cursor(table, arena)
+    B, N = pts.shape[0], pts.shape[1]
+    cin, cout = [d_in, 64, 64, 128], [64, 64, 128, 256]
+    feats = []
+    x = pts
+    idxs = []
+    for i in range(4):
+        pq = c.linear(cin[i], 0, 2 * cout[i])
+        idx = knn_fn(x, k)
+        idxs.append(idx)
+        PQ = lin(pq, x.reshape(B * N, -1)).view(B, N, 2 * cout[i])
+        P, Q = PQ[..., :cout[i]], PQ[..., cout[i]:]
+        gathered = torch.stack([P[b][idx[b]] for b in range(B)])  # [B,N,k,Cout]
+        x = F.leaky_relu(gathered.max(dim=2)[0] + Q, 0.2)
+        feats.append(x)
+    conv5 = c.linear(512, 0, 512)
+    y = F.leaky_relu(lin(conv5, torch.cat(feats, dim=-1).reshape(B * N, 512)), 0.2)
+    out_mlp = c.mlp(1024 if kind == 1 else 512, 0, out_hid, n_out, E)
+    assert c.pos == len(c.table)
+    if kind == 0:
+        return lin(out_mlp["out"], mlp_hidden(out_mlp, y)).view(B, N, E), idxs
+    y = y.view(B, N, 512)
+    pooled = torch.cat((y.max(dim=1)[0], y.mean(dim=1)), dim=1)
+    return lin(out_mlp["out"], mlp_hidden(out_mlp, pooled)), idxs

@@ -1,0 +1,160 @@
+"""CPU tests: the oracle port against the reference's golden outputs (and against the live reference
+when /root/reference is present), the kNN C oracle, and the pack-time algebra (arena interpreter)."""
+import os
+
+import pytest
+import torch
+
+from flowcompare_b200 import configs, packing, spec
+from oracle import knn_ref, port, refload
+from oracle.make_golden import FIXTURES, fixture_inputs
+from tests import arena_sim
+from tests.conftest import load_golden
+
+torch.set_grad_enabled(False)
+
+TINY = ["tiny_dgcnn_attn", "tiny_dgcnn_attn_extra", "tiny_dgcnn_global"]
+
+
+def _port_forward(name):
+    cfg, fsd, esd, batch = fixture_inputs(name)
+    dcfg = configs.derive(cfg)
+    loss, lp, bpd = port.inner_loop((batch["extract_0"], batch["extract_1"], batch["extra_context"]), fsd, esd, dcfg,
+                                    batch["eps"])
+    return cfg, fsd, esd, batch, loss, lp, bpd
+
+
+@pytest.mark.parametrize("name", TINY + ["mid_dgcnn_attn"])
+def test_port_matches_reference_golden(name):
+    """tolerance: north_star's 1e-3 nats absolute per point, 1e-4 relative on the mean."""
+    gold = load_golden(name)
+    cfg, fsd, esd, batch, loss, lp, bpd = _port_forward(name)
+    assert lp.shape == gold["log_prob"].shape
+    assert (lp - gold["log_prob"]).abs().max().item() < 1e-3
+    assert abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
+    assert abs(bpd.item() - gold["bpd"].item()) / abs(gold["bpd"].item()) < 1e-4
+
+
+def test_port_embedding_matches_golden():
+    gold = load_golden("tiny_dgcnn_attn")
+    cfg, fsd, esd, batch = fixture_inputs("tiny_dgcnn_attn")
+    emb, idxs = port.dgcnn_embed(esd, batch["extract_0"], cfg["n_neighbors"])
+    assert (emb - gold["embedding"]).abs().max().item() < 1e-5
+    assert torch.equal(idxs[0].to(torch.int32), gold["knn_idx_layer1"])
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_state_dict_layout_matches_reference():
+    models, mi = refload.load()
+    for label in ["dgcnn_attn", "dgcnn_attn_extra", "dgcnn_global"]:
+        cfg = configs.get_config(label, n_flow_layers=2)
+        md = mi.initialize_flow(dict(cfg), "cpu", "test")
+        fsd, esd = spec.random_state_dicts(cfg, seed=0)
+        rf, re_ = md["flow"].state_dict(), md["input_embedder"].state_dict()
+        assert list(rf.keys()) == list(fsd.keys())
+        assert list(re_.keys()) == list(esd.keys())
+        assert all(tuple(rf[k].shape) == tuple(fsd[k].shape) for k in rf)
+        assert all(tuple(re_[k].shape) == tuple(esd[k].shape) for k in re_)
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_port_matches_live_reference_with_reference_init():
+    """Reference's own (unperturbed) init, live forward, eps injected."""
+    from oracle.make_golden import run_reference
+    cfg = configs.get_config("dgcnn_attn_extra", n_flow_layers=2, sample_size=64, n_samples_context=80)
+    models, mi = refload.load()
+    torch.manual_seed(5)
+    md = mi.initialize_flow(dict(cfg), "cpu", "test")
+    fsd, esd = md["flow"].state_dict(), md["input_embedder"].state_dict()
+    batch = spec.synthetic_batch(cfg, 2, seed=9)
+    out = run_reference(cfg, fsd, esd, batch)
+    _, lp, _ = port.inner_loop((batch["extract_0"], batch["extract_1"], batch["extra_context"]), fsd, esd,
+                               configs.derive(cfg), batch["eps"])
+    assert (lp - out["log_prob"]).abs().max().item() < 1e-3
+
+
+# ----------------------------------------------------------------------------- kNN oracle
+def _tie_safe_mismatches(x, idx_a, idx_b, k):
+    """Rows where the neighbour SETS differ must be rounding ties: the fp64 distances of the symmetric
+    difference are equal to ~1e-6 relative."""
+    bad = 0
+    xd = x.double()
+    for b in range(x.shape[0]):
+        d = torch.cdist(xd[b], xd[b]) ** 2
+        for i in range(x.shape[1]):
+            sa, sb = set(idx_a[b, i].tolist()), set(idx_b[b, i].tolist())
+            if sa != sb:
+                da = sorted(d[i, list(sa - sb)].tolist())
+                db = sorted(d[i, list(sb - sa)].tolist())
+                if any(abs(p - q) > 1e-5 * max(1.0, abs(p)) for p, q in zip(da, db)):
+                    bad += 1
+    return bad
+
+
+@pytest.mark.parametrize("C,N", [(6, 300), (64, 257), (128, 200)])
+def test_knn_c_oracle_vs_reference_form(C, N):
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(2, N, C, generator=g)
+    k = 40
+    a = knn_ref.knn_self(x, k)
+    b = port.knn_reference_form(x.permute(0, 2, 1), k)
+    assert (a == b).float().mean().item() > 0.999
+    assert _tie_safe_mismatches(x, a, b, k) == 0
+
+
+def test_knn_c_oracle_ties_lower_index_first():
+    x = torch.rand(1, 64, 6)
+    x[0, 32:] = x[0, :32]  # exact duplicates
+    idx = knn_ref.knn_self(x, 4)
+    for i in range(32):
+        assert idx[0, i, 0].item() == i and idx[0, i, 1].item() == i + 32
+        assert idx[0, i + 32, 0].item() == i and idx[0, i + 32, 1].item() == i + 32
+
+
+def test_knn_query_oracle_vs_reference_form():
+    g = torch.Generator().manual_seed(3)
+    q, t = torch.randn(100, 3, generator=g), torch.randn(500, 3, generator=g)
+    diss = (q ** 2).sum(-1).view(-1, 1) + (t ** 2).sum(-1).view(1, -1) - 2 * q @ t.t()   # knn.py:44-49
+    ref = diss.topk(8, dim=1, largest=False).indices
+    got = knn_ref.knn_query(q, t, 8)
+    assert (got == ref).float().mean().item() > 0.995
+
+
+# ----------------------------------------------------------------------------- packing algebra
+@pytest.mark.parametrize("name", TINY)
+def test_packed_flow_algebra_matches_port(name):
+    cfg, fsd, esd, batch = fixture_inputs(name)
+    dcfg = configs.derive(cfg)
+    packed = packing.pack_flow(fsd, cfg)
+    if dcfg["global"]:
+        ctx, _ = port.dgcnn_embed_global(esd, batch["extract_0"], cfg["n_neighbors"])
+        ctx_port = ctx.unsqueeze(1).expand(-1, batch["extract_1"].shape[1], -1)
+    else:
+        ctx, _ = port.dgcnn_embed(esd, batch["extract_0"], cfg["n_neighbors"])
+        ctx_port = ctx
+    extra = batch["extra_context"]
+    ex_port = None if extra is None else extra.unsqueeze(1).expand(-1, batch["extract_1"].shape[1], -1)
+    want = port.flow_log_prob(fsd, dcfg, batch["extract_1"], ctx_port, ex_port, batch["eps"])
+    got = arena_sim.flow_log_prob(packed, batch["extract_1"], ctx, extra, batch["eps"])
+    assert (got - want).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_global"])
+def test_packed_embedder_algebra_matches_port(name):
+    cfg, fsd, esd, batch = fixture_inputs(name)
+    packed = packing.pack_embedder(esd, cfg)
+    got, idxs = arena_sim.dgcnn_embed(packed, batch["extract_0"], knn_ref.knn_self)
+    if configs.derive(cfg)["global"]:
+        want, _ = port.dgcnn_embed_global(esd, batch["extract_0"], cfg["n_neighbors"], idx_list=idxs)
+    else:
+        want, _ = port.dgcnn_embed(esd, batch["extract_0"], cfg["n_neighbors"], idx_list=idxs)
+    assert (got - want).abs().max().item() < 2e-5
+
+
+def test_change_score_port_properties():
+    g = torch.Generator().manual_seed(0)
+    lp10 = torch.randn(3, 200, generator=g) * 5 - 20
+    lp00 = torch.randn(3, 200, generator=g) - 10
+    lp10[0, 3] = float("-inf")
+    ch = port.log_prob_to_change(lp10, lp00, 1.0)
+    assert ch.min() >= 0 and ch.max() <= 1 and torch.isfinite(ch).all()
