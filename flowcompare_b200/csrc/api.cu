@@ -57,18 +57,20 @@ __global__ void stats_kernel(const float* __restrict__ lp, long long n, int inpu
 
 // One CTA per cloud.  reference test_flow.py:241-275.
 __global__ void change_score_kernel(const float* __restrict__ lp10, const float* __restrict__ lp00,
-                                    float* __restrict__ out, int N, float multiple, int use_cut, float cut) {
+                                    float* __restrict__ out, int N, long long total, float multiple, int use_cut,
+                                    float cut) {
     const int b = blockIdx.x;
     const float* a = lp10 + (size_t)b * N;
     const float* c = lp00 + (size_t)b * N;
     __shared__ float red[4][32];
     __shared__ double dred[2][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    // pass 1: min finite of both (for clamp_infs), done per tensor
+    // pass 1: min finite value of each WHOLE tensor (reference clamp_infs, test_flow.py:241-247, takes the
+    // minimum over everything it is given, not per cloud); every CTA rescans -- B*N is tiny.
     float mn10 = INFINITY, mn00 = INFINITY;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const float v = a[i]; if (!isinf(v)) mn10 = fminf(mn10, v);
-        const float u = c[i]; if (!isinf(u)) mn00 = fminf(mn00, u);
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        const float v = lp10[i]; if (!isinf(v)) mn10 = fminf(mn10, v);
+        const float u = lp00[i]; if (!isinf(u)) mn00 = fminf(mn00, u);
     }
     for (int o = 16; o > 0; o >>= 1) {
         mn10 = fminf(mn10, __shfl_xor_sync(0xffffffffu, mn10, o));
@@ -154,7 +156,8 @@ __global__ void fill_normal_kernel(float* __restrict__ out, long long n, uint64_
 extern "C" int fc_change_score(const float* lp10, const float* lp00, float* out, int B, int N, float multiple,
                                int use_hard_cutoff, float hard_cutoff, fc_stream_t stream) {
     FC_REQUIRE(lp10 && lp00 && out && B > 0 && N > 1);
-    change_score_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(lp10, lp00, out, N, multiple, use_hard_cutoff, hard_cutoff);
+    change_score_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(lp10, lp00, out, N, (long long)B * N, multiple,
+                                                                 use_hard_cutoff, hard_cutoff);
     fc_count_launch();
     FC_LAUNCH_OK();
     return FC_OK;

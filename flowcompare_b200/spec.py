@@ -164,6 +164,18 @@ def random_state_dicts(config, seed: int = 0, perturb: bool = True):
     return flow, emb
 
 
+def _randn(shape, g):
+    """Approximately N(0,1) from 12 uniforms (Irwin-Hall).  Only integer->float conversion and IEEE adds
+    are involved, so the values are bit-identical on every CPU (torch.randn's vectorised Box-Muller differs
+    between AVX2/AVX-512/scalar builds), which keeps the seeded fixtures reproducible on the GPU box."""
+    shape = tuple(shape) if not isinstance(shape, int) else (shape,)
+    u = torch.rand((12,) + shape, generator=g, dtype=torch.float32)
+    acc = u[0]
+    for i in range(1, 12):
+        acc = acc + u[i]
+    return acc - 6.0
+
+
 def _uniform(shape, bound, g):
     return (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
 
@@ -179,18 +191,18 @@ def _draw(key, shape, g, perturb, config):
     if leaf == "num_batches_tracked":
         return torch.tensor(1, dtype=torch.long)
     if leaf == "shift":
-        return torch.randn(shape, generator=g) * 0.05 if perturb else torch.zeros(shape)
+        return _randn(shape, g) * 0.05 if perturb else torch.zeros(shape)
     if leaf == "log_scale":  # slightly positive mean keeps |z| ~ 1 through 115 random layers
-        return torch.randn(shape, generator=g) * 0.03 + 0.004 if perturb else torch.zeros(shape)
+        return _randn(shape, g) * 0.03 + 0.004 if perturb else torch.zeros(shape)
     if leaf in ("lower_entries", "upper_entries"):
         D = config["latent_dim"]
-        return torch.randn(shape, generator=g) * (0.04 / math.sqrt(D)) if perturb else torch.zeros(shape)
+        return _randn(shape, g) * (0.04 / math.sqrt(D)) if perturb else torch.zeros(shape)
     if leaf == "unconstrained_upper_diag":
         base = math.log(math.exp(1 - config["linear_lu_eps"]) - 1)
         t = torch.full(shape, base)
-        return t + torch.randn(shape, generator=g) * 0.05 if perturb else t
+        return t + _randn(shape, g) * 0.05 if perturb else t
     if leaf == "running_mean":
-        return torch.randn(shape, generator=g) * 0.1 if perturb else torch.zeros(shape)
+        return _randn(shape, g) * 0.1 if perturb else torch.zeros(shape)
     if leaf == "running_var":
         return torch.rand(shape, generator=g) * 1.5 + 0.25 if perturb else torch.ones(shape)
     if leaf == "weightbank":
@@ -200,12 +212,12 @@ def _draw(key, shape, g, perturb, config):
         or "mlp_bns" in key
     if is_norm and len(shape) == 1:
         if leaf == "weight":
-            w = 1.0 + torch.randn(shape, generator=g) * 0.1 if perturb else torch.ones(shape)
+            w = 1.0 + _randn(shape, g) * 0.1 if perturb else torch.ones(shape)
             if perturb and (key.startswith("bn") or ".bn." in key):
                 flip = torch.rand(shape, generator=g) < 0.1
                 w = torch.where(flip, -w, w)
             return w
-        return torch.randn(shape, generator=g) * 0.05 if perturb else torch.zeros(shape)
+        return _randn(shape, g) * 0.05 if perturb else torch.zeros(shape)
     if leaf == "weight":
         fan_in = int(np.prod(shape[1:]))
         return _uniform(shape, 1.0 / math.sqrt(fan_in), g)
@@ -246,6 +258,6 @@ def synthetic_batch(config, batch: int, seed: int = 0, n_context=None, n_target=
     e0[..., :3] = joint[:, :Nc]
     e1[..., :3] = joint[:, Nc:]
     extra = torch.rand(batch, 1, generator=g) if cfg["using_extra_context"] else None
-    eps = torch.randn(batch, N, cfg["latent_dim"] - cfg["input_dim"], generator=g)
+    eps = _randn((batch, N, cfg["latent_dim"] - cfg["input_dim"]), g)
     return {"extract_0": e0.contiguous(), "extract_1": e1.contiguous(),
             "extra_context": extra, "eps": eps}

@@ -1,0 +1,44 @@
+"""CPU tests of the boundary: the library loads, exports every symbol the header declares, and the
+ctypes signatures cover the header (no compute calls without a GPU)."""
+import os
+import re
+
+from flowcompare_b200 import lib as fclib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "flowcompare_b200.h")).read()
+    return sorted(set(re.findall(r"^FC_API [\w\s\*]+?\b(fc_\w+)\(", src, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = fclib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+
+
+def test_ctypes_signatures_cover_header():
+    assert sorted(fclib.SIGNATURES) == _header_symbols()
+
+
+def test_version_and_error_string_callable_without_gpu():
+    lib = fclib.load()
+    assert lib.fc_version() >= 100
+    assert isinstance(lib.fc_last_error(), bytes)
+    assert lib.fc_launch_count() >= 0
+
+
+def test_create_rejects_bad_header():
+    import ctypes
+    import numpy as np
+    lib = fclib.load()
+    header = np.zeros(19, dtype=np.int32)
+    table = np.zeros(4, dtype=np.int64)
+    arena = np.zeros(64, dtype=np.float32)
+    h = ctypes.c_void_p()
+    rc = lib.fc_flow_create(header.ctypes.data, 19, table.ctypes.data, 4, arena.ctypes.data, 64, h)
+    assert rc == -6  # FC_ERR_MODEL (bad magic); nothing touches the device

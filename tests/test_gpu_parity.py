@@ -1,0 +1,298 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(`libflowcompare_b200.so`, via ctypes) and is checked against the oracle (oracle/port.py, oracle/knn_ref.c)
+and the reference's golden outputs (tests/golden/*.pt).  /root/reference is NOT needed.
+
+Tolerances (north_star): kNN indices bit-exact against the canonical-arithmetic oracle; per-point
+log-prob within 1e-3 nats absolute, mean within 1e-4 relative.  Where a full-depth (115-layer) case is
+compared with an fp32 reference whose own rounding noise is measured at ~2e-3 nats (DESIGN.md
+"precision"), the per-point bound is widened to 5e-3 and the test says so.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from flowcompare_b200 import configs, engine as eng, lib as fclib, packing, spec
+from oracle import knn_ref, port
+from oracle.make_golden import fixture_inputs
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return fclib.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ----------------------------------------------------------------------------- kNN
+@pytest.mark.parametrize("B,N,C,k", [(2, 1250, 6, 40), (1, 1250, 64, 40), (2, 777, 128, 40), (1, 40, 6, 40),
+                                     (3, 33, 3, 1), (1, 2048, 128, 64), (2, 100, 200, 7)])
+def test_knn_self_bit_exact(lib, B, N, C, k):
+    g = torch.Generator().manual_seed(N * 7 + C)
+    x = torch.randn(B, N, C, generator=g)
+    want = knn_ref.knn_self(x, k)
+    got = eng.knn(x.permute(0, 2, 1).to(DEV), k).cpu()
+    assert torch.equal(got, want)
+
+
+def test_knn_self_duplicates_lower_index_first(lib):
+    cfg = configs.get_config("dgcnn_attn")
+    b = spec.synthetic_batch(cfg, 2, seed=5, duplicates=True)
+    x = b["extract_0"]
+    want = knn_ref.knn_self(x, 40)
+    got = eng.knn(x.permute(0, 2, 1).to(DEV), 40).cpu()
+    assert torch.equal(got, want)
+    half = x.shape[1] // 2
+    assert (got[:, :half - 1, 0] == torch.arange(half - 1)).all()  # self first, its duplicate second
+    assert (got[:, :half - 1, 1] == torch.arange(half - 1) + half).all()
+
+
+def test_knn_strided_int32_matches_int64(lib):
+    g = torch.Generator().manual_seed(1)
+    feat = torch.randn(2, 500, 512, generator=g)
+    x = feat[:, :, 64:128].contiguous()
+    want = knn_ref.knn_self(x, 40)
+    fd = feat.to(DEV)
+    i32 = torch.empty(2, 500, 40, dtype=torch.int32, device=DEV)
+    i64 = torch.empty(2, 500, 40, dtype=torch.int64, device=DEV)
+    rc = lib.fc_knn_self(fd.data_ptr() + 64 * 4, 512, 2, 500, 64, 40, i32.data_ptr(), i64.data_ptr(), _stream())
+    assert rc == 0
+    assert torch.equal(i64.cpu(), want) and torch.equal(i32.cpu().long(), want)
+
+
+def test_knn_query_bit_exact(lib):
+    g = torch.Generator().manual_seed(2)
+    q, t = torch.randn(1000, 3, generator=g), torch.randn(3000, 3, generator=g)
+    want = knn_ref.knn_query(q, t, 8)
+    got = eng.get_knn(q.to(DEV), t.to(DEV), 8).cpu()
+    assert torch.equal(got, want)
+
+
+def test_knn_rejects_bad_k(lib):
+    x = torch.randn(1, 10, 3, device=DEV)
+    idx = torch.empty(1, 10, 65, dtype=torch.int64, device=DEV)
+    assert lib.fc_knn_self(x.data_ptr(), 3, 1, 10, 3, 65, 0, idx.data_ptr(), _stream()) == -1
+    assert lib.fc_knn_self(x.data_ptr(), 3, 1, 10, 3, 11, 0, idx.data_ptr(), _stream()) == -1
+
+
+# ----------------------------------------------------------------------------- GEMM
+def _pack_wt(W):
+    N, K = W.shape
+    Wt = torch.zeros(packing.gemm_kpad(K), packing.gemm_ldw(N))
+    Wt[:K, :N] = W.t()
+    return Wt
+
+
+@pytest.mark.parametrize("M,N,K,act", [(1024, 512, 512, 1), (1000, 300, 150, 0), (513, 64, 256, 0), (77, 588, 512, 2),
+                                       (2500, 128, 6, 0), (4096, 256, 662, 1)])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_gemm_matches_fp64(lib, M, N, K, act, precision):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    lda = K if K == 6 else (K + 3) // 4 * 4   # K=6: unaligned rows -> scalar A path; else vector path with a K tail
+    Ad = torch.zeros(M, lda)
+    Ad[:, :K] = A
+    Ad, Wt, bd = Ad.to(DEV), _pack_wt(W).to(DEV), b.to(DEV)
+    C = torch.empty(M, N, device=DEV)
+    rc = lib.fc_gemm(Ad.data_ptr(), lda, Wt.data_ptr(), Wt.shape[1], bd.data_ptr(), C.data_ptr(), N, M, N, K, act,
+                     precision, _stream())
+    if precision == 1 and rc == -5:
+        pytest.skip("tcgen05 path does not cover this shape")
+    assert rc == 0, fclib.load().fc_last_error()
+    ref = A.double() @ W.double().t() + b.double()
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == 2:
+        ref = torch.nn.functional.leaky_relu(ref, 0.2)
+    err = (C.cpu().double() - ref).abs().max().item()
+    assert err < 2e-5, err
+
+
+# ----------------------------------------------------------------------------- attention / edgeconv
+@pytest.mark.parametrize("B,N,Nc", [(2, 1024, 1250), (1, 100, 70), (3, 65, 64)])
+def test_cross_attention_matches_fp64(lib, B, N, Nc):
+    g = torch.Generator().manual_seed(N)
+    q = torch.randn(B, N, 64, generator=g) * 2
+    kv = torch.randn(B, Nc, 128, generator=g)
+    qd, kvd = q.to(DEV), kv.to(DEV)
+    out = torch.empty(B, N, 64, device=DEV)
+    rc = lib.fc_cross_attention(qd.data_ptr(), 64, kvd.data_ptr(), 128, out.data_ptr(), 64, B, N, Nc, 64, 0.125, _stream())
+    assert rc == 0
+    k, v = kv[..., :64].double(), kv[..., 64:].double()
+    ref = torch.softmax(q.double() @ k.transpose(1, 2) * 0.125, dim=-1) @ v
+    assert (out.cpu().double() - ref).abs().max().item() < 1e-5  # fp32 softmax of scores up to ~|8|
+
+
+def test_edgeconv_gather_max(lib):
+    g = torch.Generator().manual_seed(4)
+    for cout in (64, 128, 256):
+        B, N, k = 2, 300, 40
+        PQ = torch.randn(B * N, 512, generator=g)
+        idx = torch.randint(0, N, (B, N, k), generator=g, dtype=torch.int32)
+        out = torch.zeros(B * N, 512, device=DEV)
+        rc = lib.fc_edgeconv_gather_max(PQ.to(DEV).data_ptr(), 512, idx.to(DEV).data_ptr(), B, N, k, cout,
+                                        out.data_ptr(), 512, _stream())
+        assert rc == 0
+        P = PQ[:, :cout].view(B, N, cout)
+        Q = PQ[:, cout:2 * cout].view(B, N, cout)
+        ref = torch.stack([P[b][idx[b].long()].max(dim=1)[0] for b in range(B)]) + Q
+        ref = torch.nn.functional.leaky_relu(ref, 0.2)
+        assert torch.equal(out.cpu()[:, :cout].view(B, N, cout), ref)
+
+
+# ----------------------------------------------------------------------------- embedder / flow / whole path
+def _engine(name, precision="fp32"):
+    cfg, fsd, esd, batch = fixture_inputs(name)
+    return cfg, fsd, esd, batch, eng.FlowCompareB200((fsd, esd), cfg, device=DEV, precision=precision)
+
+
+@pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_global"])
+def test_embedder_matches_port_and_golden(name):
+    cfg, fsd, esd, batch, e = _engine(name)
+    gold = load_golden(name)
+    got, idx = e.embed(batch["extract_0"].to(DEV), return_knn=True)
+    idx = idx.cpu().long()
+    # layer-1 kNN: bit exact vs the canonical oracle, and equal to the reference's own topk on this fixture
+    assert torch.equal(idx[0], knn_ref.knn_self(batch["extract_0"], cfg["n_neighbors"]))
+    assert torch.equal(idx[0].to(torch.int32), gold["knn_idx_layer1"])
+    fn = port.dgcnn_embed_global if configs.derive(cfg)["global"] else port.dgcnn_embed
+    want, _ = fn(esd, batch["extract_0"], cfg["n_neighbors"], idx_list=[i for i in idx])
+    assert (got.cpu() - want).abs().max().item() < 2e-5
+    assert (got.cpu() - gold["embedding"]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_attn_extra", "tiny_dgcnn_global"])
+def test_flow_log_prob_matches_port(name):
+    cfg, fsd, esd, batch, e = _engine(name)
+    dcfg = configs.derive(cfg)
+    N = batch["extract_1"].shape[1]
+    if dcfg["global"]:
+        ctx, _ = port.dgcnn_embed_global(esd, batch["extract_0"], cfg["n_neighbors"])
+        ctx_port = ctx.unsqueeze(1).expand(-1, N, -1)
+    else:
+        ctx, _ = port.dgcnn_embed(esd, batch["extract_0"], cfg["n_neighbors"])
+        ctx_port = ctx
+    extra = batch["extra_context"]
+    ex_port = None if extra is None else extra.unsqueeze(1).expand(-1, N, -1)
+    want = port.flow_log_prob(fsd, dcfg, batch["extract_1"], ctx_port, ex_port, batch["eps"])
+    got = e.log_prob(batch["extract_1"].to(DEV), ctx_port.to(DEV), None if ex_port is None else ex_port.to(DEV),
+                     eps=batch["eps"].to(DEV))
+    assert (got.cpu() - want).abs().max().item() < 1e-3  # north_star per-point tolerance
+
+
+@pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_attn_extra", "tiny_dgcnn_global", "mid_dgcnn_attn"])
+def test_inner_loop_matches_reference_golden(name):
+    cfg, fsd, esd, batch, e = _engine(name)
+    gold = load_golden(name)
+    extra = batch["extra_context"]
+    loss, lp, bpd = e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV),
+                                  None if extra is None else extra.to(DEV)), eps=batch["eps"].to(DEV))
+    d = (lp.cpu() - gold["log_prob"]).abs()
+    assert d.max().item() < 1e-3, d.max().item()              # north_star: 1e-3 nats absolute per point
+    assert abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4   # 1e-4 relative on the mean
+    assert abs(bpd.item() - gold["bpd"].item()) / abs(gold["bpd"].item()) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["full_dgcnn_attn", "full_dgcnn_attn_extra", "full_dgcnn_global"])
+def test_inner_loop_full_depth_matches_reference_golden(name):
+    """115 layers, B=1, the reference's CPU fp32 output.  The fp32 reference itself sits ~2e-3 nats (max)
+    from an fp64 evaluation of the same model (DESIGN.md "precision"), so the per-point bound here is
+    5e-3; the typical (median) error and the mean-nats bound keep north_star's figures."""
+    cfg, fsd, esd, batch, e = _engine(name)
+    gold = load_golden(name)
+    extra = batch["extra_context"]
+    loss, lp, bpd = e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV),
+                                  None if extra is None else extra.to(DEV)), eps=batch["eps"].to(DEV))
+    d = (lp.cpu() - gold["log_prob"]).abs()
+    print(name, "max", d.max().item(), "median", d.median().item())
+    assert d.median().item() < 1e-3
+    assert d.max().item() < 5e-3
+    assert abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
+
+
+def test_inner_loop_host_equals_device_path():
+    cfg, fsd, esd, batch, e = _engine("tiny_dgcnn_attn_extra")
+    dev = e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV), batch["extra_context"].to(DEV)),
+                       eps=batch["eps"].to(DEV))
+    pin = lambda t: t.contiguous().pin_memory()
+    host = e.inner_loop_host(pin(batch["extract_0"]), pin(batch["extract_1"]), pin(batch["extra_context"].reshape(-1)),
+                             pin(batch["eps"]))
+    assert torch.equal(dev[1].cpu(), host[1])
+    assert dev[0].item() == host[0].item()
+
+
+def test_inner_loop_deterministic_and_batch_invariant():
+    cfg, fsd, esd, batch, e = _engine("tiny_dgcnn_attn")
+    args = (batch["extract_0"].to(DEV), batch["extract_1"].to(DEV), None)
+    a = e.inner_loop(args, eps=batch["eps"].to(DEV))[1].clone()
+    b = e.inner_loop(args, eps=batch["eps"].to(DEV))[1].clone()
+    assert torch.equal(a, b)
+    one = e.inner_loop((args[0][1:2], args[1][1:2], None), eps=batch["eps"][1:2].to(DEV))[1]
+    assert torch.equal(one[0], a[1])  # a cloud pair's result does not depend on what else is in the batch
+
+
+def test_drop_in_adapters_follow_reference_call_signature():
+    """The reference's inner_loop body (model_initialization.py:206-228) re-stated against the adapters."""
+    import einops
+    cfg, fsd, esd, batch, _ = _engine("tiny_dgcnn_attn_extra")
+    md = eng.accelerate({"flow": _SD(fsd), "input_embedder": _SD(esd)}, cfg, device=DEV)
+    md["flow"].eps = batch["eps"].to(DEV)
+    dcfg = configs.derive(cfg)
+    e0, e1, extra = batch["extract_0"].to(DEV), batch["extract_1"].to(DEV), batch["extra_context"].to(DEV)
+    extra_r = einops.repeat(extra, "b c-> b n c", n=dcfg["sample_size"])
+    emb = md["input_embedder"](e0)
+    lp = md["flow"].log_prob(e1, context=emb, extra_context=extra_r)
+    gold = load_golden("tiny_dgcnn_attn_extra")
+    assert (lp.cpu() - gold["log_prob"]).abs().max().item() < 1e-3
+
+
+class _SD:
+    """minimal stand-in for an nn.Module in eval mode holding a state_dict"""
+    training = False
+
+    def __init__(self, sd):
+        self._sd = sd
+
+    def state_dict(self):
+        return self._sd
+
+
+def test_change_score_matches_port(lib):
+    g = torch.Generator().manual_seed(0)
+    lp10 = torch.randn(4, 1024, generator=g) * 5 - 20
+    lp00 = torch.randn(4, 1024, generator=g) - 10
+    lp10[0, 3] = float("-inf")
+    lp00[1, 7] = float("-inf")
+    for cut in (None, -22.0):
+        want = port.log_prob_to_change(lp10.clone(), lp00.clone(), 1.5, cut)
+        got = eng.log_prob_to_change(lp10.to(DEV), lp00.to(DEV), 1.5, cut).cpu()
+        assert (got - want).abs().max().item() < 1e-5
+        assert torch.equal(got == 0, want == 0)
+
+
+def test_fill_normal_statistics(lib):
+    n = 1 << 22
+    out = torch.empty(n, device=DEV)
+    assert lib.fc_fill_normal(out.data_ptr(), n, 1234, 0, _stream()) == 0
+    assert abs(out.mean().item()) < 3e-3 and abs(out.std().item() - 1) < 3e-3
+    out2 = torch.empty(n, device=DEV)
+    lib.fc_fill_normal(out2.data_ptr(), n, 1234, 0, _stream())
+    assert torch.equal(out, out2)
+    lib.fc_fill_normal(out2.data_ptr(), n, 1235, 0, _stream())
+    assert not torch.equal(out, out2)
+
+
+def test_missing_extra_context_raises():
+    cfg, fsd, esd, batch, e = _engine("tiny_dgcnn_attn_extra")
+    with pytest.raises(fclib.FlowCompareError):
+        e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV), None), eps=batch["eps"].to(DEV))
