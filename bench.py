@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Headline benchmark: cloud-pairs/s for per-point log p(x | context)  (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+A "step" is one `inner_loop` pass (embed the context cloud, score the target cloud, reference
+model_initialization.py:206-228) over one batch of B synthetic cloud pairs per GPU.  Workload = BASELINE.json
+configs[1]: "summer-terrain (DGCNN Attention/Perceiver, no extra context)" = architecture `dgcnn_attn`
+(content of reference config/swept-energy.yaml): Nc=1250 context points, N=1024 target
+points, 115 coupling layers, random-init weights of that architecture, synthetic data.
+
+One JSON line is printed by rank 0.  `value` = pairs/s with inputs resident in HBM (CUDA events, max
+over ranks); `e2e` = pairs/s through `fc_inner_loop_host` with pinned HOST buffers (H2D of the clouds and
+eps, D2H of log_prob inside the timed region); `roofline` = the GEMM class (the dominant kernels) timed
+with per-launch CUDA events in one extra instrumented step; `cpu_baseline` = the oracle port on the
+host cores on a bounded sample.  Multi-GPU: pairs are sharded across ranks (weak scaling, B per rank),
+no collective on the data path, one all_gather of per-cloud mean log-prob at the end of each step.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "cloud-pairs/sec for per-point log p(x|ctx)"
+UNIT = "pairs/s"
+CLASS_NAMES = ["gemm_fp32_ffma", "gemm_tf32x3_tcgen05", "cross_attention", "knn", "edgeconv_gather_max", "other"]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="dgcnn_attn")
+    ap.add_argument("--batch", type=int, default=32, help="cloud pairs per step per GPU")
+    ap.add_argument("--precision", default=os.environ.get("FC_PRECISION", "auto"), choices=["auto", "fp32", "tf32x3"])
+    ap.add_argument("--cpu-pairs", type=int, default=6, help="pairs in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiling run: 1 warm-up, timed steps only (not a bench value)")
+    ap.add_argument("--n-context", type=int, default=None)
+    ap.add_argument("--n-target", type=int, default=None)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(cfg, pairs, seed=0):
+    """Times the oracle port (the reference algorithm restated on CPU, oracle/port.py) on the host cores.
+    /root/reference does not exist on the GPU box, so kind is "port"."""
+    from flowcompare_b200 import configs, spec
+    from oracle import port
+    torch.set_num_threads(os.cpu_count())
+    fsd, esd = spec.random_state_dicts(cfg, seed=seed)
+    dcfg = configs.derive(cfg)
+    batch = spec.synthetic_batch(cfg, 1, seed=1)
+    args = (batch["extract_0"], batch["extract_1"], batch["extra_context"])
+    with torch.no_grad():
+        port.inner_loop(args, fsd, esd, dcfg, batch["eps"])  # warm-up
+        t0 = time.perf_counter()
+        for _ in range(pairs):
+            port.inner_loop(args, fsd, esd, dcfg, batch["eps"])
+        dt = time.perf_counter() - t0
+    return pairs / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host threads, B=1 per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from flowcompare_b200 import configs, spec
+    from oracle import port
+    cfg = configs.get_config(args.config)
+    torch.set_num_threads(os.cpu_count())
+    fsd, esd = spec.random_state_dicts(cfg, seed=0)
+    dcfg = configs.derive(cfg)
+    batch = spec.synthetic_batch(cfg, 1, seed=1, n_context=args.n_context, n_target=args.n_target)
+    a = (batch["extract_0"], batch["extract_1"], batch["extra_context"])
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            port.inner_loop(a, fsd, esd, dcfg, batch["eps"])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            port.inner_loop(a, fsd, esd, dcfg, batch["eps"])
+        dt = time.perf_counter() - t0
+    v = args.steps / dt
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args, cfg, 1, "cpu"),
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"{args.steps} steps x 1 pair (Nc={batch['extract_0'].shape[1]}, N={batch['extract_1'].shape[1]}), "
+                                      "oracle/port.py = reference algorithm in torch CPU fp32 (reference tree is absent on the GPU box)"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, cfg, B, where):
+    from flowcompare_b200 import configs
+    return {"workload": configs.BASELINE_LABEL.get(args.config, args.config), "architecture": args.config,
+            "reference_yaml": configs.REFERENCE_YAML.get(args.config), "pairs_per_step_per_gpu": B,
+            "n_context": args.n_context or cfg["n_samples_context"], "n_target": args.n_target or cfg["sample_size"],
+            "n_flow_layers": cfg["n_flow_layers"], "latent_dim": cfg["latent_dim"], "sharding": "pairs across ranks",
+            "l2": "per-step working set (653 MB weights + >0.5 GB activations) exceeds the 126 MB L2; no explicit flush",
+            "where": where}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from flowcompare_b200 import configs, engine, lib, spec
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    torch.set_grad_enabled(False)
+
+    cfg = configs.get_config(args.config)
+    if args.n_target:
+        cfg["sample_size"] = args.n_target
+    B = args.batch
+    precision = args.precision
+    clib = lib.load()
+    if precision == "auto":
+        precision = "tf32x3" if os.environ.get("FC_DEFAULT_TF32X3", "0") == "1" else "fp32"
+    fsd, esd = spec.random_state_dicts(cfg, seed=0)          # same weights on every rank
+    eng = engine.FlowCompareB200((fsd, esd), cfg, device=dev, precision=precision)
+    del fsd, esd
+    batch = spec.synthetic_batch(cfg, B, seed=100 + rank, n_context=args.n_context, n_target=args.n_target)
+    Nc, N = batch["extract_0"].shape[1], batch["extract_1"].shape[1]
+    e0, e1, eps = batch["extract_0"].to(dev), batch["extract_1"].to(dev), batch["eps"].to(dev)
+    extra = None if batch["extra_context"] is None else batch["extra_context"].to(dev)
+    gathered = [torch.empty(B, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step():
+        loss, lp, bpd = eng.inner_loop((e0, e1, extra), eps=eps)
+        if world > 1:  # the one collective of the path: gather of per-cloud scalar nats
+            dist.all_gather(gathered, lp.mean(dim=1))
+        return loss, lp, bpd
+
+    for _ in range(1 if args.ncu else max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.launch_count()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        loss, lp, bpd = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * B * args.steps / (ms / 1e3)
+    if args.ncu:
+        if rank == 0:
+            print(json.dumps({"ncu_run": True, "not_a_bench_value": round(value, 2), "gpu_launches": int(launches)}), flush=True)
+        return
+
+    # ---- end to end through the C ABI with host buffers
+    pin = lambda x: x.contiguous().pin_memory()
+    h0, h1, heps = pin(batch["extract_0"]), pin(batch["extract_1"]), pin(batch["eps"])
+    hex_ = None if batch["extra_context"] is None else pin(batch["extra_context"].reshape(-1))
+    hlp, hst = torch.empty(B, N).pin_memory(), torch.empty(2).pin_memory()
+    for _ in range(2):
+        eng.inner_loop_host(h0, h1, hex_, heps, hlp, hst)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.inner_loop_host(h0, h1, hex_, heps, hlp, hst)   # synchronous: returns after the D2H copy
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / t.item()
+    h2d = 4 * (h0.numel() + h1.numel() + heps.numel() + (0 if hex_ is None else hex_.numel()))
+    d2h = 4 * (hlp.numel() + 2)
+    # e2e result must equal the device-resident result
+    same = bool(torch.equal(hlp, lp.cpu()))
+
+    # ---- one instrumented step: per-class kernel time with CUDA events around every launch
+    roofline, classes = None, None
+    if rank == 0:
+        clib.fc_profile_begin()
+        step()
+        ms_c = (ctypes.c_double * 6)(); fl_c = (ctypes.c_double * 6)(); by_c = (ctypes.c_double * 6)()
+        ln_c = (ctypes.c_int64 * 6)()
+        clib.fc_profile_end(ms_c, fl_c, by_c, ln_c, 6)
+        total_ms = sum(ms_c)
+        classes = {}
+        for i, nm in enumerate(CLASS_NAMES):
+            if ln_c[i]:
+                classes[nm] = {"launches": int(ln_c[i]), "ms": round(ms_c[i], 3), "share": round(ms_c[i] / total_ms, 4),
+                               "tflops": round(fl_c[i] / ms_c[i] / 1e9, 2), "gbs": round(by_c[i] / ms_c[i] / 1e6, 1)}
+        pk = peaks()
+        top = 1 if ln_c[1] and ms_c[1] >= ms_c[0] else 0
+        achieved = fl_c[top] / ms_c[top] / 1e9
+        roofline = {"kernel": CLASS_NAMES[top], "bound": "tensor", "achieved": round(achieved, 2),
+                    "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_sustained"], 4),
+                    "traffic": None, "peak_source": pk["source"] + ", dense bf16 sustained",
+                    "note": "achieved = algorithmic 2*M*N*K flops of every launch of the class / summed CUDA-event time "
+                            "in one instrumented step; fp32-faithful GEMMs cannot exceed TF32/3 ~ bf16/6 of this peak",
+                    "avg_launch_ms": round(ms_c[top] / max(1, ln_c[top]), 4)}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        v, dt = cpu_baseline(cfg, args.cpu_pairs)
+        cpu = {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{args.cpu_pairs} pairs (B=1 per call, Nc=1250, N=1024, same architecture and weights), {dt:.1f} s of "
+                         "oracle/port.py (reference algorithm, torch CPU fp32, all host threads)"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "tf32x3(f32-faithful)",
+               "data": "synthetic", "config": workload_config(args, cfg, B, "B200"),
+               "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "matches_device_resident_result": same},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_classes": classes,
+               "cpu_baseline": cpu, "mean_log_prob": float(lp.mean().item()), "bpd": float(bpd.item()),
+               "weights_mb": round(eng.weight_bytes() / 1e6, 1)}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream);  // gemm_tc.cu
 bool fc_gemm_tc_supported(const GemmArgs& a);
@@ -16,6 +17,42 @@ void fc_set_last_cuda_error(int code, const char* file, int line) {
     snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", code, cudaGetErrorString((cudaError_t)code), file, line);
 }
 void fc_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t a, b; };
+std::atomic<bool> g_prof_on{false};
+std::vector<ProfRec> g_prof;
+}  // namespace
+bool fc_prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void fc_prof_open(int cls, double flops, double bytes, cudaStream_t s) {
+    ProfRec r{cls, flops, bytes, nullptr, nullptr};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    g_prof.push_back(r);
+}
+void fc_prof_close(cudaStream_t s) { if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, s); }
+
+extern "C" int fc_profile_begin(void) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on.store(true);
+    return FC_OK;
+}
+extern "C" int fc_profile_end(double* ms, double* flops, double* bytes, int64_t* launches, int n_classes) {
+    g_prof_on.store(false);
+    FC_REQUIRE(ms && flops && bytes && launches && n_classes >= FC_N_CLASSES);
+    for (int i = 0; i < n_classes; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+    FC_CUDA_OK(cudaDeviceSynchronize());
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1;
+        }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return FC_OK;
+}
 
 extern "C" int fc_version(void) { return 100; }
 extern "C" const char* fc_last_error(void) { return g_err; }

@@ -157,6 +157,7 @@ int fc_launch_cross_attention(const float* q, int ldq, const float* kv, int ldkv
         configured = true;
     }
     dim3 grid((N + AQ - 1) / AQ, B);
+    FcProfScope prof(FC_CLS_ATTENTION, 4.0 * B * (double)N * Nc * d, 4.0 * B * ((double)N * d * 2 + (double)Nc * d * 2), stream);
     cross_attention_kernel<<<grid, ATHREADS, sizeof(AttnSmem), stream>>>(q, ldq, kv, ldkv, out, ldo, N, Nc, scale);
     fc_count_launch();
     FC_LAUNCH_OK();

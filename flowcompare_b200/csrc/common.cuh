@@ -42,3 +42,20 @@ __device__ __forceinline__ float fc_warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// ----------------------------------------------------------------------------- per-class event profiler
+// bench.py turns this on for ONE instrumented step: every launcher brackets its kernel with two CUDA
+// events on the launch stream; fc_profile_end() sums the elapsed time, algorithmic flops and bytes per
+// kernel class.  Off (the default) it costs one relaxed load per launch.
+enum { FC_CLS_GEMM_FFMA = 0, FC_CLS_GEMM_TC = 1, FC_CLS_ATTENTION = 2, FC_CLS_KNN = 3, FC_CLS_EDGECONV = 4,
+       FC_CLS_OTHER = 5, FC_N_CLASSES = 6 };
+bool fc_prof_enabled();
+void fc_prof_open(int cls, double flops, double bytes, cudaStream_t s);
+void fc_prof_close(cudaStream_t s);
+struct FcProfScope {
+    cudaStream_t s; bool on;
+    FcProfScope(int cls, double flops, double bytes, cudaStream_t st) : s(st), on(fc_prof_enabled()) {
+        if (on) fc_prof_open(cls, flops, bytes, s);
+    }
+    ~FcProfScope() { if (on) fc_prof_close(s); }
+};

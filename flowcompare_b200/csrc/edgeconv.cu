@@ -63,6 +63,8 @@ int fc_launch_edgeconv_gather_max(const float* PQ, int ldpq, const int32_t* idx,
     FC_REQUIRE(((reinterpret_cast<uintptr_t>(PQ) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
     const long long total = (long long)B * N;
     auto blocks = [&](int lanes) { return (unsigned)((total + (EC_THREADS / lanes) - 1) / (EC_THREADS / lanes)); };
+    FcProfScope prof(FC_CLS_EDGECONV, (double)total * k * Cout,
+                     4.0 * ((double)total * Cout * 3 + (double)total * k), stream);
     switch (Cout) {
         case 64:  edgeconv_gather_max_kernel<16><<<blocks(16), EC_THREADS, 0, stream>>>(PQ, ldpq, idx, total, N, k, Cout, out, ldo); break;
         case 128: edgeconv_gather_max_kernel<32><<<blocks(32), EC_THREADS, 0, stream>>>(PQ, ldpq, idx, total, N, k, Cout, out, ldo); break;

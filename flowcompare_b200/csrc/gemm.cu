@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_ffma_kernel(const GemmArgs a
 template <int BN>
 int launch(const GemmArgs& a, cudaStream_t stream) {
     dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
+    FcProfScope prof(FC_CLS_GEMM_FFMA, 2.0 * a.M * a.N * (a.K1 + a.K2),
+                     4.0 * ((double)a.M * (a.K1 + a.K2) + (double)a.N * (a.K1 + a.K2) + (double)a.M * a.N), stream);
     const bool vec = ((a.lda1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A1) & 15) == 0) &&
                      (a.K2 == 0 || (((a.lda2 & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A2) & 15) == 0)));
     if (vec) gemm_ffma_kernel<BN, true><<<grid, NTHREADS, 0, stream>>>(a);

@@ -169,6 +169,8 @@ int fc_knn_launch(const float* q, int ldq, long long q_bstride, const float* t, 
     FC_REQUIRE(B <= 65535);
     FC_REQUIRE(idx32 || idx64);
     dim3 grid((Nq + QT - 1) / QT, B);
+    FcProfScope prof(FC_CLS_KNN, 2.0 * B * (double)Nq * Nt * C,
+                     4.0 * B * ((double)(q == t ? Nt : Nq + Nt) * C + (double)Nq * k), stream);
     knn_kernel<<<grid, KNN_THREADS, 0, stream>>>(q, ldq, q_bstride, t, ldt, t_bstride, Nq, Nt, C, k, mode, idx32, idx64);
     fc_count_launch();
     FC_LAUNCH_OK();

@@ -42,6 +42,8 @@ SIGNATURES = {
     "fc_inner_loop_host_workspace_bytes": (c_i64, [c_vp, c_vp, c_int, c_int, c_int]),
     "fc_inner_loop_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
     "fc_change_score": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_f, c_int, c_f, c_vp]),
+    "fc_profile_begin": (c_int, []),
+    "fc_profile_end": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int]),
     "fc_fill_normal": (c_int, [c_vp, c_i64, c_u64, c_u64, c_vp]),
 }
 

@@ -154,6 +154,13 @@ FC_API int fc_change_score(const float* lp10, const float* lp00, float* change_o
 /* Standard-normal fill (Philox-4x32-10 + Box-Muller) for callers that do not inject eps.      */
 FC_API int fc_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, fc_stream_t stream);
 
+/* Per-class kernel timing for ONE instrumented step (bench.py's roofline): fc_profile_begin() makes every
+ * launcher bracket its kernel with CUDA events; fc_profile_end() synchronises the device and returns, per
+ * class (0 fp32 GEMM, 1 tcgen05 GEMM, 2 attention, 3 kNN, 4 EdgeConv gather-max, 5 other), the summed
+ * milliseconds, algorithmic flops, algorithmic bytes and launch counts.  n_classes must be >= 6.        */
+FC_API int fc_profile_begin(void);
+FC_API int fc_profile_end(double* ms, double* flops, double* bytes, int64_t* launches, int n_classes);
+
 /* Number of kernels this library has launched in this process since load (bench bookkeeping). */
 FC_API int64_t fc_launch_count(void);
 
