@@ -107,7 +107,7 @@ extern "C" int64_t fc_embedder_workspace_bytes(const fc_embedder* e, int B, int 
 static int gemm_simple(const FcLinear& l, const float* A, int lda, int act, float* C, int ldc, int M, int precision,
                        cudaStream_t s) {
     GemmArgs g = fc_gemm_args_zero();
-    g.A1 = A; g.lda1 = lda; g.K1 = l.K1; g.Wt = l.w; g.ldw = l.ldw; g.bias = l.b; g.act = act;
+    g.A1 = A; g.lda1 = lda; g.K1 = l.K1; g.Wt = l.w; g.ldw = l.ldw; g.bias = l.b; g.act = act; g.Whi = l.whi; g.Wlo = l.wlo; g.ldk = l.ldk;
     g.C = C; g.ldc = ldc; g.M = M; g.N = l.N; g.precision = precision;
     return fc_launch_gemm(g, s);
 }

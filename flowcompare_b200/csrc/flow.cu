@@ -98,7 +98,7 @@ static int gemm_plain(const FcLinear& l, const float* A1, int lda1, const float*
                       int precision, cudaStream_t stream) {
     GemmArgs g = fc_gemm_args_zero();
     g.A1 = A1; g.lda1 = lda1; g.K1 = l.K1; g.A2 = A2; g.lda2 = lda2; g.K2 = l.K2;
-    g.Wt = l.w; g.ldw = l.ldw;
+    g.Wt = l.w; g.ldw = l.ldw; g.Whi = l.whi; g.Wlo = l.wlo; g.ldk = l.ldk;
     if (bias) { g.bias = bias; g.bias_ld = bias_ld; g.bias_group = bias_group; }
     else { g.bias = l.b; }
     g.res = res; g.ldres = ldres; g.act = act; g.C = C; g.ldc = ldc; g.M = M; g.N = l.N;
@@ -179,7 +179,11 @@ extern "C" int fc_flow_create(const int32_t* header, int n_header, const int64_t
         }
         y.cpl = c.mlp(f->half, attn_k2, f->hid, f->n_hid, 2 * (f->D - f->half));
         y.has_lu = (l != f->L - 1);
-        if (y.has_lu) y.lu = c.linear(f->D, 0, f->D);
+        if (y.has_lu) {
+            y.lu = c.linear(f->D, 0, f->D);
+            y.lu_diag = c.ptr(c.next(), f->D);
+            if (!y.lu_diag) c.ok = false;
+        }
     }
     if (!c.ok || c.pos != n_table) { fc_flow_destroy(f); return FC_ERR_MODEL; }
     *out = f;
@@ -247,7 +251,7 @@ static int run_attention_block(const fc_flow* f, const FcMlp& pre, const FcAttn&
     if (rc) return rc;
     {
         GemmArgs g = fc_gemm_args_zero();
-        g.A1 = h4; g.lda1 = w.ldh; g.K1 = f->attn_in; g.Wt = at.q.w; g.ldw = at.q.ldw; g.bias = at.qbias;
+        g.A1 = h4; g.lda1 = w.ldh; g.K1 = f->attn_in; g.Wt = at.q.w; g.ldw = at.q.ldw; g.bias = at.qbias; g.Whi = at.q.whi; g.Wlo = at.q.wlo; g.ldk = at.q.ldk;
         g.C = w.q; g.ldc = 64; g.M = M; g.N = f->inner; g.epi = FC_EPI_LNQ; g.row_mu = w.mu; g.row_rstd = w.rstd;
         g.csum = at.csum; g.precision = precision;
         rc = fc_launch_gemm(g, s);
@@ -281,7 +285,10 @@ extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* c
         fc_count_launch();
         FC_LAUNCH_OK();
     }
+    // partial log-det slabs: the FFMA and tcgen05 GEMMs tile N differently (128 vs <=256 wide), so slabs a
+    // path does not write must read as zero in finalize
     FC_CUDA_OK(cudaMemsetAsync(w.cpart, 0, (size_t)M * w.n_cpart * sizeof(float), s));
+    FC_CUDA_OK(cudaMemsetAsync(w.apart, 0, (size_t)M * w.n_apart * sizeof(float), s));
     // per-cloud bias of every conditioner's first layer (extra context and/or global embedding)
     if (f->has_cb) {
         const int tot = B * w.cbA_ld;
@@ -306,7 +313,7 @@ extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* c
         rc = fc_run_mlp_hidden(f->aug, in, M, w.hA, w.hB, w.ldh, precision, s, &last);
         if (rc) return rc;
         GemmArgs g = fc_gemm_args_zero();
-        g.A1 = last; g.lda1 = w.ldh; g.K1 = f->aug_hid; g.Wt = f->aug.out.w; g.ldw = f->aug.out.ldw; g.bias = f->aug.out.b;
+        g.A1 = last; g.lda1 = w.ldh; g.K1 = f->aug_hid; g.Wt = f->aug.out.w; g.ldw = f->aug.out.ldw; g.bias = f->aug.out.b; g.Whi = f->aug.out.whi; g.Wlo = f->aug.out.wlo; g.ldk = f->aug.out.ldk;
         g.M = M; g.N = f->aug.out.N; g.epi = FC_EPI_AUGMENT; g.x = w.lat0; g.ldx = w.ldx; g.col0 = f->d_in;
         g.part = w.apart; g.eps = eps; g.ld_eps = f->D - f->d_in; g.precision = precision;
         rc = fc_launch_gemm(g, s);
@@ -328,15 +335,21 @@ extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* c
         if (rc) return rc;
         {
             GemmArgs g = fc_gemm_args_zero();
-            g.A1 = last; g.lda1 = w.ldh; g.K1 = f->hid; g.Wt = y.cpl.out.w; g.ldw = y.cpl.out.ldw; g.bias = y.cpl.out.b;
+            g.A1 = last; g.lda1 = w.ldh; g.K1 = f->hid; g.Wt = y.cpl.out.w; g.ldw = y.cpl.out.ldw; g.bias = y.cpl.out.b; g.Whi = y.cpl.out.whi; g.Wlo = y.cpl.out.wlo; g.ldk = y.cpl.out.ldk;
             g.M = M; g.N = y.cpl.out.N; g.epi = FC_EPI_COUPLING; g.x = lat; g.ldx = w.ldx; g.col0 = f->half;
             g.part = w.cpart; g.precision = precision;
             rc = fc_launch_gemm(g, s);
             if (rc) return rc;
         }
         if (y.has_lu) {
-            rc = gemm_plain(y.lu, lat, w.ldx, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, lat_next, w.ldx, M,
-                            precision, s);
+            // z' = diag.z + (W' - diag) z + b': the diagonal (~1) is applied to the fp32 latent in the epilogue,
+            // the GEMM only carries the off-diagonal mixing, so its rounding (and the tensor core's accumulate
+            // truncation) acts on the small part instead of shrinking z itself 114 times in a row.
+            GemmArgs g = fc_gemm_args_zero();
+            g.A1 = lat; g.lda1 = w.ldx; g.K1 = y.lu.K1; g.Wt = y.lu.w; g.ldw = y.lu.ldw; g.Whi = y.lu.whi; g.Wlo = y.lu.wlo;
+            g.ldk = y.lu.ldk; g.bias = y.lu.b; g.res = lat; g.ldres = w.ldx; g.res_scale = y.lu_diag;
+            g.C = lat_next; g.ldc = w.ldx; g.M = M; g.N = y.lu.N; g.precision = precision;
+            rc = fc_launch_gemm(g, s);
             if (rc) return rc;
             float* t = lat; lat = lat_next; lat_next = t;
         }

@@ -153,7 +153,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_ffma_kernel(const GemmArgs a
             if (epi == FC_EPI_STORE || epi == FC_EPI_LNQ) {
                 if (a.res) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (col + j < a.N) v[j] += a.res[(size_t)row * a.ldres + col + j];
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < a.N) {
+                            const float rv = a.res[(size_t)row * a.ldres + col + j];
+                            v[j] = a.res_scale ? fmaf(a.res_scale[col + j], rv, v[j]) : v[j] + rv;
+                        }
                 }
                 if (a.act == FC_ACT_GELU) {
 #pragma unroll

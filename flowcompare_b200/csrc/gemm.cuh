@@ -23,6 +23,7 @@ struct GemmArgs {
     // bias[n] if bias_group == 0, else bias[(row / bias_group) * bias_ld + n]  (per-cloud bias)
     const float* bias; int bias_ld; int bias_group;
     const float* res; int ldres;   // optional residual added before the activation
+    const float* res_scale;        // optional per-column factor on the residual (the LinearLU diagonal)
     int act;
     float* C; int ldc;
     int M, N;
@@ -34,16 +35,26 @@ struct GemmArgs {
     float* part;                   // [gridDim.x][M] partial log-det sums (deterministic, no atomics)
     const float* eps; int ld_eps;  // FC_EPI_AUGMENT
     int precision;                 // 0 fp32 FFMA, 1 3xTF32 tcgen05 (where available)
+    // tcgen05 path: the same weight pre-split into TF32 hi / lo parts, N-major rows, K contiguous:
+    // [n_tiles*BN][ldk] with ldk = round32(K1) + round32(K2) (zero padded); null -> FFMA only
+    const float* Whi; const float* Wlo; int ldk;
 };
+
+// tcgen05 tiling of the N dimension: n_tiles = ceil(N/128), BN = ceil(N/n_tiles) rounded up to 16.
+// BN <= 128 so that FOUR accumulators fit the 512 TMEM columns (see gemm_tc.cu: the tensor core truncates when
+// it accumulates, so the sum is spread over 3 main accumulators + 1 for the small compensation terms).
+static inline int fc_tc_n_tiles(int N) { return (N + 127) / 128; }
+static inline int fc_tc_bn(int N) { const int t = fc_tc_n_tiles(N); return fc_round_up((N + t - 1) / t, 16); }
+static inline int fc_tc_kpad(int K) { return fc_round_up(K, 32); }
 
 static inline GemmArgs fc_gemm_args_zero() {
     GemmArgs a;
     a.A1 = nullptr; a.lda1 = 0; a.K1 = 0; a.A2 = nullptr; a.lda2 = 0; a.K2 = 0;
     a.Wt = nullptr; a.ldw = 0; a.bias = nullptr; a.bias_ld = 0; a.bias_group = 0;
-    a.res = nullptr; a.ldres = 0; a.act = FC_ACT_NONE; a.C = nullptr; a.ldc = 0; a.M = 0; a.N = 0;
+    a.res = nullptr; a.ldres = 0; a.res_scale = nullptr; a.act = FC_ACT_NONE; a.C = nullptr; a.ldc = 0; a.M = 0; a.N = 0;
     a.epi = FC_EPI_STORE; a.row_mu = nullptr; a.row_rstd = nullptr; a.csum = nullptr;
     a.x = nullptr; a.ldx = 0; a.col0 = 0; a.part = nullptr; a.eps = nullptr; a.ld_eps = 0;
-    a.precision = 0;
+    a.precision = 0; a.Whi = nullptr; a.Wlo = nullptr; a.ldk = 0;
     return a;
 }
 

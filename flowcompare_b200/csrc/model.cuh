@@ -8,12 +8,13 @@
 constexpr int FC_MAX_HIDDEN = 8;
 constexpr int32_t FC_FLOW_MAGIC = 0x46435F46;  // 'FC_F'
 constexpr int32_t FC_EMB_MAGIC = 0x46435F45;   // 'FC_E'
-constexpr int32_t FC_ARENA_VERSION = 1;
+constexpr int32_t FC_ARENA_VERSION = 2;
 
 struct FcLinear {
     const float* w = nullptr;  // K-major [Kp][ldw]
     const float* b = nullptr;  // [N] or null
-    int K1 = 0, K2 = 0, N = 0, ldw = 0;
+    const float* whi = nullptr; const float* wlo = nullptr;  // tcgen05 copies [n_tiles*BN][ldk] or null
+    int K1 = 0, K2 = 0, N = 0, ldw = 0, ldk = 0;
 };
 
 struct FcMlp {
@@ -34,7 +35,8 @@ struct FcFlowLayer {
     FcMlp pre;      // pre-attention MLP (attention configs)
     FcAttn attn;
     FcMlp cpl;      // coupling conditioner; in.K2 = inner for attention configs
-    FcLinear lu;    // folded ActNorm + LinearLU (absent on the last layer)
+    FcLinear lu;    // folded ActNorm + LinearLU minus its diagonal (absent on the last layer)
+    const float* lu_diag = nullptr;  // [D] the diagonal, applied to the latent in the GEMM epilogue
     bool has_lu = false;
 };
 
@@ -81,6 +83,13 @@ struct FcCursor {
         const int64_t boff = next();
         l.b = has_bias ? ptr(boff, N) : nullptr;
         if (!l.w || (has_bias && !l.b)) ok = false;
+        const int64_t hoff = next(), loff = next();
+        if (hoff >= 0 && loff >= 0) {
+            l.ldk = fc_tc_kpad(K1) + (K2 ? fc_tc_kpad(K2) : 0);
+            const int64_t cnt = (int64_t)fc_tc_n_tiles(N) * fc_tc_bn(N) * l.ldk;
+            l.whi = ptr(hoff, cnt); l.wlo = ptr(loff, cnt);
+            if (!l.whi || !l.wlo) ok = false;
+        }
         return l;
     }
     FcMlp mlp(int K1, int K2, int hid, int n_hidden, int N_out) {

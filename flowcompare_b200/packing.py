@@ -29,7 +29,7 @@ from .configs import derive
 
 FLOW_MAGIC = 0x46435F46
 EMB_MAGIC = 0x46435F45
-ARENA_VERSION = 1
+ARENA_VERSION = 2
 
 
 def gemm_ldw(n):
@@ -38,6 +38,27 @@ def gemm_ldw(n):
 
 def gemm_kpad(k):
     return (k + 15) // 16 * 16
+
+
+# tcgen05 tiling (mirrors csrc/gemm.cuh fc_tc_*)
+def tc_n_tiles(n):
+    return (n + 127) // 128
+
+
+def tc_bn(n):
+    t = tc_n_tiles(n)
+    return ((n + t - 1) // t + 15) // 16 * 16
+
+
+def tc_kpad(k):
+    return (k + 31) // 32 * 32
+
+
+def tf32_round(x):
+    """Round-to-nearest (ties away, like cvt.rna.tf32.f32) of fp32 to the 10-bit-mantissa TF32 grid."""
+    i = x.contiguous().view(torch.int32)
+    r = (i + 0x1000) & ~0x1FFF
+    return r.view(torch.float32)
 
 
 class Arena:
@@ -57,8 +78,12 @@ class Arena:
         self.size += t.numel() + pad
         return off
 
-    def linear(self, W, b, K1, K2=0):
-        """W [N, K1+K2] (fp64 ok), b [N] or None -> table entries (w_off, b_off)."""
+    def linear(self, W, b, K1, K2=0, tc=True):
+        """W [N, K1+K2] (fp64 ok), b [N] or None -> table entries (w_off, b_off, whi_off, wlo_off).
+
+        w: K-major fp32 copy for the FFMA kernel.  whi/wlo (tc=True): the same weight rounded to fp32 and
+        split into TF32 hi / lo parts, [n_tiles*BN][ldk] N-major (the layout tcgen05 K-major operands and
+        their TMA boxes want), for the 3xTF32 tensor-core kernel (csrc/gemm_tc.cu)."""
         N = W.shape[0]
         assert W.shape[1] == K1 + K2, (W.shape, K1, K2)
         ldw = gemm_ldw(N)
@@ -70,6 +95,20 @@ class Arena:
             Wt[kp1:kp1 + K2, :N] = W[:, K1:].t()
         self.table.append(self.add(Wt))
         self.table.append(self.add(b) if b is not None else -1)
+        if not tc or N < 16:
+            self.table.extend([-1, -1])
+            return
+        t1 = tc_kpad(K1)
+        ldk = t1 + (tc_kpad(K2) if K2 else 0)
+        rows = tc_n_tiles(N) * tc_bn(N)
+        W32 = torch.zeros(rows, ldk, dtype=torch.float32)
+        W32[:N, :K1] = W[:, :K1].to(torch.float32)
+        if K2:
+            W32[:N, t1:t1 + K2] = W[:, K1:].to(torch.float32)
+        hi = tf32_round(W32)
+        lo = tf32_round(W32 - hi)
+        self.table.append(self.add(hi))
+        self.table.append(self.add(lo))
 
     def vector(self, v):
         self.table.append(self.add(v))
@@ -183,7 +222,7 @@ def pack_flow(flow_sd, config):
     aug_hid, n_aug = pack_conditioner("transforms.0.augment.noise_dist.net", "transforms.0.attn", d_in, 2 * (D - d_in))
     cb_slot = len(ar.table)
     if has_cb:
-        ar.table.extend([0, 0])  # patched below once every layer's columns are known
+        ar.table.extend([0, 0, -1, -1])  # (w, b, whi, wlo): w/b patched below once every layer's columns are known
     ldj_const = 0.0
     t = 1
     hid = n_hid = pre_hid = n_pre = 0
@@ -209,7 +248,9 @@ def pack_flow(flow_sd, config):
             diag = F.softplus(dg) + cfg["linear_lu_eps"]
             Um[range(D), range(D)] = diag
             Wp = Lm @ Um @ torch.diag(torch.exp(-log_scale))
-            ar.linear(Wp, -(Wp @ shift), D)
+            wdiag = torch.diagonal(Wp).clone()
+            ar.linear(Wp - torch.diag(wdiag), -(Wp @ shift), D)   # off-diagonal part in the GEMM ...
+            ar.vector(wdiag)                                      # ... the diagonal in its epilogue (fp32, exact input)
             ldj_const += float((-log_scale).sum() + torch.log(diag).sum())
             t += 1
     if not is_global:
@@ -219,8 +260,8 @@ def pack_flow(flow_sd, config):
         bcb = torch.cat(cb_bias, dim=0)
         saved = ar.table
         ar.table = []
-        ar.linear(Wcb, bcb, Wcb.shape[1])
-        w_off, b_off = ar.table
+        ar.linear(Wcb, bcb, Wcb.shape[1], tc=False)   # B rows only: always the exact fp32 kernel
+        w_off, b_off = ar.table[:2]
         ar.table = saved
         ar.table[cb_slot], ar.table[cb_slot + 1] = w_off, b_off
     assert hid == aug_hid, "coupling and augment conditioners must share the hidden width"
@@ -258,7 +299,7 @@ def pack_embedder(emb_sd, config):
         w1, w2 = W[:, :cin], W[:, cin:]
         Wpq = torch.cat((a[:, None] * w1, a[:, None] * (w2 - w1)), dim=0)
         bpq = torch.cat((torch.zeros_like(b), b), dim=0)
-        ar.linear(Wpq, bpq, cin)
+        ar.linear(Wpq, bpq, cin, tc=False)   # feeds the bit-exact kNN of the next block: exact fp32 only
     W5 = _d(emb_sd, "conv5.0.weight")[:, :, 0]
     a5, b5 = _bn_fold(emb_sd, "bn5")
     ar.linear(a5[:, None] * W5, b5, 512)

@@ -36,14 +36,46 @@ class Cursor:
         Wt = self.arena[off:off + kp * ldw].view(kp, ldw)
         boff = self.next()
         b = self.arena[boff:boff + N] if has_bias else None
-        return dict(Wt=Wt, b=b, K1=K1, K2=K2, N=N, kp1=kp1)
+        hoff, loff = self.next(), self.next()
+        tc = None
+        if hoff >= 0:
+            # tcgen05 copies: hi + lo must reproduce the fp32 weight (to ~2^-22), in [rows][ldk] layout
+            from flowcompare_b200.packing import tc_bn, tc_kpad, tc_n_tiles
+            t1 = tc_kpad(K1)
+            ldk = t1 + (tc_kpad(K2) if K2 else 0)
+            rows = tc_n_tiles(N) * tc_bn(N)
+            hi = self.arena[hoff:hoff + rows * ldk].view(rows, ldk)
+            lo = self.arena[loff:loff + rows * ldk].view(rows, ldk)
+            tc = dict(hi=hi, lo=lo, t1=t1, ldk=ldk)
+        return dict(Wt=Wt, b=b, K1=K1, K2=K2, N=N, kp1=kp1, tc=tc)
 
     def mlp(self, K1, K2, hid, n_hidden, N_out):
         return dict(inp=self.linear(K1, K2, hid), hidden=[self.linear(hid, 0, hid) for _ in range(n_hidden)],
                     out=self.linear(hid, 0, N_out))
 
 
+USE_TC = False   # True: evaluate every linear that has tcgen05 copies the way csrc/gemm_tc.cu does (3xTF32)
+
+
+def _lin_3xtf32(l, A1, A2):
+    from flowcompare_b200.packing import tf32_round
+    tc = l["tc"]
+    A = torch.zeros(A1.shape[0], tc["ldk"])
+    A[:, :l["K1"]] = A1[:, :l["K1"]]
+    if l["K2"]:
+        A[:, tc["t1"]:tc["t1"] + l["K2"]] = A2[:, :l["K2"]]
+    a_hi = tf32_round(A)
+    a_lo = tf32_round(A - a_hi)
+    whi, wlo = tc["hi"].double(), tc["lo"].double()
+    y = a_lo.double() @ whi.t() + a_hi.double() @ wlo.t() + a_hi.double() @ whi.t()
+    return y[:, :l["N"]].float()
+
+
 def lin(l, A1, A2=None, bias=None):
+    if USE_TC and l["tc"] is not None:
+        y = _lin_3xtf32(l, A1, A2)
+        b = bias if bias is not None else l["b"]
+        return y + b if b is not None else y
     y = A1[:, :l["K1"]] @ l["Wt"][:l["K1"], :l["N"]]
     if l["K2"]:
         y = y + A2[:, :l["K2"]] @ l["Wt"][l["kp1"]:l["kp1"] + l["K2"], :l["N"]]
@@ -72,7 +104,7 @@ def attention_block(pre, at, lat_cols, context, B, N, inner):
     h4 = lin(pre["out"], h)
     mu = h4.mean(-1, keepdim=True)
     rstd = torch.rsqrt(((h4 - mu) ** 2).mean(-1, keepdim=True) + 1e-5)
-    acc = h4 @ at["q"]["Wt"][:h4.shape[1], :inner]
+    acc = lin(at["q"], h4)
     q = rstd * (acc - mu * at["csum"]) + at["qbias"]
     kv = lin(at["kv"], context.reshape(-1, context.shape[-1]))
     q = q.view(B, N, inner)
@@ -135,7 +167,7 @@ def flow_log_prob(packed, x, context, extra, eps):
         logp = logp + torch.log(s).sum(-1)
         if l != L - 1:
             lu = c.linear(D, 0, D)
-            lat = lin(lu, lat)
+            lat = lin(lu, lat) + c.vec(D) * lat
     assert c.pos == len(c.table), (c.pos, len(c.table))
     logp = logp + ldj_const + (-0.5 * math.log(2 * math.pi) - 0.5 * lat ** 2).sum(-1)
     return logp.view(B, N)

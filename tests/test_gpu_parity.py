@@ -104,11 +104,21 @@ def test_gemm_matches_fp64(lib, M, N, K, act, precision):
     Ad[:, :K] = A
     Ad, Wt, bd = Ad.to(DEV), _pack_wt(W).to(DEV), b.to(DEV)
     C = torch.empty(M, N, device=DEV)
-    rc = lib.fc_gemm(Ad.data_ptr(), lda, Wt.data_ptr(), Wt.shape[1], bd.data_ptr(), C.data_ptr(), N, M, N, K, act,
-                     precision, _stream())
+    if precision == 0:
+        rc = lib.fc_gemm(Ad.data_ptr(), lda, Wt.data_ptr(), Wt.shape[1], bd.data_ptr(), C.data_ptr(), N, M, N, K, act,
+                         0, _stream())
+    else:
+        rows, ldk = packing.tc_n_tiles(N) * packing.tc_bn(N), packing.tc_kpad(K)
+        W32 = torch.zeros(rows, ldk)
+        W32[:N, :K] = W
+        hi = packing.tf32_round(W32)
+        lo = packing.tf32_round(W32 - hi)
+        hi, lo = hi.to(DEV), lo.to(DEV)
+        rc = lib.fc_gemm_tf32x3(Ad.data_ptr(), lda, hi.data_ptr(), lo.data_ptr(), ldk, bd.data_ptr(), C.data_ptr(), N, M, N,
+                                K, act, _stream())
     if precision == 1 and rc == -5:
         pytest.skip("tcgen05 path does not cover this shape")
-    assert rc == 0, fclib.load().fc_last_error()
+    assert rc == 0, (rc, fclib.load().fc_last_error())
     ref = A.double() @ W.double().t() + b.double()
     if act == 1:
         ref = torch.nn.functional.gelu(ref)
@@ -217,6 +227,24 @@ def test_inner_loop_full_depth_matches_reference_golden(name):
     print(name, "max", d.max().item(), "median", d.median().item())
     assert d.median().item() < 1e-3
     assert d.max().item() < 5e-3
+    assert abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_attn_extra", "tiny_dgcnn_global", "mid_dgcnn_attn",
+                                  "full_dgcnn_attn", "full_dgcnn_attn_extra", "full_dgcnn_global"])
+def test_inner_loop_tf32x3_tensor_core_path_matches_reference_golden(name):
+    """Same goldens through the tcgen05 3xTF32 GEMMs (precision='tf32x3')."""
+    cfg, fsd, esd, batch, e = _engine(name, precision="tf32x3")
+    gold = load_golden(name)
+    extra = batch["extra_context"]
+    n0 = fclib.launch_count()
+    loss, lp, bpd = e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV),
+                                  None if extra is None else extra.to(DEV)), eps=batch["eps"].to(DEV))
+    d = (lp.cpu() - gold["log_prob"]).abs()
+    print(name, "tf32x3 max", d.max().item(), "median", d.median().item())
+    full = name.startswith("full")
+    assert d.median().item() < 1e-3
+    assert d.max().item() < (5e-3 if full else 1e-3)   # full depth: see the fp32-noise note above
     assert abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
 
 

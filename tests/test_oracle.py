@@ -139,6 +139,25 @@ def test_packed_flow_algebra_matches_port(name):
     assert (got - want).abs().max().item() < 1e-3
 
 
+def test_packed_tf32x3_copies_match_port():
+    """The TF32 hi/lo weight copies + a 3xTF32 evaluation of every GEMM (what csrc/gemm_tc.cu computes)
+    stay within north_star's 1e-3 nats of the fp32 oracle."""
+    name = "tiny_dgcnn_attn_extra"
+    cfg, fsd, esd, batch = fixture_inputs(name)
+    dcfg = configs.derive(cfg)
+    packed = packing.pack_flow(fsd, cfg)
+    ctx, _ = port.dgcnn_embed(esd, batch["extract_0"], cfg["n_neighbors"])
+    extra = batch["extra_context"]
+    ex_port = extra.unsqueeze(1).expand(-1, batch["extract_1"].shape[1], -1)
+    want = port.flow_log_prob(fsd, dcfg, batch["extract_1"], ctx, ex_port, batch["eps"])
+    arena_sim.USE_TC = True
+    try:
+        got = arena_sim.flow_log_prob(packed, batch["extract_1"], ctx, extra, batch["eps"])
+    finally:
+        arena_sim.USE_TC = False
+    assert (got - want).abs().max().item() < 1e-3
+
+
 @pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_global"])
 def test_packed_embedder_algebra_matches_port(name):
     cfg, fsd, esd, batch = fixture_inputs(name)
