@@ -2,47 +2,50 @@
 // operands staged by TMA (128B swizzle), the same fused epilogues as the FFMA kernel (gemm.cu).
 //
 //   C = A W^T  with  A = Ahi + Alo,  W = Whi + Wlo  (TF32 splits)   =>   D = Ahi Whi + Alo Whi + Ahi Wlo
-// (the dropped Alo Wlo term is ~2^-22 relative).  W is split once at pack time; A (an activation that only
-// exists in fp32) is split ON CHIP: TMA lands the raw fp32 tile in shared memory, four converter warps rewrite
-// it in place as the TF32 hi part and write the lo part beside it (same swizzled offsets), then the single MMA
-// thread issues three tcgen05.mma per 8-wide k-step against the TMEM accumulator.  Nothing but the fp32
-// activations themselves ever travels through HBM.
+// (the dropped Alo Wlo term is ~2^-22 relative).  W is split once at pack time.  A (an activation that only
+// exists in fp32) is split ON CHIP and never touches HBM or shared memory again: TMA lands the raw fp32 tile in
+// shared memory, each converter thread reads its own row (bank-conflict free under the 128B swizzle), rounds
+// it to TF32 (hi) and keeps the exact remainder (lo), and writes both straight into TENSOR MEMORY
+// (tcgen05.st), from where tcgen05.mma takes its A operand.  Only the B operand (the weights) is read from
+// shared memory by the tensor core, which halves the shared-memory traffic per flop of the SS form.
 //
-// CTA = one 128 x BN output tile (BN <= 256, runtime), 6 warps:
-//   warp 0  TMA producer (one lane)          warp 1  TMEM allocator + MMA issuer (one lane)
-//   warps 2-5  fp32 -> (hi, lo) converters during the main loop, then the epilogue (one thread per row,
-//              tcgen05.ld 32x32b, fused bias / GELU / residual / LayerNorm-q / coupling / augment epilogues)
-// Two shared-memory stages of {A hi, A lo, W hi, W lo} x 32 k, mbarrier pipeline:
-//   full[s]  (TMA bytes landed)  ->  conv[s] (128 converter arrivals)  ->  tcgen05.commit -> empty[s]
+// The tensor core truncates when it adds a product block to its accumulator (measured ~0.25 ulp one-sided per
+// tcgen05.mma).  The two small compensation products therefore get their OWN accumulator (truncation at 2^-11
+// of the magnitude), and the one GEMM whose output is the latent itself (ActNorm+LinearLU) applies its
+// diagonal in fp32 in the epilogue (flow.cu), so the residual bias is below the fp32 noise of the reference.
+//
+// CTA = one 128 x BN output tile (BN <= 192, runtime), 10 warps:
+//   warp 0      TMA producer (one lane)
+//   warp 1      TMEM allocator + MMA issuer (one lane)
+//   warps 2-5   converters (one thread per tile row) during the main loop, then epilogue
+//   warps 6-9   epilogue only (each TMEM lane quadrant is drained by two warps, alternating 16-column chunks)
+// TMEM (512 columns): [0,192) main accumulator | [192,384) compensation accumulator |
+//                     [384,512) two stages of A: 32 columns hi + 32 columns lo each.
+// Pipeline (mbarriers): full[s] (TMA bytes landed, 3 smem stages) -> converter -> a_free[s] (A smem reusable) and
+//   conv[ts] (A in TMEM stage ts ready) -> MMA -> tcgen05.commit -> w_free[s] (W smem reusable), tfree[ts].
 #include "gemm.cuh"
 #include <cuda.h>
-#include <mutex>
-#include <unordered_map>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 namespace {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;                     // 32 fp32 = one 128-byte swizzle row
-constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 192;
+constexpr int TC_BK = 32;                      // 32 fp32 = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;                   // shared-memory stages
+constexpr int TC_TSTAGES = 2;                  // TMEM stages of the A operand
+constexpr int TC_THREADS = 320;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_TMEM_COLS = 512;
-// The tensor core TRUNCATES when it adds a product block to the TMEM accumulator (measured: ~0.25 ulp of
-// one-sided error per tcgen05.mma, i.e. a systematic shrink of every output that grows with K and shows up
-// as a constant offset in the log-density).  Two counter-measures keep the result at fp32-FFMA quality:
-//   * the two small compensation products (Alo Whi, Ahi Wlo) go to their OWN accumulator, where the
-//     truncation happens at 2^-11 of the magnitude;
-//   * the main product Ahi Whi is spread round-robin by k-block over TC_MAIN_ACC accumulators, so each sees
-//     1/3 of the sequential truncations; the epilogue adds the four partial sums in round-to-nearest fp32.
-// 4 accumulators x BN (<= 128) columns = the whole 512-column TMEM.
-constexpr int TC_MAIN_ACC = 3;
-constexpr int TC_ACC_STRIDE = 128;             // TMEM columns between accumulators
+constexpr int TC_COL_MAIN = 0;
+constexpr int TC_COL_CORR = 192;
+constexpr int TC_COL_A = 384;                  // + 64 * stage: hi at +0, lo at +32
 
 struct TcParams {
     GemmArgs g;
-    int BN;        // N tile (multiple of 16, <= 256)
+    int BN;        // N tile (multiple of 16, <= 192)
     int T1, T2;    // k-blocks of segment 1 / 2
     int passes;    // 3 = 3xTF32, 1 = plain TF32 (debug)
 };
@@ -83,13 +86,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* smem_d
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem descriptor]   (A: 128 lanes x 8 columns of TF32, B: K-major tile)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO), version 1 (Blackwell)
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
@@ -109,28 +113,39 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
 
 // ----------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 1];
+    __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 1];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float ldj_sm[TC_BM];
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024 B alignment
     const int BN = p.BN;
     const int w_bytes = BN * TC_BK * 4;
-    const int stage_bytes = 2 * TC_A_BYTES + 2 * w_bytes;
-    auto a_hi = [&](int s) { return smem + s * stage_bytes; };
-    auto a_lo = [&](int s) { return smem + s * stage_bytes + TC_A_BYTES; };
-    auto w_hi = [&](int s) { return smem + s * stage_bytes + 2 * TC_A_BYTES; };
-    auto w_lo = [&](int s) { return smem + s * stage_bytes + 2 * TC_A_BYTES + w_bytes; };
-    uint64_t* full = bars;
-    uint64_t* conv = bars + TC_STAGES;
-    uint64_t* empty = bars + 2 * TC_STAGES;
-    uint64_t* accum = bars + 3 * TC_STAGES;
+    const int stage_bytes = TC_A_BYTES + 2 * w_bytes;
+    auto a_raw = [&](int s) { return smem + s * stage_bytes; };
+    auto w_hi = [&](int s) { return smem + s * stage_bytes + TC_A_BYTES; };
+    auto w_lo = [&](int s) { return smem + s * stage_bytes + TC_A_BYTES + w_bytes; };
+    uint64_t* full = bars;                                   // [TC_STAGES]  TMA bytes landed
+    uint64_t* a_free = bars + TC_STAGES;                     // [TC_STAGES]  converters done reading A smem
+    uint64_t* w_free = bars + 2 * TC_STAGES;                 // [TC_STAGES]  MMAs done reading W smem
+    uint64_t* conv = bars + 3 * TC_STAGES;                   // [TC_TSTAGES] A hi/lo written to TMEM
+    uint64_t* tfree = bars + 3 * TC_STAGES + TC_TSTAGES;     // [TC_TSTAGES] MMAs done reading A TMEM
+    uint64_t* accum = bars + 3 * TC_STAGES + 2 * TC_TSTAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TC_BM;
@@ -138,7 +153,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     const int T = p.T1 + p.T2;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], 128); mbar_init(&w_free[s], 1); }
+        for (int s = 0; s < TC_TSTAGES; ++s) { mbar_init(&conv[s], 128); mbar_init(&tfree[s], 1); }
         mbar_init(accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -149,7 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = tmem_base_slot;
+    const uint32_t tmem = tmem_base_slot;
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -157,10 +173,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             for (int t = 0; t < T; ++t) {
                 const int s = t % TC_STAGES;
                 const uint32_t ph = (t / TC_STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1, 100 + t);
+                mbar_wait(&a_free[s], ph ^ 1, 100 + t);
+                mbar_wait(&w_free[s], ph ^ 1, 150 + t);
                 mbar_expect_tx(&full[s], (uint32_t)(TC_A_BYTES + (p.passes == 3 ? 2 : 1) * w_bytes));
-                if (t < p.T1) tma_load_2d(&mapA1, a_hi(s), &full[s], t * TC_BK, m0);
-                else          tma_load_2d(&mapA2, a_hi(s), &full[s], (t - p.T1) * TC_BK, m0);
+                if (t < p.T1) tma_load_2d(&mapA1, a_raw(s), &full[s], t * TC_BK, m0);
+                else          tma_load_2d(&mapA2, a_raw(s), &full[s], (t - p.T1) * TC_BK, m0);
                 tma_load_2d(&mapWhi, w_hi(s), &full[s], t * TC_BK, n_tile * BN);
                 if (p.passes == 3) tma_load_2d(&mapWlo, w_lo(s), &full[s], t * TC_BK, n_tile * BN);
             }
@@ -168,67 +185,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     } else if (warp == 1) {
         // ===================================================== MMA issuer
         if (lane == 0) {
-            // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2), both K-major, N>>3 at bit 17, M>>4 at bit 24
+            // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2), K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t d_main = tmem + TC_COL_MAIN, d_corr = tmem + TC_COL_CORR;
             for (int t = 0; t < T; ++t) {
-                const int s = t % TC_STAGES;
-                const uint32_t ph = (t / TC_STAGES) & 1;
+                const int s = t % TC_STAGES, ts = t % TC_TSTAGES;
+                const uint32_t ph = (t / TC_STAGES) & 1, tph = (t / TC_TSTAGES) & 1;
                 mbar_wait(&full[s], ph, 200 + t);
-                mbar_wait(&conv[s], ph, 300 + t);
+                mbar_wait(&conv[ts], tph, 300 + t);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t dah = make_kmajor_sw128_desc(smem_u32(a_hi(s)));
-                const uint64_t dal = make_kmajor_sw128_desc(smem_u32(a_lo(s)));
                 const uint64_t dbh = make_kmajor_sw128_desc(smem_u32(w_hi(s)));
                 const uint64_t dbl = make_kmajor_sw128_desc(smem_u32(w_lo(s)));
-                const uint32_t d_main = tmem_d + (uint32_t)((t % TC_MAIN_ACC) * TC_ACC_STRIDE);
-                const uint32_t d_corr = tmem_d + (uint32_t)(TC_MAIN_ACC * TC_ACC_STRIDE);
-                const bool main_first = t < TC_MAIN_ACC;   // first k-block landing in this main accumulator
+                const uint32_t t_hi = tmem + TC_COL_A + 64 * ts, t_lo = t_hi + 32;
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
                     const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
                     if (p.passes == 3) {
-                        umma_tf32(d_corr, dal + adv, dbh + adv, idesc, (t | k) != 0);
-                        umma_tf32(d_corr, dah + adv, dbl + adv, idesc, 1);
+                        umma_tf32_ts(d_corr, t_lo + 8 * k, dbh + adv, idesc, (t | k) != 0);
+                        umma_tf32_ts(d_corr, t_hi + 8 * k, dbl + adv, idesc, 1);
                     }
-                    umma_tf32(d_main, dah + adv, dbh + adv, idesc, !(main_first && k == 0));
+                    umma_tf32_ts(d_main, t_hi + 8 * k, dbh + adv, idesc, (t | k) != 0);
                 }
-                umma_commit(&empty[s]);      // stage s may be refilled once these MMAs retire
+                umma_commit(&w_free[s]);     // W smem stage reusable once these MMAs retire
+                umma_commit(&tfree[ts]);     // ... and so is the TMEM A stage
             }
-            umma_commit(accum);              // accumulator complete
+            umma_commit(accum);              // accumulators complete
         }
     } else {
-        // ===================================================== converters, then epilogue
-        const int cid = threadIdx.x - 64;   // 0..127
-        for (int t = 0; t < T; ++t) {
-            const int s = t % TC_STAGES;
-            const uint32_t ph = (t / TC_STAGES) & 1;
-            mbar_wait(&full[s], ph, 400 + t);
-            if (p.passes == 3) {
-                float4* hi = reinterpret_cast<float4*>(a_hi(s));
-                float4* lo = reinterpret_cast<float4*>(a_lo(s));
+        const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
+        const int row_in_tile = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        if (warp < 6) {
+            // ===================================================== converters: fp32 smem row -> (hi, lo) in TMEM
+            for (int t = 0; t < T; ++t) {
+                const int s = t % TC_STAGES, ts = t % TC_TSTAGES;
+                const uint32_t ph = (t / TC_STAGES) & 1, tph = (t / TC_TSTAGES) & 1;
+                mbar_wait(&full[s], ph, 400 + t);
+                const float4* rowp = reinterpret_cast<const float4*>(a_raw(s) + row_in_tile * 128);
+                uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
-                    const int c = cid + i * 128;
-                    const float4 x = hi[c];
-                    float4 h, l;
-                    uint32_t u;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); h.x = __uint_as_float(u); l.x = x.x - h.x;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); h.y = __uint_as_float(u); l.y = x.y - h.y;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); h.z = __uint_as_float(u); l.z = x.z - h.z;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); h.w = __uint_as_float(u); l.w = x.w - h.w;
-                    hi[c] = h;
-                    lo[c] = l;
+                for (int j = 0; j < 8; ++j) {
+                    // 128B swizzle: logical 16-byte chunk j of row r sits at physical chunk j ^ (r & 7); a quarter
+                    // warp (8 consecutive rows) therefore hits all 32 banks exactly once
+                    const float4 x = rowp[j ^ (row_in_tile & 7)];
+                    const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint32_t u;
+                        if (p.passes == 3) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(xv[e]));
+                        else u = __float_as_uint(xv[e]);
+                        hi[4 * j + e] = u;
+                        lo[4 * j + e] = __float_as_uint(xv[e] - __uint_as_float(u));
+                    }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+                mbar_arrive(&a_free[s]);             // values are in registers: the A smem stage may be refilled
+                mbar_wait(&tfree[ts], tph ^ 1, 450 + t);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tcol = tmem + lane_addr + TC_COL_A + 64 * ts;
+                tmem_st32(tcol, hi);
+                if (p.passes == 3) tmem_st32(tcol + 32, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&conv[ts]);
             }
-            mbar_arrive(&conv[s]);
         }
-        // ---- epilogue: TMEM lane = row within the tile; warp w may touch lanes 32*(w%4) .. +31
+        // ===================================================== epilogue (8 warps)
+        // TMEM lane = row within the tile; the two warps of a quadrant take alternate 16-column chunks
+        const int half = warp >= 6 ? 1 : 0;
         mbar_wait(accum, 0, 500);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const GemmArgs& a = p.g;
-        const int lane_base = (warp & 3) * 32;
-        const int row = m0 + lane_base + lane;
+        const int row = m0 + row_in_tile;
         const bool row_ok = row < a.M;
         const int n0 = n_tile * BN;
         float ldj = 0.f;
@@ -236,22 +263,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         if (a.epi == FC_EPI_LNQ && row_ok) { mu = a.row_mu[row]; rstd = a.row_rstd[row]; }
         const float* bias_row = a.bias;
         if (a.bias && a.bias_group > 0 && row_ok) bias_row = a.bias + (size_t)(row / a.bias_group) * a.bias_ld;
-        const int n_main = T < TC_MAIN_ACC ? T : TC_MAIN_ACC;   // main accumulators that were written
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = half * 16; c0 < BN; c0 += 32) {
             uint32_t r[16];
             float v[16];
             __syncwarp();
-            const uint32_t tbase = tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)c0;
-            tmem_ld16(tbase, r);
+            tmem_ld16(tmem + lane_addr + TC_COL_MAIN + (uint32_t)c0, r);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            for (int m = 1; m < n_main; ++m) {
-                tmem_ld16(tbase + (uint32_t)(m * TC_ACC_STRIDE), r);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
-            }
             if (p.passes == 3) {
-                tmem_ld16(tbase + (uint32_t)(TC_MAIN_ACC * TC_ACC_STRIDE), r);
+                tmem_ld16(tmem + lane_addr + TC_COL_CORR + (uint32_t)c0, r);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
             }
@@ -316,15 +336,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 }
             }
         }
-        if ((a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) && row_ok) {
-            float* pp = a.part + (size_t)n_tile * a.M + row;
-            if (a.epi == FC_EPI_COUPLING) *pp += ldj; else *pp = ldj;
+        if (a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) {
+            // the two threads that share a row combine their partial log-dets in a fixed order (deterministic)
+            if (half == 1) ldj_sm[row_in_tile] = ldj;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0 && row_ok) {
+                const float tot = ldj + ldj_sm[row_in_tile];
+                float* pp = a.part + (size_t)n_tile * a.M + row;
+                if (a.epi == FC_EPI_COUPLING) *pp += tot; else *pp = tot;
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_TMEM_COLS));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS));
     }
 }
 
@@ -364,7 +390,8 @@ struct MapKeyHash {
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 std::mutex g_maps_mu;
 
-// fp32 [outer][inner] row-major with row stride `stride_floats`; box = 32 x box_outer, 128B swizzle, OOB -> 0
+// fp32 [outer][inner] row-major with row stride `stride_floats`; box = 32 x box_outer, 128B swizzle, OOB -> 0.
+// Maps only encode address + geometry, so they are cached (the flow re-uses the same workspace every call).
 bool get_map(const float* base, uint64_t inner, uint64_t outer, uint64_t stride_floats, uint32_t box_outer, CUtensorMap* out) {
     MapKey key{base, inner, outer, stride_floats, box_outer};
     std::lock_guard<std::mutex> lk(g_maps_mu);
@@ -416,6 +443,7 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     static int passes_env = -1;
     if (passes_env < 0) { const char* e = getenv("FC_TC_PASSES"); passes_env = (e && e[0] == '1') ? 1 : 3; }
     p.passes = passes_env;
+    FC_REQUIRE(p.BN <= 192 && (p.BN & 15) == 0);
     FC_REQUIRE(a.ldk == (p.T1 + p.T2) * TC_BK);
     const int n_tiles = fc_tc_n_tiles(a.N);
     CUtensorMap mA1, mA2, mWh, mWl;
@@ -424,10 +452,10 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     else mA2 = mA1;
     if (!get_map(a.Whi, (uint64_t)a.ldk, (uint64_t)n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWh)) return FC_ERR_CUDA;
     if (!get_map(a.Wlo, (uint64_t)a.ldk, (uint64_t)n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWl)) return FC_ERR_CUDA;
-    const int smem = TC_STAGES * (2 * TC_A_BYTES + 2 * p.BN * TC_BK * 4) + 1024;
+    const int smem = TC_STAGES * (TC_A_BYTES + 2 * p.BN * TC_BK * 4) + 1024;
     static bool configured = false;
     if (!configured) {
-        // 2 stages x (2 x 16 KB A + 2 x 32 KB W) + 1 KB alignment slack; static smem (barriers) comes on top
+        // 3 stages x (16 KB A + 2 x 24 KB W at BN=192) + 1 KB alignment slack; static smem (barriers) comes on top
         FC_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }

@@ -76,7 +76,7 @@ FC_API int fc_gemm(const float* A, int lda, const float* Wt, int ldw, const floa
             float* C, int ldc, int M, int N, int K, int act, int precision, fc_stream_t stream);
 
 /* The same product on the tensor cores (3xTF32 tcgen05.mma, TMEM accumulators, TMA-fed): Whi / Wlo are
- * the TF32 hi / lo parts of W, N-major [ceil(N/128)*BN][ldk] with BN = ceil(N / ceil(N/128)) rounded up to
+ * the TF32 hi / lo parts of W, N-major [ceil(N/192)*BN][ldk] with BN = ceil(N / ceil(N/192)) rounded up to
  * 16 and ldk = K rounded up to 32 (zero padded); A is split on chip.  Requires lda % 4 == 0, N >= 16.    */
 FC_API int fc_gemm_tf32x3(const float* A, int lda, const float* Whi, const float* Wlo, int ldk,
                    const float* bias, float* C, int ldc, int M, int N, int K, int act, fc_stream_t stream);
