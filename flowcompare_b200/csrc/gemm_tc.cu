@@ -48,6 +48,8 @@ struct TcParams {
     int BN;        // N tile (multiple of 16, <= 192)
     int T1, T2;    // k-blocks of segment 1 / 2
     int passes;    // 3 = 3xTF32, 1 = plain TF32 (debug)
+    int debug;     // 1: accumulate phase cycle counts into fc_tc_dbg
+    int merge_corr; // experiment: compensation products into the main accumulator
 };
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -83,8 +85,24 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* smem_d
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// same load, delivered to the same shared-memory offset (data and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* map, void* smem_dst, uint64_t* bar, int c0, int c1,
+                                                  uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem descriptor]   (A: 128 lanes x 8 columns of TF32, B: K-major tile)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -123,6 +141,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
           "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 
+// phase timing (debug): [0] CTAs, [1] cycles setup->accumulator ready, [2] cycles of the epilogue, [3] cycles setup
+__device__ unsigned long long fc_tc_dbg[8];   // [4] tmem loads, [5] bias/act math, [6] staging + global stores
+
 // ----------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
@@ -131,6 +152,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 1];
     __shared__ uint32_t tmem_base_slot;
     __shared__ float ldj_sm[TC_BM];
+    __shared__ __align__(16) float bias_sm[192];   // this tile's bias (and LayerNorm-q column sums), prefetched
+    __shared__ __align__(16) float csum_sm[192];
+    __shared__ int bias_in_smem;
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024 B alignment
@@ -147,13 +171,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     uint64_t* tfree = bars + 3 * TC_STAGES + TC_TSTAGES;     // [TC_TSTAGES] MMAs done reading A TMEM
     uint64_t* accum = bars + 3 * TC_STAGES + 2 * TC_TSTAGES;
 
+    const long long t_begin = clock64();
+    long long t_accum_g = 0, dbg_ld = 0, dbg_math = 0, dbg_st = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TC_BM;
     const int n_tile = blockIdx.x;
     const int T = p.T1 + p.T2;
 
+    // Thread-block cluster along M (1 x cs x 1): the cs CTAs of a cluster work on the SAME weight tile, so each
+    // loads 1/cs of its rows and TMA-multicasts them to all peers -- the L2 -> SM weight traffic, which dominates
+    // (hi + lo copies, re-read by every 128-row tile), drops by cs.
+    uint32_t cta_rank = 0, cs = 1;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cs));
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], 128); mbar_init(&w_free[s], 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], 128); mbar_init(&w_free[s], cs); }
         for (int s = 0; s < TC_TSTAGES; ++s) { mbar_init(&conv[s], 128); mbar_init(&tfree[s], 1); }
         mbar_init(accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -164,8 +198,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_slot;
+    const long long t_setup = clock64();
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -178,8 +214,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 mbar_expect_tx(&full[s], (uint32_t)(TC_A_BYTES + (p.passes == 3 ? 2 : 1) * w_bytes));
                 if (t < p.T1) tma_load_2d(&mapA1, a_raw(s), &full[s], t * TC_BK, m0);
                 else          tma_load_2d(&mapA2, a_raw(s), &full[s], (t - p.T1) * TC_BK, m0);
-                tma_load_2d(&mapWhi, w_hi(s), &full[s], t * TC_BK, n_tile * BN);
-                if (p.passes == 3) tma_load_2d(&mapWlo, w_lo(s), &full[s], t * TC_BK, n_tile * BN);
+                if (cs == 1) {
+                    tma_load_2d(&mapWhi, w_hi(s), &full[s], t * TC_BK, n_tile * BN);
+                    if (p.passes == 3) tma_load_2d(&mapWlo, w_lo(s), &full[s], t * TC_BK, n_tile * BN);
+                } else {
+                    // my slice of the tile's rows (the W maps are built with box_outer = BN / cs)
+                    const int slice = BN / (int)cs;
+                    const int off = (int)cta_rank * slice;
+                    tma_load_2d_mcast(&mapWhi, w_hi(s) + off * 128, &full[s], t * TC_BK, n_tile * BN + off, cmask);
+                    if (p.passes == 3)
+                        tma_load_2d_mcast(&mapWlo, w_lo(s) + off * 128, &full[s], t * TC_BK, n_tile * BN + off, cmask);
+                }
             }
         }
     } else if (warp == 1) {
@@ -187,7 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         if (lane == 0) {
             // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2), K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            const uint32_t d_main = tmem + TC_COL_MAIN, d_corr = tmem + TC_COL_CORR;
+            const uint32_t d_main = tmem + TC_COL_MAIN, d_corr = tmem + (p.merge_corr ? TC_COL_MAIN : TC_COL_CORR);
             for (int t = 0; t < T; ++t) {
                 const int s = t % TC_STAGES, ts = t % TC_TSTAGES;
                 const uint32_t ph = (t / TC_STAGES) & 1, tph = (t / TC_TSTAGES) & 1;
@@ -204,9 +249,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         umma_tf32_ts(d_corr, t_lo + 8 * k, dbh + adv, idesc, (t | k) != 0);
                         umma_tf32_ts(d_corr, t_hi + 8 * k, dbl + adv, idesc, 1);
                     }
-                    umma_tf32_ts(d_main, t_hi + 8 * k, dbh + adv, idesc, (t | k) != 0);
+                    umma_tf32_ts(d_main, t_hi + 8 * k, dbh + adv, idesc, (t | k) != 0 || (p.merge_corr && p.passes == 3));
                 }
-                umma_commit(&w_free[s]);     // W smem stage reusable once these MMAs retire
+                // W smem stage reusable once these MMAs retire -- every CTA of the cluster writes into it
+                if (cs == 1) umma_commit(&w_free[s]); else umma_commit_mcast(&w_free[s], cmask);
                 umma_commit(&tfree[ts]);     // ... and so is the TMEM A stage
             }
             umma_commit(accum);              // accumulators complete
@@ -249,11 +295,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 mbar_arrive(&conv[ts]);
             }
         }
+        else {
+            // epilogue-only warps are idle during the main loop: fetch this tile's bias row (a cold L2 miss per
+            // 16-column chunk otherwise -- measured ~600 cycles each) into shared memory
+            const GemmArgs& a = p.g;
+            const int n0p = n_tile * BN;
+            const int last_row = min(m0 + TC_BM, a.M) - 1;
+            const bool one_group = a.bias_group <= 0 || (m0 / a.bias_group) == (last_row / a.bias_group);
+            const float* brow = a.bias;
+            if (a.bias && a.bias_group > 0) brow = a.bias + (size_t)(m0 / a.bias_group) * a.bias_ld;
+            for (int i = threadIdx.x - 192; i < BN; i += 128) {
+                const int col = n0p + i;
+                bias_sm[i] = (brow && one_group && col < a.N) ? brow[col] : 0.f;
+                csum_sm[i] = (a.epi == FC_EPI_LNQ && col < a.N) ? a.csum[col] : 0.f;
+            }
+            if (threadIdx.x == 192) bias_in_smem = (one_group && m0 < a.M) ? 1 : 0;
+        }
         // ===================================================== epilogue (8 warps)
         // TMEM lane = row within the tile; the two warps of a quadrant take alternate 16-column chunks
         const int half = warp >= 6 ? 1 : 0;
         mbar_wait(accum, 0, 500);
+        t_accum_g = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");    // bias_sm / csum_sm visible to all 8 epilogue warps
+        const bool bias_smem = bias_in_smem != 0;
         const GemmArgs& a = p.g;
         const int row = m0 + row_in_tile;
         const bool row_ok = row < a.M;
@@ -263,36 +328,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         if (a.epi == FC_EPI_LNQ && row_ok) { mu = a.row_mu[row]; rstd = a.row_rstd[row]; }
         const float* bias_row = a.bias;
         if (a.bias && a.bias_group > 0 && row_ok) bias_row = a.bias + (size_t)(row / a.bias_group) * a.bias_ld;
+        // per-warp staging tile [32 rows][16 + 1 pad]; the pipeline stages are dead once `accum` has fired
+        float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 17);
+        const int row0 = m0 + quad * 32;
+        long long d_ld = 0, d_math = 0, d_st = 0;
         for (int c0 = half * 16; c0 < BN; c0 += 32) {
             uint32_t r[16];
             float v[16];
             __syncwarp();
+            const long long q0 = clock64();
             tmem_ld16(tmem + lane_addr + TC_COL_MAIN + (uint32_t)c0, r);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.passes == 3) {
+            if (p.passes == 3 && !p.merge_corr) {
                 tmem_ld16(tmem + lane_addr + TC_COL_CORR + (uint32_t)c0, r);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
             }
+            const long long q1 = clock64();
+            d_ld += q1 - q0;
             const int col = n0 + c0;
-            if (!row_ok || col >= a.N) continue;
+            if (col >= a.N) continue;                     // warp-uniform
             if (a.epi == FC_EPI_LNQ) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (col + j < a.N) v[j] = rstd * (v[j] - mu * a.csum[col + j]) + a.bias[col + j];
-            } else if (bias_row) {
+                    if (col + j < a.N) v[j] = rstd * (v[j] - mu * csum_sm[c0 + j]) + bias_sm[c0 + j];
+            } else if (bias_row && bias_smem) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) if (col + j < a.N) v[j] += bias_row[col + j];
+                for (int j = 0; j < 16; ++j) v[j] += bias_sm[c0 + j];   // zero beyond N
+            } else if (bias_row) {
+                if (col + 15 < a.N && ((reinterpret_cast<uintptr_t>(bias_row + col) & 15) == 0)) {
+                    // four 16-byte loads at a warp-uniform address (issued back to back) instead of 16 predicated ones
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_row + col);
+                    const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1), b2 = __ldg(b4 + 2), b3 = __ldg(b4 + 3);
+                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    v[8] += b2.x; v[9] += b2.y; v[10] += b2.z; v[11] += b2.w;
+                    v[12] += b3.x; v[13] += b3.y; v[14] += b3.z; v[15] += b3.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (col + j < a.N) v[j] += bias_row[col + j];
+                }
             }
             if (a.epi == FC_EPI_STORE || a.epi == FC_EPI_LNQ) {
+                // Global traffic goes through a per-warp staging tile so that it is COALESCED: with one thread per
+                // row, direct loads/stores touch 32 different lines per instruction (ncu: the residual layers took 2x
+                // as long as the plain ones).  Each warp instruction below moves 2 rows x 64 contiguous bytes.
+                const int sr = lane >> 4, sc = lane & 15;
                 if (a.res) {
+                    float rx[16];   // all loads first, then all shared stores: no store->load ordering stalls
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (col + j < a.N) {
-                            const float rv = a.res[(size_t)row * a.ldres + col + j];
-                            v[j] = a.res_scale ? fmaf(a.res_scale[col + j], rv, v[j]) : v[j] + rv;
-                        }
+                    for (int i = 0; i < 16; ++i) {
+                        const int gr = row0 + 2 * i + sr;
+                        rx[i] = (gr < a.M && col + sc < a.N) ? __ldg(a.res + (size_t)gr * a.ldres + col + sc) : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) stg[(2 * i + sr) * 17 + sc] = rx[i];
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float rv = stg[lane * 17 + j];
+                        if (col + j < a.N) v[j] = a.res_scale ? fmaf(a.res_scale[col + j], rv, v[j]) : v[j] + rv;
+                    }
+                    __syncwarp();
                 }
                 if (a.act == FC_ACT_GELU) {
 #pragma unroll
@@ -301,15 +399,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fc_leaky_relu02(v[j]);
                 }
-                float* dst = a.C + (size_t)row * a.ldc + col;
-                if (col + 15 < a.N && (a.ldc & 3) == 0) {
+                const long long q2 = clock64();
+                d_math += q2 - q1;
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
+                for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = v[j];
+                __syncwarp();
+                float ox[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (col + j < a.N) dst[j] = v[j];
+                for (int i = 0; i < 16; ++i) ox[i] = stg[(2 * i + sr) * 17 + sc];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int gr = row0 + 2 * i + sr;
+                    if (gr < a.M && col + sc < a.N) a.C[(size_t)gr * a.ldc + col + sc] = ox[i];
                 }
+                __syncwarp();
+                d_st += clock64() - q2;
+            } else if (!row_ok) {
+                // nothing: out-of-range rows of the coupling / augment epilogues
             } else if (a.epi == FC_EPI_COUPLING) {
                 // reference models/affine_coupling.py:40-46 (see gemm.cu for the arithmetic notes)
 #pragma unroll
@@ -336,6 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 }
             }
         }
+        dbg_ld = d_ld; dbg_math = d_math; dbg_st = d_st;
         if (a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) {
             // the two threads that share a row combine their partial log-dets in a fixed order (deterministic)
             if (half == 1) ldj_sm[row_in_tile] = ldj;
@@ -347,11 +454,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             }
         }
     }
+    if (p.debug && threadIdx.x == 64) {
+        const long long t_end = clock64();
+        atomicAdd(&fc_tc_dbg[0], 1ull);
+        atomicAdd(&fc_tc_dbg[1], (unsigned long long)(t_accum_g - t_setup));
+        atomicAdd(&fc_tc_dbg[2], (unsigned long long)(t_end - t_accum_g));
+        atomicAdd(&fc_tc_dbg[3], (unsigned long long)(t_setup - t_begin));
+        atomicAdd(&fc_tc_dbg[4], (unsigned long long)dbg_ld);
+        atomicAdd(&fc_tc_dbg[5], (unsigned long long)dbg_math);
+        atomicAdd(&fc_tc_dbg[6], (unsigned long long)dbg_st);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS));
     }
+    if (cs > 1) cluster_sync_all();   // nobody exits while a peer may still arrive on its barriers
 }
 
 // ----------------------------------------------------------------------------- host: tensor maps
@@ -443,15 +561,29 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     static int passes_env = -1;
     if (passes_env < 0) { const char* e = getenv("FC_TC_PASSES"); passes_env = (e && e[0] == '1') ? 1 : 3; }
     p.passes = passes_env;
+    static int dbg_env = -1;
+    if (dbg_env < 0) { const char* e = getenv("FC_TC_DEBUG"); dbg_env = (e && e[0] == '1') ? 1 : 0; }
+    p.debug = dbg_env;
+    static int mc_env = -1;
+    if (mc_env < 0) { const char* e = getenv("FC_TC_MERGE_CORR"); mc_env = (e && e[0] == '1') ? 1 : 0; }
+    p.merge_corr = mc_env;
     FC_REQUIRE(p.BN <= 192 && (p.BN & 15) == 0);
     FC_REQUIRE(a.ldk == (p.T1 + p.T2) * TC_BK);
     const int n_tiles = fc_tc_n_tiles(a.N);
+    int m_tiles = (a.M + TC_BM - 1) / TC_BM;
+    // cluster size along M (weight-tile multicast); FC_TC_CLUSTER=1 disables it
+    static int cs_env = -1;
+    if (cs_env < 0) { const char* e = getenv("FC_TC_CLUSTER"); cs_env = e ? atoi(e) : 2; if (cs_env != 1 && cs_env != 2 && cs_env != 4) cs_env = 2; }
+    int cs = cs_env;
+    while (cs > 1 && (m_tiles < cs || (p.BN % (8 * cs)) != 0)) cs >>= 1;
+    m_tiles = (m_tiles + cs - 1) / cs * cs;   // padded M tiles run on out-of-range rows (TMA zero fill, stores masked)
     CUtensorMap mA1, mA2, mWh, mWl;
     if (!get_map(a.A1, (uint64_t)a.K1, (uint64_t)a.M, (uint64_t)a.lda1, TC_BM, &mA1)) return FC_ERR_CUDA;
     if (a.K2) { if (!get_map(a.A2, (uint64_t)a.K2, (uint64_t)a.M, (uint64_t)a.lda2, TC_BM, &mA2)) return FC_ERR_CUDA; }
     else mA2 = mA1;
-    if (!get_map(a.Whi, (uint64_t)a.ldk, (uint64_t)n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWh)) return FC_ERR_CUDA;
-    if (!get_map(a.Wlo, (uint64_t)a.ldk, (uint64_t)n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWl)) return FC_ERR_CUDA;
+    const uint32_t wbox = (uint32_t)(p.BN / cs);
+    if (!get_map(a.Whi, (uint64_t)a.ldk, (uint64_t)n_tiles * p.BN, (uint64_t)a.ldk, wbox, &mWh)) return FC_ERR_CUDA;
+    if (!get_map(a.Wlo, (uint64_t)a.ldk, (uint64_t)n_tiles * p.BN, (uint64_t)a.ldk, wbox, &mWl)) return FC_ERR_CUDA;
     const int smem = TC_STAGES * (TC_A_BYTES + 2 * p.BN * TC_BK * 4) + 1024;
     static bool configured = false;
     if (!configured) {
@@ -459,11 +591,27 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
         FC_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    dim3 grid(n_tiles, (a.M + TC_BM - 1) / TC_BM);
     FcProfScope prof(FC_CLS_GEMM_TC, 2.0 * a.M * a.N * (a.K1 + a.K2),
                      4.0 * ((double)a.M * (a.K1 + a.K2) + (double)a.N * (a.K1 + a.K2) + (double)a.M * a.N), stream);
-    gemm_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mA1, mA2, mWh, mWl, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_tiles, m_tiles);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = cs; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel, mA1, mA2, mWh, mWl, p));
     fc_count_launch();
     FC_LAUNCH_OK();
+    return FC_OK;
+}
+
+// debug: read and reset the phase counters of gemm_tc_kernel (FC_TC_DEBUG=1)
+extern "C" __attribute__((visibility("default"))) int fc_debug_tc_phases(unsigned long long* out4) {
+    if (cudaMemcpyFromSymbol(out4, fc_tc_dbg, 8 * sizeof(unsigned long long)) != cudaSuccess) return FC_ERR_CUDA;
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(fc_tc_dbg, z, sizeof(z)) != cudaSuccess) return FC_ERR_CUDA;
     return FC_OK;
 }

@@ -31,4 +31,11 @@ for K, N, act in shapes:
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
         res[name] = (ms, 2.0 * M * N * K / ms / 1e9)
+    if os.environ.get("FC_TC_DEBUG") == "1":
+        import ctypes
+        buf = (ctypes.c_ulonglong * 8)()
+        lib.fc_debug_tc_phases.argtypes = [ctypes.c_void_p]; lib.fc_debug_tc_phases.restype = ctypes.c_int
+        lib.fc_debug_tc_phases(buf)
+        n = max(1, buf[0])
+        print(f"   phases per CTA (cycles): setup {buf[3]/n:8.0f}  mainloop(setup->accum) {buf[1]/n:8.0f}  epilogue {buf[2]/n:8.0f} (tmem ld {buf[4]/n:.0f}, math {buf[5]/n:.0f}, stage+store {buf[6]/n:.0f})  ctas {buf[0]}")
     print(f"M={M} K={K:4d} N={N:4d} act={act}  ffma {res['ffma'][0]*1e3:8.1f} us {res['ffma'][1]:6.1f} TF/s | tc {res['tc'][0]*1e3:8.1f} us {res['tc'][1]:6.1f} TF/s", flush=True)
