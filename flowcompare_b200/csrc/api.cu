@@ -68,7 +68,7 @@ extern "C" int fc_gemm(const float* A, int lda, const float* Wt, int ldw, const 
     GemmArgs g = fc_gemm_args_zero();
     g.A1 = A; g.lda1 = lda; g.K1 = K; g.Wt = Wt; g.ldw = ldw; g.bias = bias; g.act = act; g.C = C; g.ldc = ldc;
     g.M = M; g.N = N; g.precision = precision;
-    FC_REQUIRE(act >= 0 && act <= 2 && (precision == 0 || precision == 1));
+    FC_REQUIRE(act >= 0 && act <= 3 && (precision == 0 || precision == 1));
     if (precision == 1 && !fc_gemm_tc_supported(g)) return FC_ERR_UNSUPPORTED;
     return fc_launch_gemm(g, (cudaStream_t)stream);
 }
@@ -78,7 +78,7 @@ extern "C" int fc_gemm_tf32x3(const float* A, int lda, const float* Whi, const f
     GemmArgs g = fc_gemm_args_zero();
     g.A1 = A; g.lda1 = lda; g.K1 = K; g.Whi = Whi; g.Wlo = Wlo; g.ldk = ldk; g.bias = bias; g.act = act; g.C = C;
     g.ldc = ldc; g.M = M; g.N = N; g.precision = 1;
-    FC_REQUIRE(act >= 0 && act <= 2 && A && Whi && Wlo && C);
+    FC_REQUIRE(act >= 0 && act <= 3 && A && Whi && Wlo && C);
     if (!fc_gemm_tc_supported(g)) return FC_ERR_UNSUPPORTED;
     return fc_launch_gemm_tc(g, (cudaStream_t)stream);
 }

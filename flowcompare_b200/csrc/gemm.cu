@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_ffma_kernel(const GemmArgs a
                 } else if (a.act == FC_ACT_LRELU) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = fc_leaky_relu02(v[j]);
+                } else if (a.act == FC_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
                 float* dst = a.C + (size_t)row * a.ldc + col;
                 if (full && ((a.ldc & 3) == 0)) {

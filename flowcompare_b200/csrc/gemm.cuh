@@ -3,7 +3,7 @@
 #pragma once
 #include "common.cuh"
 
-enum { FC_ACT_NONE = 0, FC_ACT_GELU = 1, FC_ACT_LRELU = 2 };
+enum { FC_ACT_NONE = 0, FC_ACT_GELU = 1, FC_ACT_LRELU = 2, FC_ACT_RELU = 3 };
 
 // Epilogue kinds.  All operate on the fp32 accumulator tile while it is still in registers, so the
 // elementwise tail of each reference op never makes a separate trip through HBM.

@@ -398,6 +398,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 } else if (a.act == FC_ACT_LRELU) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fc_leaky_relu02(v[j]);
+                } else if (a.act == FC_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
                 const long long q2 = clock64();
                 d_math += q2 - q1;

@@ -29,7 +29,8 @@ FIXTURES = {
     "tiny_dgcnn_attn": ("dgcnn_attn", dict(n_flow_layers=3, sample_size=96, n_samples_context=128), 2, 11, 21),
     "tiny_dgcnn_attn_extra": ("dgcnn_attn_extra", dict(n_flow_layers=3, sample_size=96, n_samples_context=128), 2, 12, 22),
     "tiny_dgcnn_global": ("dgcnn_global", dict(n_flow_layers=3, sample_size=96, n_samples_context=128), 2, 13, 23),
-    "tiny_paconv_attn": ("paconv_attn", dict(n_flow_layers=3, sample_size=96, n_samples_context=128), 2, 14, 24),
+    "tiny_paconv_attn": ("paconv_attn", dict(n_flow_layers=3, sample_size=96, n_samples_context=320), 2, 14, 24),
+    "tiny_paconv_attn_extra": ("paconv_attn_extra", dict(n_flow_layers=2, sample_size=64, n_samples_context=272), 2, 16, 26),
     "mid_dgcnn_attn": ("dgcnn_attn", dict(n_flow_layers=12), 1, 15, 25),
     "full_dgcnn_attn": ("dgcnn_attn", {}, 1, 1, 3),
     "full_dgcnn_attn_extra": ("dgcnn_attn_extra", {}, 1, 2, 4),

@@ -181,6 +181,40 @@ def test_embedder_matches_port_and_golden(name):
     assert (got.cpu() - gold["embedding"]).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("name", ["tiny_paconv_attn", "tiny_paconv_attn_extra", "full_paconv_attn"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_paconv_embedder_matches_port_and_golden(name, precision):
+    """PAConv embedder (FPS, heap kNN, grouping, ScoreNet + weight-bank GEMM, max, 3-NN interpolation, FP MLPs)
+    against the oracle port (whose index kernels are oracle/pointops_ref.c) and the reference's golden output.
+    Any deviation of the sampled / grouped indices would show up as an O(1) difference."""
+    from oracle import port_paconv
+    cfg, fsd, esd, batch, e = _engine(name, precision=precision)
+    gold = load_golden(name)
+    got = e.embed(batch["extract_0"].to(DEV)).cpu()
+    want = port_paconv.paconv_embed(esd, batch["extract_0"], cfg)
+    scale = want.abs().max().item()
+    assert (got - want).abs().max().item() < 2e-5 * max(1.0, scale)
+    ref = gold["embedding"]
+    stride = gold.get("embedding_stride", 1)
+    assert (got[:, ::stride] - ref).abs().max().item() < 1e-4 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("name", ["tiny_paconv_attn", "tiny_paconv_attn_extra", "full_paconv_attn"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_inner_loop_paconv_matches_reference_golden(name, precision):
+    cfg, fsd, esd, batch, e = _engine(name, precision=precision)
+    gold = load_golden(name)
+    extra = batch["extra_context"]
+    loss, lp, bpd = e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV),
+                                  None if extra is None else extra.to(DEV)), eps=batch["eps"].to(DEV))
+    d = (lp.cpu() - gold["log_prob"]).abs()
+    print(name, precision, "max", d.max().item(), "median", d.median().item())
+    full = name.startswith("full")
+    assert d.median().item() < 1e-3
+    assert d.max().item() < (5e-3 if full else 1e-3)   # full depth: fp32-noise note in the module docstring
+    assert abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
+
+
 @pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_attn_extra", "tiny_dgcnn_global"])
 def test_flow_log_prob_matches_port(name):
     cfg, fsd, esd, batch, e = _engine(name)
