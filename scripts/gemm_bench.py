@@ -33,9 +33,11 @@ for K, N, act in shapes:
         res[name] = (ms, 2.0 * M * N * K / ms / 1e9)
     if os.environ.get("FC_TC_DEBUG") == "1":
         import ctypes
-        buf = (ctypes.c_ulonglong * 8)()
+        buf = (ctypes.c_ulonglong * 16)()
         lib.fc_debug_tc_phases.argtypes = [ctypes.c_void_p]; lib.fc_debug_tc_phases.restype = ctypes.c_int
         lib.fc_debug_tc_phases(buf)
         n = max(1, buf[0])
         print(f"   phases per CTA (cycles): setup {buf[3]/n:8.0f}  mainloop(setup->accum) {buf[1]/n:8.0f}  epilogue {buf[2]/n:8.0f} (tmem ld {buf[4]/n:.0f}, math {buf[5]/n:.0f}, stage+store {buf[6]/n:.0f})  ctas {buf[0]}")
+    if os.environ.get("FC_TC_DEBUG") == "1":
+        print(f"      converter/CTA: wait_full {buf[8]/n:.0f} convert {buf[9]/n:.0f} wait_tfree {buf[10]/n:.0f} tmem_st {buf[11]/n:.0f} | MMA/CTA: wait_full {buf[12]/n:.0f} wait_conv {buf[13]/n:.0f} issue {buf[14]/n:.0f}")
     print(f"M={M} K={K:4d} N={N:4d} act={act}  ffma {res['ffma'][0]*1e3:8.1f} us {res['ffma'][1]:6.1f} TF/s | tc {res['tc'][0]*1e3:8.1f} us {res['tc'][1]:6.1f} TF/s", flush=True)
