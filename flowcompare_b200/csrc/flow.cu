@@ -262,6 +262,8 @@ static int run_attention_block(const fc_flow* f, const FcMlp& pre, const FcAttn&
     if (rc) return rc;
     // reference models/perceiver.py:104: scale = inner_dim ** -0.5
     const float scale = 1.0f / sqrtf((float)f->inner);
+    if (precision == 1)
+        return fc_launch_cross_attention_mma(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
     return fc_launch_cross_attention(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
 }
 

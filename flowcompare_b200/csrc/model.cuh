@@ -106,6 +106,8 @@ struct FcCursor {
 int fc_launch_ln_stats(const float* h, int ldh, int M, int width, float eps, float* mu, float* rstd, cudaStream_t s);
 int fc_launch_cross_attention(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
                               int B, int N, int Nc, int d, float scale, cudaStream_t stream);
+int fc_launch_cross_attention_mma(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
+                                  int B, int N, int Nc, int d, float scale, cudaStream_t stream);
 int fc_launch_edgeconv_gather_max(const float* PQ, int ldpq, const int32_t* idx, int B, int N, int k, int Cout,
                                   float* out, int ldo, cudaStream_t stream);
 int fc_knn_launch(const float* q, int ldq, long long q_bstride, const float* t, int ldt, long long t_bstride,

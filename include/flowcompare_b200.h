@@ -98,6 +98,10 @@ FC_API int fc_edgeconv_gather_max(const float* PQ, int ldpq, const int32_t* idx,
 FC_API int fc_cross_attention(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
                        int B, int N, int Nc, int d, float scale, fc_stream_t stream);
 
+/* Same product on the tensor cores (3xTF32 warp-level MMA, flash style); used when precision = 1.       */
+FC_API int fc_cross_attention_tf32x3(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
+                              int B, int N, int Nc, int d, float scale, fc_stream_t stream);
+
 /* ------------------------------------------------------------------ model handles ---------
  * A model is described by (header int32[], table int64[], arena fp32[] on the device), produced by
  * flowcompare_b200/packing.py from the reference's own `state_dict`s.  The arena
