@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="dgcnn_attn")
-    ap.add_argument("--batch", type=int, default=32, help="cloud pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="cloud pairs per step per GPU")
     ap.add_argument("--precision", default=os.environ.get("FC_PRECISION", "auto"), choices=["auto", "fp32", "tf32x3"])
     ap.add_argument("--cpu-pairs", type=int, default=6, help="pairs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -181,6 +181,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     import torch.distributed as dist
+    # stdout carries exactly one JSON line: keep NCCL's banner ("NCCL version ...", printed at NCCL_DEBUG=VERSION) off it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
