@@ -209,8 +209,10 @@ FlowWs carve_flow_ws(const fc_flow* f, int B, int N, int Nc, void* base) {
     const int64_t M = (int64_t)B * N;
     w.ldx = fc_round_up(f->D, 4);
     w.ldh = 512;
-    w.n_cpart = fc_gemm_n_tiles(2 * (f->D - f->half));
-    w.n_apart = fc_gemm_n_tiles(2 * (f->D - f->d_in));
+    // one partial log-det slab per N-tile of whichever GEMM kernel runs (FFMA: 128-wide tiles, tcgen05: <= 96-wide)
+    auto slabs = [](int n) { const int a = fc_gemm_n_tiles(n), b = fc_tc_n_tiles(n); return a > b ? a : b; };
+    w.n_cpart = slabs(2 * (f->D - f->half));
+    w.n_apart = slabs(2 * (f->D - f->d_in));
     w.cb_ld = (f->L + 1) * f->hid;
     w.cbA_ld = fc_round_up(f->extra + (f->is_global ? f->E : 0), 4);
     if (w.cbA_ld == 0) w.cbA_ld = 4;

@@ -42,7 +42,7 @@ struct GemmArgs {
 
 // tcgen05 tiling of the N dimension: n_tiles = ceil(N/192), BN = ceil(N/n_tiles) rounded up to 16.
 // BN <= 192: two accumulators (main + compensation) take 384 of the 512 TMEM columns, the A operand the rest.
-static inline int fc_tc_n_tiles(int N) { return (N + 191) / 192; }
+static inline int fc_tc_n_tiles(int N) { return (N + 95) / 96; }
 static inline int fc_tc_bn(int N) { const int t = fc_tc_n_tiles(N); return fc_round_up((N + t - 1) / t, 16); }
 static inline int fc_tc_kpad(int K) { return fc_round_up(K, 32); }
 

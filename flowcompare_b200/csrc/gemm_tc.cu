@@ -34,14 +34,14 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                      // 32 fp32 = one 128-byte swizzle row
-constexpr int TC_STAGES = 3;                   // shared-memory stages
-constexpr int TC_TSTAGES = 2;                  // TMEM stages of the A operand
+constexpr int TC_STAGES = 2;                   // shared-memory stages (two CTAs per SM cover for each other)
+constexpr int TC_TSTAGES = 2;                  // TMEM stages of the A operand, each HALF a k-block
 constexpr int TC_THREADS = 320;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
-constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_TMEM_COLS = 256;                // half of TMEM: TWO CTAs are resident per SM
 constexpr int TC_COL_MAIN = 0;
-constexpr int TC_COL_CORR = 192;
-constexpr int TC_COL_A = 384;                  // + 64 * stage: hi at +0, lo at +32
+constexpr int TC_COL_CORR = 96;
+constexpr int TC_COL_A = 192;                  // + 32 * stage: 16 columns hi, 16 columns lo
 
 struct TcParams {
     GemmArgs g;
@@ -150,7 +150,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 __device__ unsigned long long fc_tc_dbg[8];   // [4] tmem loads, [5] bias/act math, [6] staging + global stores
 
 // ----------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -240,31 +240,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         {
             // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2), K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            const uint32_t d_main = tmem + TC_COL_MAIN, d_corr = tmem + (p.merge_corr ? TC_COL_MAIN : TC_COL_CORR);
+            const uint32_t d_main = tmem + TC_COL_MAIN, d_corr = tmem + TC_COL_CORR;
             for (int t = 0; t < T; ++t) {
-                const int s = t % TC_STAGES, ts = t % TC_TSTAGES;
-                const uint32_t ph = (t / TC_STAGES) & 1, tph = (t / TC_TSTAGES) & 1;
+                const int s = t % TC_STAGES;
+                const uint32_t ph = (t / TC_STAGES) & 1;
                 mbar_wait(&full[s], ph, 200 + t);
-                mbar_wait(&conv[ts], tph, 300 + t);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t dbh = make_kmajor_sw128_desc(smem_u32(w_hi(s)));
                 const uint64_t dbl = make_kmajor_sw128_desc(smem_u32(w_lo(s)));
-                const uint32_t t_hi = tmem + TC_COL_A + 64 * ts, t_lo = t_hi + 32;
-                if (elect_one()) {
+                // the A operand arrives in TMEM in HALF k-blocks (16 k: 16 columns hi + 16 lo per stage)
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
-                        if (p.passes == 3) {
-                            umma_tf32_ts(d_corr, t_lo + 8 * k, dbh + adv, idesc, (t | k) != 0);
-                            umma_tf32_ts(d_corr, t_hi + 8 * k, dbl + adv, idesc, 1);
+                for (int h = 0; h < 2; ++h) {
+                    const int ts = h;                               // (2t + h) % TC_TSTAGES with TC_TSTAGES == 2
+                    const uint32_t tph = t & 1;                     // ((2t + h) / 2) & 1
+                    mbar_wait(&conv[ts], tph, 300 + t);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t t_hi = tmem + TC_COL_A + 32 * ts, t_lo = t_hi + 16;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const int k = 2 * h + kk;
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
+                            if (p.passes == 3) {
+                                umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                                umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
+                            }
+                            umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (t | k) != 0);
                         }
-                        umma_tf32_ts(d_main, t_hi + 8 * k, dbh + adv, idesc, (t | k) != 0 || (p.merge_corr && p.passes == 3));
+                        umma_commit(&tfree[ts]);     // TMEM A stage reusable once these MMAs retire
+                        if (h == 1) {
+                            // W smem stage reusable once these MMAs retire -- every CTA of the cluster writes into it
+                            if (cs == 1) umma_commit(&w_free[s]); else umma_commit_mcast(&w_free[s], cmask);
+                        }
                     }
-                    // W smem stage reusable once these MMAs retire -- every CTA of the cluster writes into it
-                    if (cs == 1) umma_commit(&w_free[s]); else umma_commit_mcast(&w_free[s], cmask);
-                    umma_commit(&tfree[ts]);     // ... and so is the TMEM A stage
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             if (elect_one()) umma_commit(accum);              // accumulators complete
             __syncwarp();
@@ -276,35 +285,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         if (warp < 6) {
             // ===================================================== converters: fp32 smem row -> (hi, lo) in TMEM
             for (int t = 0; t < T; ++t) {
-                const int s = t % TC_STAGES, ts = t % TC_TSTAGES;
-                const uint32_t ph = (t / TC_STAGES) & 1, tph = (t / TC_TSTAGES) & 1;
+                const int s = t % TC_STAGES;
+                const uint32_t ph = (t / TC_STAGES) & 1;
                 mbar_wait(&full[s], ph, 400 + t);
                 const float4* rowp = reinterpret_cast<const float4*>(a_raw(s) + row_in_tile * 128);
-                uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    // 128B swizzle: logical 16-byte chunk j of row r sits at physical chunk j ^ (r & 7); a quarter
-                    // warp (8 consecutive rows) therefore hits all 32 banks exactly once
-                    const float4 x = rowp[j ^ (row_in_tile & 7)];
-                    const float xv[4] = {x.x, x.y, x.z, x.w};
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t hl[32];   // this half k-block: [0,16) hi, [16,32) lo  -> one 32-column TMEM stage
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        uint32_t u;
-                        if (p.passes == 3) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(xv[e]));
-                        else u = __float_as_uint(xv[e]);
-                        hi[4 * j + e] = u;
-                        lo[4 * j + e] = __float_as_uint(xv[e] - __uint_as_float(u));
+                    for (int jj = 0; jj < 4; ++jj) {
+                        // 128B swizzle: logical 16-byte chunk j of row r sits at physical chunk j ^ (r & 7); a quarter
+                        // warp (8 consecutive rows) therefore hits all 32 banks exactly once
+                        const int j = 4 * h + jj;
+                        const float4 x = rowp[j ^ (row_in_tile & 7)];
+                        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint32_t u;
+                            if (p.passes == 3) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(xv[e]));
+                            else u = __float_as_uint(xv[e]);
+                            hl[4 * jj + e] = u;
+                            hl[16 + 4 * jj + e] = __float_as_uint(xv[e] - __uint_as_float(u));
+                        }
                     }
+                    if (h == 1) mbar_arrive(&a_free[s]);   // whole row is in registers: the A smem stage may be refilled
+                    const int ts = h;
+                    const uint32_t tph = t & 1;
+                    mbar_wait(&tfree[ts], tph ^ 1, 450 + t);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    tmem_st32(tmem + lane_addr + TC_COL_A + 32 * ts, hl);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&conv[ts]);
                 }
-                mbar_arrive(&a_free[s]);             // values are in registers: the A smem stage may be refilled
-                mbar_wait(&tfree[ts], tph ^ 1, 450 + t);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tcol = tmem + lane_addr + TC_COL_A + 64 * ts;
-                tmem_st32(tcol, hi);
-                if (p.passes == 3) tmem_st32(tcol + 32, lo);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(&conv[ts]);
             }
         }
         else {
@@ -581,8 +594,8 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     p.debug = dbg_env;
     static int mc_env = -1;
     if (mc_env < 0) { const char* e = getenv("FC_TC_MERGE_CORR"); mc_env = (e && e[0] == '1') ? 1 : 0; }
-    p.merge_corr = mc_env;
-    FC_REQUIRE(p.BN <= 192 && (p.BN & 15) == 0);
+    (void)mc_env; p.merge_corr = 0;   // (experiment retired: a single accumulator degraded full-depth parity 1.5x)
+    FC_REQUIRE(p.BN <= 96 && (p.BN & 15) == 0);
     FC_REQUIRE(a.ldk == (p.T1 + p.T2) * TC_BK);
     const int n_tiles = fc_tc_n_tiles(a.N);
     int m_tiles = (a.M + TC_BM - 1) / TC_BM;
@@ -605,7 +618,7 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         // 3 stages x (16 KB A + 2 x 24 KB W at BN=192) + 1 KB alignment slack; static smem (barriers) comes on top
-        FC_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FC_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         configured = true;
     }
     FcProfScope prof(FC_CLS_GEMM_TC, 2.0 * a.M * a.N * (a.K1 + a.K2),

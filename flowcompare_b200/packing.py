@@ -42,7 +42,7 @@ def gemm_kpad(k):
 
 # tcgen05 tiling (mirrors csrc/gemm.cuh fc_tc_*)
 def tc_n_tiles(n):
-    return (n + 191) // 192
+    return (n + 95) // 96
 
 
 def tc_bn(n):
