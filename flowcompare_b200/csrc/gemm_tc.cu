@@ -14,15 +14,22 @@
 // of the magnitude), and the one GEMM whose output is the latent itself (ActNorm+LinearLU) applies its
 // diagonal in fp32 in the epilogue (flow.cu), so the residual bias is below the fp32 noise of the reference.
 //
-// CTA = one 128 x BN output tile (BN <= 192, runtime), 10 warps:
+// CTA = one 128 x BN output tile (BN <= 96, runtime), 10 warps, TWO CTAs RESIDENT PER SM (93 registers, 81 KB of
+// shared memory and 256 of the 512 TMEM columns each), so that one CTA's epilogue (exact-erf GELU is ~45
+// instructions per element and issue-bound) runs under the other CTA's main loop:
 //   warp 0      TMA producer (one lane)
-//   warp 1      TMEM allocator + MMA issuer (one lane)
+//   warp 1      TMEM allocator + MMA issuer (whole warp loops, one elected lane issues: keeps UTCHMMA operands uniform)
 //   warps 2-5   converters (one thread per tile row) during the main loop, then epilogue
-//   warps 6-9   epilogue only (each TMEM lane quadrant is drained by two warps, alternating 16-column chunks)
-// TMEM (512 columns): [0,192) main accumulator | [192,384) compensation accumulator |
-//                     [384,512) two stages of A: 32 columns hi + 32 columns lo each.
-// Pipeline (mbarriers): full[s] (TMA bytes landed, 3 smem stages) -> converter -> a_free[s] (A smem reusable) and
-//   conv[ts] (A in TMEM stage ts ready) -> MMA -> tcgen05.commit -> w_free[s] (W smem reusable), tfree[ts].
+//   warps 6-9   prefetch the tile's bias row, then epilogue (each TMEM lane quadrant is drained by two warps)
+// TMEM (256 columns): [0,96) main accumulator | [96,192) compensation accumulator |
+//                     [192,256) two stages of A, each HALF a k-block: 16 columns hi + 16 columns lo.
+// Pipeline (mbarriers): full[s] (TMA bytes landed, 2 smem stages) -> converter -> a_free[s] (A smem reusable) and
+//   conv[ts] (A half-block in TMEM stage ts) -> MMA -> tcgen05.commit -> tfree[ts], w_free[s] (W smem reusable).
+// Global traffic of the epilogue goes through a per-warp shared-memory staging tile so it is coalesced.
+// What was measured and dropped (B200, see profiles/): a 4-accumulator split of the main product (no accuracy gain
+// once the compensation terms had their own accumulator), TMA multicast of the weight tile over clusters of 2/4
+// (no gain), one N=2*BN MMA for Ahi*[Whi;Wlo] (no gain), decoupled A/W rings (slower), 128x176 tiles with one
+// CTA per SM (epilogue not hidden: 16k of 42k cycles per tile).
 #include "gemm.cuh"
 #include <cuda.h>
 #include <cstdio>

@@ -362,3 +362,21 @@ def test_missing_extra_context_raises():
     cfg, fsd, esd, batch, e = _engine("tiny_dgcnn_attn_extra")
     with pytest.raises(fclib.FlowCompareError):
         e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV), None), eps=batch["eps"].to(DEV))
+
+
+@pytest.mark.parametrize("n_points", [2048, 4096])
+def test_point_count_sweep_matches_port(n_points):
+    """BASELINE configs[4] (point-count sweep): same architecture at Nc = N = 2k / 4k, 3 flow layers so the CPU
+    oracle finishes in seconds.  kNN bit-exact vs the canonical oracle, log-prob within north_star's 1e-3."""
+    cfg = configs.get_config("dgcnn_attn", n_flow_layers=3, sample_size=n_points, n_samples_context=n_points)
+    fsd, esd = spec.random_state_dicts(cfg, seed=31)
+    batch = spec.synthetic_batch(cfg, 1, seed=n_points)
+    e = eng.FlowCompareB200((fsd, esd), cfg, device=DEV, precision="tf32x3")
+    emb, idx = e.embed(batch["extract_0"].to(DEV), return_knn=True)
+    assert torch.equal(idx[0].cpu().long(), knn_ref.knn_self(batch["extract_0"], cfg["n_neighbors"]))
+    assert (idx[0, :, :, 0].cpu() == torch.arange(n_points)).all()      # nearest neighbour of a point is itself
+    want_emb, _ = port.dgcnn_embed(esd, batch["extract_0"], cfg["n_neighbors"], idx_list=[i.cpu().long() for i in idx])
+    assert (emb.cpu() - want_emb).abs().max().item() < 2e-5
+    want = port.flow_log_prob(fsd, configs.derive(cfg), batch["extract_1"], want_emb, None, batch["eps"])
+    got = e.log_prob(batch["extract_1"].to(DEV), emb, None, eps=batch["eps"].to(DEV))
+    assert (got.cpu() - want).abs().max().item() < 1e-3
