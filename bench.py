@@ -171,6 +171,27 @@ def workload_config(args, cfg, B, where):
             "where": where}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/r01_gemm_tc_ncu_full_summary.csv, made by scripts/ncu_summarize.py).  Static evidence, not
+    measured in this run: bench.py never runs under a profiler."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_tc_ncu_full_summary.csv")
+    try:
+        import csv
+        with open(path) as f:
+            row = next(csv.DictReader(f))
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for k, v in row.items():
+            if k.startswith("dram__bytes_read.sum") or k.startswith("dram__bytes_write.sum"):
+                tot += float(v) * mult[k[k.index("[") + 1:-1]]
+        return int(tot), ("ncu --set full, one gemm_tc_kernel launch M=65536 N=512 K=512 GELU (scripts/gemm_one.py): DRAM bytes of "
+                          "that launch; its algorithmic bytes are 4*(M*K + M*N) + 8*N*K = 270.5e6, i.e. no re-reads (L2 keeps "
+                          "part of the output)")
+    except Exception as exc:  # profile not present
+        return None, f"no committed ncu capture readable: {exc}"
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -286,9 +307,10 @@ def main():
         pk = peaks()
         top = 1 if ln_c[1] and ms_c[1] >= ms_c[0] else 0
         achieved = fl_c[top] / ms_c[top] / 1e9
+        traffic, traffic_note = ncu_traffic()
         roofline = {"kernel": CLASS_NAMES[top], "bound": "tensor", "achieved": round(achieved, 2),
                     "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_sustained"], 4),
-                    "traffic": None, "peak_source": pk["source"] + ", dense bf16 sustained",
+                    "traffic": traffic if top == 1 else None, "traffic_note": traffic_note, "peak_source": pk["source"] + ", dense bf16 sustained",
                     "note": "achieved = algorithmic 2*M*N*K flops of every launch of the class / summed CUDA-event time "
                             "in one instrumented step; fp32-faithful GEMMs cannot exceed TF32/3 ~ bf16/6 of this peak",
                     "avg_launch_ms": round(ms_c[top] / max(1, ln_c[top]), 4)}
