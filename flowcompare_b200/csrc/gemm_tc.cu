@@ -309,7 +309,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             uint32_t u;
-                            if (p.passes == 3) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(xv[e]));
+                            // cvt.rna.tf32.f32 by hand (add half a TF32 ulp to the magnitude, clear the low 13 bits):
+                            // 2 ALU ops instead of the 4 (add, inf test, select, mask) ptxas emits; inputs are finite
+                            if (p.passes == 3) u = (__float_as_uint(xv[e]) + 0x1000u) & 0xffffe000u;
                             else u = __float_as_uint(xv[e]);
                             hl[4 * jj + e] = u;
                             hl[16 + 4 * jj + e] = __float_as_uint(xv[e] - __uint_as_float(u));
@@ -360,9 +362,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         if (a.epi == FC_EPI_LNQ && row_ok) { mu = a.row_mu[row]; rstd = a.row_rstd[row]; }
         const float* bias_row = a.bias;
         if (a.bias && a.bias_group > 0 && row_ok) bias_row = a.bias + (size_t)(row / a.bias_group) * a.bias_ld;
-        // per-warp staging tile [32 rows][16 + 1 pad]; the pipeline stages are dead once `accum` has fired
-        float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 17);
+        // per-warp staging tile [32 rows][16 + 4 pad] (rows 16-byte aligned; a thread's own-row float4 accesses are
+        // conflict free, the transposed ones 2-way at worst); the pipeline stages are dead once `accum` has fired
+        float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 20);
         const int row0 = m0 + quad * 32;
+        const bool vec_base = row0 + 32 <= a.M && (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0;
+        const bool vec_res = a.res && (a.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0 &&
+                             (!a.res_scale || (reinterpret_cast<uintptr_t>(a.res_scale) & 15) == 0);
         long long d_ld = 0, d_math = 0, d_st = 0;
         for (int c0 = half * 16; c0 < BN; c0 += 32) {
             uint32_t r[16];
@@ -407,26 +413,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 // row, direct loads/stores touch 32 different lines per instruction (ncu: the residual layers took 2x
                 // as long as the plain ones).  Each warp instruction below moves 2 rows x 64 contiguous bytes.
                 const int sr = lane >> 4, sc = lane & 15;
+                // fast path (every full interior chunk): 16-byte accesses, 8 rows x 64 B per warp instruction, no
+                // per-element predicates or address arithmetic -- the scalar form below cost ~19 instructions per
+                // element, more than the GELU
+                const bool vec = vec_base && col + 16 <= a.N;
+                const int r8 = lane >> 2, c4 = (lane & 3) * 4;
+                float4* my_row4 = reinterpret_cast<float4*>(stg + lane * 20);
                 if (a.res) {
-                    float rx[16];   // all loads first, then all shared stores: no store->load ordering stalls
+                    if (vec && vec_res) {
+                        const float* rp = a.res + (size_t)(row0 + r8) * a.ldres + col + c4;
+                        float4 rx4[4];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int gr = row0 + 2 * i + sr;
-                        rx[i] = (gr < a.M && col + sc < a.N) ? __ldg(a.res + (size_t)gr * a.ldres + col + sc) : 0.f;
+                        for (int i = 0; i < 4; ++i) rx4[i] = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(8 * i) * a.ldres));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + (r8 + 8 * i) * 20 + c4) = rx4[i];
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 rv = my_row4[q];
+                            if (a.res_scale) {
+                                const float4 rs = *reinterpret_cast<const float4*>(a.res_scale + col + 4 * q);
+                                v[4 * q] = fmaf(rs.x, rv.x, v[4 * q]); v[4 * q + 1] = fmaf(rs.y, rv.y, v[4 * q + 1]);
+                                v[4 * q + 2] = fmaf(rs.z, rv.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(rs.w, rv.w, v[4 * q + 3]);
+                            } else {
+                                v[4 * q] += rv.x; v[4 * q + 1] += rv.y; v[4 * q + 2] += rv.z; v[4 * q + 3] += rv.w;
+                            }
+                        }
+                        __syncwarp();
+                    } else {
+                        float rx[16];   // all loads first, then all shared stores: no store->load ordering stalls
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int gr = row0 + 2 * i + sr;
+                            rx[i] = (gr < a.M && col + sc < a.N) ? __ldg(a.res + (size_t)gr * a.ldres + col + sc) : 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) stg[(2 * i + sr) * 20 + sc] = rx[i];
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float rv = stg[lane * 20 + j];
+                            if (col + j < a.N) v[j] = a.res_scale ? fmaf(a.res_scale[col + j], rv, v[j]) : v[j] + rv;
+                        }
+                        __syncwarp();
                     }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) stg[(2 * i + sr) * 17 + sc] = rx[i];
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float rv = stg[lane * 17 + j];
-                        if (col + j < a.N) v[j] = a.res_scale ? fmaf(a.res_scale[col + j], rv, v[j]) : v[j] + rv;
-                    }
-                    __syncwarp();
                 }
                 if (a.act == FC_ACT_GELU) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fc_gelu_erf(v[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = fc_gelu_erf_fast(v[j]);
                 } else if (a.act == FC_ACT_LRELU) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fc_leaky_relu02(v[j]);
@@ -437,15 +471,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 const long long q2 = clock64();
                 d_math += q2 - q1;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = v[j];
+                for (int q = 0; q < 4; ++q) my_row4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 __syncwarp();
-                float ox[16];
+                if (vec) {
+                    float* gp = a.C + (size_t)(row0 + r8) * a.ldc + col + c4;
+                    float4 ox4[4];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) ox[i] = stg[(2 * i + sr) * 17 + sc];
+                    for (int i = 0; i < 4; ++i) ox4[i] = *reinterpret_cast<const float4*>(stg + (r8 + 8 * i) * 20 + c4);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int gr = row0 + 2 * i + sr;
-                    if (gr < a.M && col + sc < a.N) a.C[(size_t)gr * a.ldc + col + sc] = ox[i];
+                    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(gp + (size_t)(8 * i) * a.ldc) = ox4[i];
+                } else {
+                    float ox[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) ox[i] = stg[(2 * i + sr) * 20 + sc];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int gr = row0 + 2 * i + sr;
+                        if (gr < a.M && col + sc < a.N) a.C[(size_t)gr * a.ldc + col + sc] = ox[i];
+                    }
                 }
                 __syncwarp();
                 d_st += clock64() - q2;
@@ -453,15 +496,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 // nothing: out-of-range rows of the coupling / augment epilogues
             } else if (a.epi == FC_EPI_COUPLING) {
                 // reference models/affine_coupling.py:40-46 (see gemm.cu for the arithmetic notes)
+                float* xrow = a.x + (size_t)row * a.ldx + a.col0 + (col >> 1);
+                if (col + 16 <= a.N && (reinterpret_cast<uintptr_t>(xrow) & 7) == 0) {
+                    // interior chunk: the row's 8 latent values move as four 8-byte accesses, loads first
+                    float2 xv[4];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (col + 2 * q + 1 < a.N) {
-                        const int j = (col >> 1) + q;
-                        const float sig = 1.0f / (1.0f + expf(-v[2 * q]));
-                        const float sc = (2.0f * sig - 1.0f) + 1.0f;
-                        float* xp = a.x + (size_t)row * a.ldx + a.col0 + j;
-                        *xp = fmaf(*xp, sc, v[2 * q + 1]);
-                        ldj += logf(sc);
+                    for (int q = 0; q < 4; ++q) xv[q] = *reinterpret_cast<const float2*>(xrow + 2 * q);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float sig0 = 1.0f / (1.0f + expf(-v[4 * q]));
+                        const float sc0 = (2.0f * sig0 - 1.0f) + 1.0f;
+                        const float sig1 = 1.0f / (1.0f + expf(-v[4 * q + 2]));
+                        const float sc1 = (2.0f * sig1 - 1.0f) + 1.0f;
+                        xv[q].x = fmaf(xv[q].x, sc0, v[4 * q + 1]);
+                        xv[q].y = fmaf(xv[q].y, sc1, v[4 * q + 3]);
+                        ldj += logf(sc0);
+                        ldj += logf(sc1);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float2*>(xrow + 2 * q) = xv[q];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (col + 2 * q + 1 < a.N) {
+                            const float sig = 1.0f / (1.0f + expf(-v[2 * q]));
+                            const float sc = (2.0f * sig - 1.0f) + 1.0f;
+                            float* xp = xrow + q;
+                            *xp = fmaf(*xp, sc, v[2 * q + 1]);
+                            ldj += logf(sc);
+                        }
                     }
                 }
             } else if (a.epi == FC_EPI_AUGMENT) {
