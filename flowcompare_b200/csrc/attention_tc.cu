@@ -1,0 +1,428 @@
+// Single-head cross attention on the 5th-gen tensor cores (tcgen05 + TMEM), fp32-faithful (3xTF32).
+// Replaces reference models/perceiver.py:108-115 (AttentionMine.forward: softmax(q k^T * scale) v) for
+// precision = tf32x3; attention_mma.cu (mma.sync) and attention.cu (exact fp32 SIMT) stay as the smaller twins.
+//
+// CTA = 128 queries of one cloud; the context cloud's keys are streamed in blocks of 64 (flash style, nothing of
+// size N x Nc is ever written).  Per key block i:
+//     S_i = Q K_i^T          24 tcgen05.mma (128x64x8, TF32):  Qlo*Khi + Qhi*Klo + Qhi*Khi     A = Q  in TMEM
+//     P_i = exp2(S_i - m_i)  one softmax thread per query row straight out of TMEM (no shuffles), split to hi/lo
+//     O_i = P_i V_i          24 tcgen05.mma:  Plo*Vhi + Phi*Vlo + Phi*Vhi                      A = P  in TMEM
+//     O   = O * alpha + O_i  in registers (fp32), so the tensor core never chains more than 24 accumulations
+// K and V arrive pre-split into TF32 hi/lo (kv_split_kernel below; V transposed to [dim][key] so that both MMAs
+// take K-major B operands through the same 128B-swizzle descriptors as the GEMM) by TMA into two 2-stage rings.
+//   warp 0      TMA producer            warp 1   TMEM allocator + MMA issuer (S_{i+1} is issued before P_i is awaited)
+//   warps 2-5   Q converter, softmax, O accumulation, output
+// TMEM (512 columns): Qhi [0,64) | Qlo [64,128) | S x2 [128,256) | Phi [256,320) | Plo [320,384) | O_i x2 [384,512).
+#include "common.cuh"
+#include "gemm.cuh"
+#include "tcgen05.cuh"
+#include <mutex>
+#include <vector>
+
+namespace {
+
+constexpr int AQ = 128;                 // queries per CTA
+constexpr int AK = 64;                  // keys per block
+constexpr int AD = 64;                  // head dim
+constexpr int A_THREADS = 192;
+constexpr int A_ATOM = 64 * 128;        // 64 rows x 128 B  (one swizzle atom of a 64-row tile)
+constexpr int A_TILE = 4 * A_ATOM;      // hi atom 0/1, lo atom 0/1 = 32 KB per K (or V) block
+constexpr int A_QBYTES = 2 * AQ * 128;  // raw fp32 Q tile: two atoms of 128 rows
+constexpr int A_STAGES = 2;
+constexpr int A_SMEM = A_QBYTES + 2 * A_STAGES * A_TILE + 1024;
+constexpr uint32_t C_QHI = 0, C_QLO = 64, C_S = 128, C_PHI = 256, C_PLO = 320, C_O = 384;
+
+struct AttnTcParams {
+    float* out; int ldo;
+    int N, Nc, nblk;
+    float scale;
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+
+// D[128 x 64] (+)= A[tmem, 64 columns of K] * B[64-row K-major tile: two 32-wide swizzle atoms], 3xTF32
+__device__ __forceinline__ void issue_3xtf32(uint32_t d, uint32_t a_hi, uint32_t a_lo, const unsigned char* b_tile, uint32_t idesc) {
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t atom = (uint32_t)(kk >> 2) * A_ATOM;
+        const uint64_t adv = (uint64_t)((kk & 3) * 32 >> 4);
+        const uint64_t dbh = make_kmajor_sw128_desc(smem_u32(b_tile + atom)) + adv;
+        const uint64_t dbl = make_kmajor_sw128_desc(smem_u32(b_tile + 2 * A_ATOM + atom)) + adv;
+        umma_tf32_ts(d, a_lo + 8 * kk, dbh, idesc, kk != 0);
+        umma_tf32_ts(d, a_hi + 8 * kk, dbl, idesc, 1);
+        umma_tf32_ts(d, a_hi + 8 * kk, dbh, idesc, 1);
+    }
+}
+
+__global__ void __launch_bounds__(A_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKhi,
+                    const __grid_constant__ CUtensorMap mapKlo, const __grid_constant__ CUtensorMap mapVhi,
+                    const __grid_constant__ CUtensorMap mapVlo, const AttnTcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 + 4 * A_STAGES + 10];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    unsigned char* q_raw = smem;
+    auto k_tile = [&](int s) { return smem + A_QBYTES + s * A_TILE; };
+    auto v_tile = [&](int s) { return smem + A_QBYTES + (A_STAGES + s) * A_TILE; };
+    uint64_t* qfull = bars;                   // Q tile landed
+    uint64_t* qready = bars + 1;              // Q hi/lo in TMEM                      (128 arrivals)
+    uint64_t* kfull = bars + 2;               // [A_STAGES]
+    uint64_t* kfree = kfull + A_STAGES;       // [A_STAGES] S MMAs retired
+    uint64_t* vfull = kfree + A_STAGES;       // [A_STAGES]
+    uint64_t* vfree = vfull + A_STAGES;       // [A_STAGES] PV MMAs retired
+    uint64_t* s_ready = vfree + A_STAGES;     // [2] S_i complete in TMEM
+    uint64_t* s_free = s_ready + 2;           // [2] softmax threads have S_i in registers (128 arrivals)
+    uint64_t* p_ready = s_free + 2;           // P_i hi/lo in TMEM                    (128 arrivals)
+    uint64_t* p_free = p_ready + 1;           // PV_i retired: P may be overwritten
+    uint64_t* o_ready = p_free + 1;           // [2] O_i complete in TMEM
+    uint64_t* o_free = o_ready + 2;           // [2] O_i read back                    (128 arrivals)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * AQ;
+    const int nblk = p.nblk;
+
+    if (threadIdx.x == 0) {
+        mbar_init(qfull, 1); mbar_init(qready, 128);
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(&kfull[s], 1); mbar_init(&kfree[s], 1); mbar_init(&vfull[s], 1); mbar_init(&vfree[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_ready[s], 1); mbar_init(&s_free[s], 128); mbar_init(&o_ready[s], 1); mbar_init(&o_free[s], 128); }
+        mbar_init(p_ready, 128); mbar_init(p_free, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(qfull, A_QBYTES);
+            tma_load_2d(&mapQ, q_raw, qfull, 0, b * p.N + q0);
+            tma_load_2d(&mapQ, q_raw + AQ * 128, qfull, 32, b * p.N + q0);
+            for (int i = 0; i < nblk; ++i) {
+                const int s = i % A_STAGES;
+                const uint32_t ph = (i / A_STAGES) & 1;
+                const int krow = b * p.Nc + i * AK;      // rows past this cloud are masked in the softmax
+                mbar_wait(&kfree[s], ph ^ 1, 100 + i);
+                mbar_expect_tx(&kfull[s], A_TILE);
+                tma_load_2d(&mapKhi, k_tile(s), &kfull[s], 0, krow);
+                tma_load_2d(&mapKhi, k_tile(s) + A_ATOM, &kfull[s], 32, krow);
+                tma_load_2d(&mapKlo, k_tile(s) + 2 * A_ATOM, &kfull[s], 0, krow);
+                tma_load_2d(&mapKlo, k_tile(s) + 3 * A_ATOM, &kfull[s], 32, krow);
+                mbar_wait(&vfree[s], ph ^ 1, 150 + i);
+                mbar_expect_tx(&vfull[s], A_TILE);
+                tma_load_3d(&mapVhi, v_tile(s), &vfull[s], i * AK, 0, b);            // keys past Nc: zero fill
+                tma_load_3d(&mapVhi, v_tile(s) + A_ATOM, &vfull[s], i * AK + 32, 0, b);
+                tma_load_3d(&mapVlo, v_tile(s) + 2 * A_ATOM, &vfull[s], i * AK, 0, b);
+                tma_load_3d(&mapVlo, v_tile(s) + 3 * A_ATOM, &vfull[s], i * AK + 32, 0, b);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (whole warp loops, one elected lane issues)
+        // instruction descriptor: D=f32, A=B=tf32, K-major, N=64 (>>3 at bit 17), M=128 (>>4 at bit 24)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AK >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
+        mbar_wait(qready, 0, 200);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        mbar_wait(&kfull[0], 0, 201);
+        if (elect_one()) {
+            issue_3xtf32(tmem + C_S, tmem + C_QHI, tmem + C_QLO, k_tile(0), idesc);
+            umma_commit(&s_ready[0]);
+            umma_commit(&kfree[0]);
+        }
+        __syncwarp();
+        for (int i = 0; i < nblk; ++i) {
+            if (i + 1 < nblk) {
+                const int j = i + 1, ks = j % A_STAGES, sb = j & 1;
+                mbar_wait(&kfull[ks], (j / A_STAGES) & 1, 210 + i);
+                mbar_wait(&s_free[sb], ((j >> 1) & 1) ^ 1, 220 + i);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    issue_3xtf32(tmem + C_S + 64 * sb, tmem + C_QHI, tmem + C_QLO, k_tile(ks), idesc);
+                    umma_commit(&s_ready[sb]);
+                    umma_commit(&kfree[ks]);
+                }
+                __syncwarp();
+            }
+            const int vs = i % A_STAGES, ob = i & 1;
+            mbar_wait(&vfull[vs], (i / A_STAGES) & 1, 230 + i);
+            mbar_wait(&o_free[ob], ((i >> 1) & 1) ^ 1, 240 + i);
+            mbar_wait(p_ready, i & 1, 250 + i);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                issue_3xtf32(tmem + C_O + 64 * ob, tmem + C_PHI, tmem + C_PLO, v_tile(vs), idesc);
+                umma_commit(&o_ready[ob]);
+                umma_commit(p_free);
+                umma_commit(&vfree[vs]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================================================== Q converter + softmax + O accumulation (one thread per row)
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const float LOG2E = 1.4426950408889634f;
+
+        // ---- Q: fp32 smem row -> scale -> (hi, lo) in TMEM
+        mbar_wait(qfull, 0, 300);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {          // 16 dims per step
+            uint32_t hi[16], lo[16];
+            const unsigned char* atom = q_raw + (c >> 1) * (AQ * 128) + r * 128;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = (c & 1) * 4 + jj;                       // 16-byte chunk inside the 128-byte row
+                const float4 x = *reinterpret_cast<const float4*>(atom + ((j ^ (r & 7)) << 4));
+                const float xv[4] = {x.x * p.scale, x.y * p.scale, x.z * p.scale, x.w * p.scale};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    hi[4 * jj + e] = tf32_hi(xv[e]);
+                    lo[4 * jj + e] = __float_as_uint(xv[e] - __uint_as_float(hi[4 * jj + e]));
+                }
+            }
+            tmem_st16(tmem + lane_addr + C_QHI + 16 * c, hi);
+            tmem_st16(tmem + lane_addr + C_QLO + 16 * c, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(qready);
+
+        float o[AD];
+#pragma unroll
+        for (int j = 0; j < AD; ++j) o[j] = 0.f;
+        float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+
+        for (int i = 0; i < nblk; ++i) {
+            const int sb = i & 1;
+            float sv[AK];
+            mbar_wait(&s_ready[sb], (i >> 1) & 1, 310 + i);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {
+                uint32_t t32[32];
+                tmem_ld32(tmem + lane_addr + C_S + 64 * sb, t32);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(t32[j]);
+                tmem_ld32(tmem + lane_addr + C_S + 64 * sb + 32, t32);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sv[32 + j] = __uint_as_float(t32[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&s_free[sb]);
+            const int valid = p.Nc - i * AK;          // keys of this block that exist
+            if (valid < AK) {
+#pragma unroll
+                for (int j = 0; j < AK; ++j) if (j >= valid) sv[j] = -INFINITY;
+            }
+            float mx = sv[0];
+#pragma unroll
+            for (int j = 1; j < AK; ++j) mx = fmaxf(mx, sv[j]);
+            const float m_new = fmaxf(m, mx);
+            const float alpha = ex2_approx((m - m_new) * LOG2E);   // first block: exp2(-inf) = 0
+            const float mc = m_new * LOG2E;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < AK; ++j) { sv[j] = ex2_approx(fmaf(sv[j], LOG2E, -mc)); sum += sv[j]; }
+            l = fmaf(l, alpha, sum);
+            m = m_new;
+
+            // P -> TMEM (hi, lo); the previous block's PV MMAs must have retired
+            mbar_wait(p_free, (i & 1) ^ 1, 330 + i);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    hi[j] = tf32_hi(sv[16 * c + j]);
+                    lo[j] = __float_as_uint(sv[16 * c + j] - __uint_as_float(hi[j]));
+                }
+                tmem_st16(tmem + lane_addr + C_PHI + 16 * c, hi);
+                tmem_st16(tmem + lane_addr + C_PLO + 16 * c, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(p_ready);
+
+            // fold in the PREVIOUS block's O (its MMAs ran while this block's softmax was computed)
+            if (i > 0) {
+                const int ob = (i - 1) & 1;
+                mbar_wait(&o_ready[ob], ((i - 1) >> 1) & 1, 350 + i);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t t32[32];
+                tmem_ld32(tmem + lane_addr + C_O + 64 * ob, t32);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = fmaf(o[j], alpha_prev, __uint_as_float(t32[j]));
+                tmem_ld32(tmem + lane_addr + C_O + 64 * ob + 32, t32);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[32 + j] = fmaf(o[32 + j], alpha_prev, __uint_as_float(t32[j]));
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&o_free[ob]);
+            }
+            alpha_prev = alpha;
+        }
+        {
+            const int ob = (nblk - 1) & 1;
+            mbar_wait(&o_ready[ob], ((nblk - 1) >> 1) & 1, 390);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t t32[32];
+            tmem_ld32(tmem + lane_addr + C_O + 64 * ob, t32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = fmaf(o[j], alpha_prev, __uint_as_float(t32[j]));
+            tmem_ld32(tmem + lane_addr + C_O + 64 * ob + 32, t32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[32 + j] = fmaf(o[32 + j], alpha_prev, __uint_as_float(t32[j]));
+        }
+        if (q0 + r < p.N) {
+            const float inv = 1.0f / l;
+            float4* dst = reinterpret_cast<float4*>(p.out + ((size_t)b * p.N + q0 + r) * p.ldo);
+#pragma unroll
+            for (int j = 0; j < AD / 4; ++j)
+                dst[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    }
+}
+
+// kv [B*Nc][ldkv] (K = columns 0..63, V = 64..127)  ->  Khi, Klo [B*Nc][64]  and  Vt hi, lo [B][64][Ncp] (TF32 splits)
+__global__ void __launch_bounds__(256)
+kv_split_kernel(const float* __restrict__ kv, int ldkv, int Nc, int Ncp, float* __restrict__ khi, float* __restrict__ klo,
+                float* __restrict__ vthi, float* __restrict__ vtlo) {
+    __shared__ float tile[32][AD + 1];
+    const int b = blockIdx.y, key0 = blockIdx.x * 32, tid = threadIdx.x;
+    for (int idx = tid; idx < 32 * AD; idx += 256) {
+        const int kk = idx >> 6, d = idx & 63;
+        const int key = key0 + kk;
+        if (key < Nc) {
+            const float* src = kv + ((size_t)b * Nc + key) * ldkv;
+            const float x = src[d];
+            const float h = __uint_as_float(tf32_hi(x));
+            khi[((size_t)b * Nc + key) * AD + d] = h;
+            klo[((size_t)b * Nc + key) * AD + d] = x - h;
+            tile[kk][d] = src[AD + d];
+        } else {
+            tile[kk][d] = 0.f;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 32 * AD; idx += 256) {
+        const int d = idx >> 5, kk = idx & 31;
+        const int key = key0 + kk;
+        if (key < Ncp) {
+            const float x = tile[kk][d];
+            const float h = __uint_as_float(tf32_hi(x));
+            vthi[((size_t)b * AD + d) * Ncp + key] = h;
+            vtlo[((size_t)b * AD + d) * Ncp + key] = x - h;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- host: tensor maps (cached)
+struct AMapKey {
+    const void* base; uint64_t d0, d1, d2, s1, s2; uint32_t b0, b1;
+    bool operator==(const AMapKey& o) const {
+        return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 && b0 == o.b0 && b1 == o.b1;
+    }
+};
+std::vector<std::pair<AMapKey, CUtensorMap>> g_amaps;
+std::mutex g_amaps_mu;
+
+// fp32 tensor, dims (d0 fastest, d1, d2), strides in floats of d1 / d2, box = b0 x b1 x 1, 128B swizzle, OOB -> 0
+bool get_amap(const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2, uint32_t b0, uint32_t b1,
+              CUtensorMap* out) {
+    AMapKey key{base, d0, d1, d2, s1, s2, b0, b1};
+    std::lock_guard<std::mutex> lk(g_amaps_mu);
+    for (auto& kv : g_amaps) if (kv.first == key) { *out = kv.second; return true; }
+    FcEncodeTiledFn enc = fc_get_encode_fn();
+    if (!enc) return false;
+    const cuuint32_t rank = d2 > 0 ? 3 : 2;
+    cuuint64_t dims[3] = {d0, d1, d2 > 0 ? d2 : 1};
+    cuuint64_t strides[2] = {s1 * 4, s2 * 4};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap m;
+    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (g_amaps.size() > 256) g_amaps.clear();
+    g_amaps.emplace_back(key, m);
+    *out = m;
+    return true;
+}
+
+}  // namespace
+
+int64_t fc_attention_tc_scratch_floats(int B, int Nc) {
+    const int64_t Ncp = fc_round_up(Nc, 4);
+    return 2 * (int64_t)B * Nc * AD + 2 * (int64_t)B * AD * Ncp + 64;
+}
+
+int fc_launch_cross_attention_tc(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo, int B, int N,
+                                 int Nc, int d, float scale, float* scratch, cudaStream_t stream) {
+    FC_REQUIRE(q && kv && out && scratch && B > 0 && N > 0 && Nc > 0);
+    if (d != AD) return FC_ERR_UNSUPPORTED;
+    FC_REQUIRE((ldq & 3) == 0 && (ldo & 3) == 0 && ldkv >= 2 * AD && ldq >= AD && ldo >= AD && B <= 65535);
+    FC_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(scratch) & 127) == 0);
+    const int Ncp = fc_round_up(Nc, 4);
+    float* khi = scratch;
+    float* klo = khi + fc_round_up_ll((int64_t)B * Nc * AD, 32);
+    float* vthi = klo + fc_round_up_ll((int64_t)B * Nc * AD, 32);
+    float* vtlo = vthi + (int64_t)B * AD * Ncp;
+    CUtensorMap mQ, mKh, mKl, mVh, mVl;
+    if (!get_amap(q, AD, (uint64_t)B * N, 0, (uint64_t)ldq, 0, 32, AQ, &mQ)) return FC_ERR_CUDA;
+    if (!get_amap(khi, AD, (uint64_t)B * Nc, 0, AD, 0, 32, AK, &mKh)) return FC_ERR_CUDA;
+    if (!get_amap(klo, AD, (uint64_t)B * Nc, 0, AD, 0, 32, AK, &mKl)) return FC_ERR_CUDA;
+    if (!get_amap(vthi, (uint64_t)Nc, AD, (uint64_t)B, (uint64_t)Ncp, (uint64_t)AD * Ncp, 32, AD, &mVh)) return FC_ERR_CUDA;
+    if (!get_amap(vtlo, (uint64_t)Nc, AD, (uint64_t)B, (uint64_t)Ncp, (uint64_t)AD * Ncp, 32, AD, &mVl)) return FC_ERR_CUDA;
+    static bool configured = false;
+    if (!configured) {
+        FC_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
+        configured = true;
+    }
+    FcProfScope prof(FC_CLS_ATTENTION, 4.0 * B * (double)N * Nc * d, 4.0 * B * ((double)N * d * 2 + (double)Nc * d * 2), stream);
+    kv_split_kernel<<<dim3((Ncp + 31) / 32, B), 256, 0, stream>>>(kv, ldkv, Nc, Ncp, khi, klo, vthi, vtlo);
+    fc_count_launch();
+    AttnTcParams p{out, ldo, N, Nc, (Nc + AK - 1) / AK, scale};
+    attention_tc_kernel<<<dim3((N + AQ - 1) / AQ, B), A_THREADS, A_SMEM, stream>>>(mQ, mKh, mKl, mVh, mVl, p);
+    fc_count_launch();
+    FC_LAUNCH_OK();
+    return FC_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t fc_cross_attention_tc_scratch_bytes(int B, int Nc) {
+    if (B <= 0 || Nc <= 0) return FC_ERR_INVALID_ARG;
+    return fc_attention_tc_scratch_floats(B, Nc) * 4;
+}
+
+extern "C" __attribute__((visibility("default"))) int fc_cross_attention_tc(const float* q, int ldq, const float* kv, int ldkv,
+                                                                             float* out, int ldo, int B, int N, int Nc, int d,
+                                                                             float scale, void* scratch, int64_t scratch_bytes,
+                                                                             fc_stream_t stream) {
+    FC_REQUIRE(scratch && scratch_bytes >= fc_cross_attention_tc_scratch_bytes(B, Nc));
+    return fc_launch_cross_attention_tc(q, ldq, kv, ldkv, out, ldo, B, N, Nc, d, scale, static_cast<float*>(scratch),
+                                        (cudaStream_t)stream);
+}

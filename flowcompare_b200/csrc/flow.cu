@@ -13,6 +13,7 @@
 //   ActNorm + LinearLU folded into one 300x300 GEMM (act_norm.py:37-43, permuters.py:164-169)     1 GEMM
 // The running log-det never leaves fp32 registers/partials until the final reduction.
 #include "model.cuh"
+#include <cstdlib>
 #include <new>
 
 namespace {
@@ -199,7 +200,7 @@ extern "C" void fc_flow_destroy(fc_flow* f) {
 // ------------------------------------------------------------------------------------------ workspace
 namespace {
 struct FlowWs {
-    float *lat0, *lat1, *hA, *hB, *hC, *q, *o, *mu, *rstd, *cpart, *apart, *kv, *cb, *cbA;
+    float *lat0, *lat1, *hA, *hB, *hC, *q, *o, *mu, *rstd, *cpart, *apart, *kv, *kvs, *cb, *cbA;
     int ldx, ldh, n_cpart, n_apart, cb_ld, cbA_ld;
     int64_t total_bytes;
 };
@@ -225,6 +226,7 @@ FlowWs carve_flow_ws(const fc_flow* f, int B, int N, int Nc, void* base) {
     w.mu = take(M); w.rstd = take(M);
     w.cpart = take(M * w.n_cpart); w.apart = take(M * w.n_apart);
     w.kv = take((int64_t)B * Nc * 128);
+    w.kvs = take(fc_attention_tc_scratch_floats(B, Nc));   // TF32 hi/lo copies of k, v^T for the tcgen05 attention
     w.cb = take((int64_t)B * w.cb_ld);
     w.cbA = take((int64_t)B * w.cbA_ld);
     w.total_bytes = off;
@@ -264,8 +266,12 @@ static int run_attention_block(const fc_flow* f, const FcMlp& pre, const FcAttn&
     if (rc) return rc;
     // reference models/perceiver.py:104: scale = inner_dim ** -0.5
     const float scale = 1.0f / sqrtf((float)f->inner);
-    if (precision == 1)
-        return fc_launch_cross_attention_mma(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
+    if (precision == 1) {
+        static int use_mma = -1;   // FC_ATTN=mma: the warp-level MMA kernel (A/B runs)
+        if (use_mma < 0) { const char* e = getenv("FC_ATTN"); use_mma = (e && e[0] == 'm') ? 1 : 0; }
+        if (use_mma) return fc_launch_cross_attention_mma(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
+        return fc_launch_cross_attention_tc(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, w.kvs, s);
+    }
     return fc_launch_cross_attention(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
 }
 

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflowcompare_b200.so")
+# FLOWCOMPARE_B200_LIB: another build of the same library (kernel A/B experiments, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("FLOWCOMPARE_B200_LIB") or os.path.join(_HERE, "libflowcompare_b200.so")
 
 FC_OK = 0
 ERRORS = {0: "FC_OK", -1: "FC_ERR_INVALID_ARG", -2: "FC_ERR_CUDA", -3: "FC_ERR_LAUNCH",
@@ -31,6 +32,8 @@ SIGNATURES = {
     "fc_edgeconv_gather_max": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "fc_cross_attention": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_vp]),
     "fc_cross_attention_tf32x3": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_vp]),
+    "fc_cross_attention_tc_scratch_bytes": (c_i64, [c_int, c_int]),
+    "fc_cross_attention_tc": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_vp, c_i64, c_vp]),
     "fc_flow_create": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_i64, ctypes.POINTER(c_vp)]),
     "fc_flow_destroy": (None, [c_vp]),
     "fc_flow_workspace_bytes": (c_i64, [c_vp, c_int, c_int, c_int]),

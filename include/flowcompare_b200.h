@@ -98,9 +98,16 @@ FC_API int fc_edgeconv_gather_max(const float* PQ, int ldpq, const int32_t* idx,
 FC_API int fc_cross_attention(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
                        int B, int N, int Nc, int d, float scale, fc_stream_t stream);
 
-/* Same product on the tensor cores (3xTF32 warp-level MMA, flash style); used when precision = 1.       */
+/* Same product on the tensor cores with warp-level MMA (mma.sync 3xTF32, flash style).                  */
 FC_API int fc_cross_attention_tf32x3(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
                               int B, int N, int Nc, int d, float scale, fc_stream_t stream);
+
+/* Same product on the 5th-gen tensor cores (tcgen05 + TMEM, 3xTF32); the one the flow uses when precision = 1.
+ * Needs caller-provided device scratch (TF32 hi/lo copies of k and of v transposed), 128-byte aligned.  */
+FC_API int64_t fc_cross_attention_tc_scratch_bytes(int B, int Nc);
+FC_API int fc_cross_attention_tc(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
+                          int B, int N, int Nc, int d, float scale, void* scratch, int64_t scratch_bytes,
+                          fc_stream_t stream);
 
 /* ------------------------------------------------------------------ model handles ---------
  * A model is described by (header int32[], table int64[], arena fp32[] on the device), produced by

@@ -1,0 +1,32 @@
+"""Per-CTA phase cycle counts of the tcgen05 GEMM (FC_TC_DEBUG=1): setup / main loop / epilogue (tmem ld, math, stores)."""
+import ctypes, math, os, sys
+os.environ["FC_TC_DEBUG"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from flowcompare_b200 import lib as fclib, packing
+
+lib = fclib.load()
+lib.fc_debug_tc_phases.argtypes = [ctypes.c_void_p]
+shapes = [(32768, 512, 512, 1), (32768, 512, 512, 0), (32768, 256, 256, 1), (32768, 256, 150, 1), (32768, 64, 256, 0), (32768, 300, 300, 0)]
+for (M, N, K, act) in shapes:
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(M, (K + 3) // 4 * 4, generator=g).cuda()
+    rows, ldk = packing.tc_n_tiles(N) * packing.tc_bn(N), packing.tc_kpad(K)
+    W32 = torch.zeros(rows, ldk); W32[:N, :K] = torch.randn(N, K, generator=g) / math.sqrt(K)
+    hi = packing.tf32_round(W32); lo = packing.tf32_round(W32 - hi)
+    hi, lo, b = hi.cuda(), lo.cuda(), torch.randn(N, generator=g).cuda()
+    C = torch.empty(M, N, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    def run():
+        rc = lib.fc_gemm_tf32x3(A.data_ptr(), A.shape[1], hi.data_ptr(), lo.data_ptr(), ldk, b.data_ptr(), C.data_ptr(), N, M, N, K, act, st)
+        assert rc == 0
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    out = (ctypes.c_ulonglong * 8)()
+    lib.fc_debug_tc_phases(out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(); e1.record(); torch.cuda.synchronize()
+    lib.fc_debug_tc_phases(out)
+    n = max(1, out[0])
+    print(f"M={M} N={N} K={K} act={act} BN={packing.tc_bn(N)} ctas={out[0]} us={e0.elapsed_time(e1)*1e3:.1f} per-CTA cycles: setup={out[3]/n:.0f} "
+          f"mainloop={out[1]/n:.0f} epilogue={out[2]/n:.0f} (tmem_ld={out[4]/n:.0f} math={out[5]/n:.0f} store={out[6]/n:.0f})", flush=True)
