@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tcgen05.cuh"
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -24,7 +25,10 @@ namespace {
 constexpr int AQ = 128;                 // queries per CTA
 constexpr int AK = 64;                  // keys per block
 constexpr int AD = 64;                  // head dim
-constexpr int A_THREADS = 192;
+#ifndef A_SPL
+#define A_SPL 2                        // softmax threads per query row (1, 2 or 4)
+#endif
+constexpr int A_THREADS = 64 + 128 * A_SPL;
 constexpr int A_ATOM = 64 * 128;        // 64 rows x 128 B  (one swizzle atom of a 64-row tile)
 constexpr int A_TILE = 4 * A_ATOM;      // hi atom 0/1, lo atom 0/1 = 32 KB per K (or V) block
 constexpr int A_QBYTES = 2 * AQ * 128;  // raw fp32 Q tile: two atoms of 128 rows
@@ -36,6 +40,8 @@ struct AttnTcParams {
     float* out; int ldo;
     int N, Nc, nblk;
     float scale;
+    int debug;
+    int dbg_loads;   // experiment: 1 = skip the lo tiles' loads (timing only, wrong results)
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -65,6 +71,18 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t d, uint32_t a_hi, uint32_t
     }
 }
 
+// debug (FC_ATTN_DEBUG=1): cycles [0] CTAs [1] total [2..6] MMA warp waits kfull,s_free,vfull,o_free,p_ready
+//   [7..9] softmax thread waits s_ready,p_free,o_ready [10] softmax total [11] Q phase
+__device__ unsigned long long fc_attn_dbg[16];
+#ifndef A_PHASE_TIMERS
+#define A_PHASE_TIMERS 0
+#endif
+#if A_PHASE_TIMERS
+#define DBG_T(var) const long long var = p.debug ? clock64() : 0
+#else
+#define DBG_T(var) const long long var = 0
+#endif
+
 __global__ void __launch_bounds__(A_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKhi,
                     const __grid_constant__ CUtensorMap mapKlo, const __grid_constant__ CUtensorMap mapVhi,
@@ -72,6 +90,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 + 4 * A_STAGES + 10];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float mx_sm[2][A_SPL][AQ];     // row-maximum exchange between the threads of a row (by block parity)
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -97,10 +116,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     const int nblk = p.nblk;
 
     if (threadIdx.x == 0) {
-        mbar_init(qfull, 1); mbar_init(qready, 128);
+        mbar_init(qfull, 1); mbar_init(qready, 128 * A_SPL);
         for (int s = 0; s < A_STAGES; ++s) { mbar_init(&kfull[s], 1); mbar_init(&kfree[s], 1); mbar_init(&vfull[s], 1); mbar_init(&vfree[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_ready[s], 1); mbar_init(&s_free[s], 128); mbar_init(&o_ready[s], 1); mbar_init(&o_free[s], 128); }
-        mbar_init(p_ready, 128); mbar_init(p_free, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_ready[s], 1); mbar_init(&s_free[s], 128 * A_SPL); mbar_init(&o_ready[s], 1); mbar_init(&o_free[s], 128 * A_SPL); }
+        mbar_init(p_ready, 128 * A_SPL); mbar_init(p_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -123,25 +142,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                 const uint32_t ph = (i / A_STAGES) & 1;
                 const int krow = b * p.Nc + i * AK;      // rows past this cloud are masked in the softmax
                 mbar_wait(&kfree[s], ph ^ 1, 100 + i);
-                mbar_expect_tx(&kfull[s], A_TILE);
+                mbar_expect_tx(&kfull[s], p.dbg_loads ? A_TILE / 2 : A_TILE);
                 tma_load_2d(&mapKhi, k_tile(s), &kfull[s], 0, krow);
                 tma_load_2d(&mapKhi, k_tile(s) + A_ATOM, &kfull[s], 32, krow);
+                if (!p.dbg_loads) {
                 tma_load_2d(&mapKlo, k_tile(s) + 2 * A_ATOM, &kfull[s], 0, krow);
                 tma_load_2d(&mapKlo, k_tile(s) + 3 * A_ATOM, &kfull[s], 32, krow);
+                }
                 mbar_wait(&vfree[s], ph ^ 1, 150 + i);
-                mbar_expect_tx(&vfull[s], A_TILE);
+                mbar_expect_tx(&vfull[s], p.dbg_loads ? A_TILE / 2 : A_TILE);
                 tma_load_3d(&mapVhi, v_tile(s), &vfull[s], i * AK, 0, b);            // keys past Nc: zero fill
                 tma_load_3d(&mapVhi, v_tile(s) + A_ATOM, &vfull[s], i * AK + 32, 0, b);
+                if (!p.dbg_loads) {
                 tma_load_3d(&mapVlo, v_tile(s) + 2 * A_ATOM, &vfull[s], i * AK, 0, b);
                 tma_load_3d(&mapVlo, v_tile(s) + 3 * A_ATOM, &vfull[s], i * AK + 32, 0, b);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer (whole warp loops, one elected lane issues)
         // instruction descriptor: D=f32, A=B=tf32, K-major, N=64 (>>3 at bit 17), M=128 (>>4 at bit 24)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AK >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
+        long long w_kfull = 0, w_sfree = 0, w_vfull = 0, w_ofree = 0, w_pready = 0;
+        DBG_T(t_start);
         mbar_wait(qready, 0, 200);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        DBG_T(t_q);
         mbar_wait(&kfull[0], 0, 201);
         if (elect_one()) {
             issue_3xtf32(tmem + C_S, tmem + C_QHI, tmem + C_QLO, k_tile(0), idesc);
@@ -152,8 +178,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         for (int i = 0; i < nblk; ++i) {
             if (i + 1 < nblk) {
                 const int j = i + 1, ks = j % A_STAGES, sb = j & 1;
+                DBG_T(c0);
                 mbar_wait(&kfull[ks], (j / A_STAGES) & 1, 210 + i);
+                DBG_T(c1);
                 mbar_wait(&s_free[sb], ((j >> 1) & 1) ^ 1, 220 + i);
+                DBG_T(c2);
+                w_kfull += c1 - c0; w_sfree += c2 - c1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     issue_3xtf32(tmem + C_S + 64 * sb, tmem + C_QHI, tmem + C_QLO, k_tile(ks), idesc);
@@ -163,9 +193,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                 __syncwarp();
             }
             const int vs = i % A_STAGES, ob = i & 1;
+            DBG_T(c3);
             mbar_wait(&vfull[vs], (i / A_STAGES) & 1, 230 + i);
+            DBG_T(c4);
             mbar_wait(&o_free[ob], ((i >> 1) & 1) ^ 1, 240 + i);
+            DBG_T(c5);
             mbar_wait(p_ready, i & 1, 250 + i);
+            DBG_T(c6);
+            w_vfull += c4 - c3; w_ofree += c5 - c4; w_pready += c6 - c5;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 issue_3xtf32(tmem + C_O + 64 * ob, tmem + C_PHI, tmem + C_PLO, v_tile(vs), idesc);
@@ -175,22 +210,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             }
             __syncwarp();
         }
+        if (A_PHASE_TIMERS && p.debug && lane == 0) {
+            atomicAdd(&fc_attn_dbg[0], 1ull);
+            atomicAdd(&fc_attn_dbg[1], (unsigned long long)(clock64() - t_start));
+            atomicAdd(&fc_attn_dbg[2], (unsigned long long)w_kfull); atomicAdd(&fc_attn_dbg[3], (unsigned long long)w_sfree);
+            atomicAdd(&fc_attn_dbg[4], (unsigned long long)w_vfull); atomicAdd(&fc_attn_dbg[5], (unsigned long long)w_ofree);
+            atomicAdd(&fc_attn_dbg[6], (unsigned long long)w_pready); atomicAdd(&fc_attn_dbg[11], (unsigned long long)(t_q - t_start));
+        }
     } else {
-        // ===================================================== Q converter + softmax + O accumulation (one thread per row)
+        // ===================================================== Q converter + softmax + O accumulation
+        // A_SPL threads per query row (in the A_SPL warps that may touch the row's TMEM lane quadrant): each owns
+        // 64/A_SPL keys of every block and 64/A_SPL output dims.  Only the block's row maximum is exchanged (shared
+        // memory + one named barrier per quadrant); the partial row sums are combined once at the end.
+        constexpr int KS = AK / A_SPL;            // keys (and output dims) per thread
         const int quad = warp & 3;
+        const int sub = (warp - 2) >> 2;
         const int r = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const int off = sub * KS;                 // first key of the block / first output dim of this thread
         const float LOG2E = 1.4426950408889634f;
+        const int bar_id = 1 + quad;
 
-        // ---- Q: fp32 smem row -> scale -> (hi, lo) in TMEM
+        // ---- Q: fp32 smem row -> scale -> (hi, lo) in TMEM   (dims [off, off + KS))
         mbar_wait(qfull, 0, 300);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {          // 16 dims per step
+        for (int c = 0; c < KS / 16; ++c) {
             uint32_t hi[16], lo[16];
-            const unsigned char* atom = q_raw + (c >> 1) * (AQ * 128) + r * 128;
+            const int d0 = off + 16 * c;
+            const unsigned char* atom = q_raw + (d0 >> 5) * (AQ * 128) + r * 128;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                const int j = (c & 1) * 4 + jj;                       // 16-byte chunk inside the 128-byte row
+                const int j = ((d0 & 31) >> 2) + jj;                  // 16-byte chunk inside the 128-byte row
                 const float4 x = *reinterpret_cast<const float4*>(atom + ((j ^ (r & 7)) << 4));
                 const float xv[4] = {x.x * p.scale, x.y * p.scale, x.z * p.scale, x.w * p.scale};
 #pragma unroll
@@ -199,64 +249,81 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                     lo[4 * jj + e] = __float_as_uint(xv[e] - __uint_as_float(hi[4 * jj + e]));
                 }
             }
-            tmem_st16(tmem + lane_addr + C_QHI + 16 * c, hi);
-            tmem_st16(tmem + lane_addr + C_QLO + 16 * c, lo);
+            tmem_st16(tmem + lane_addr + C_QHI + d0, hi);
+            tmem_st16(tmem + lane_addr + C_QLO + d0, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(qready);
 
-        float o[AD];
+        float o[KS];
 #pragma unroll
-        for (int j = 0; j < AD; ++j) o[j] = 0.f;
+        for (int j = 0; j < KS; ++j) o[j] = 0.f;
         float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
 
+        auto load_cols = [&](uint32_t col, float (&dst)[KS]) {
+#pragma unroll
+            for (int c = 0; c < KS / 16; ++c) {
+                uint32_t t16[16];
+                tmem_ld16(tmem + lane_addr + col + 16 * c, t16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[16 * c + j] = __uint_as_float(t16[j]);
+            }
+        };
+
+        long long w_sready = 0, w_pfree = 0, w_oready = 0;
+        DBG_T(t_sm0);
         for (int i = 0; i < nblk; ++i) {
             const int sb = i & 1;
-            float sv[AK];
+            float sv[KS];
+            DBG_T(d0);
             mbar_wait(&s_ready[sb], (i >> 1) & 1, 310 + i);
+            DBG_T(d1);
+            w_sready += d1 - d0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            {
-                uint32_t t32[32];
-                tmem_ld32(tmem + lane_addr + C_S + 64 * sb, t32);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(t32[j]);
-                tmem_ld32(tmem + lane_addr + C_S + 64 * sb + 32, t32);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sv[32 + j] = __uint_as_float(t32[j]);
-            }
+            load_cols(C_S + 64 * sb + off, sv);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&s_free[sb]);
-            const int valid = p.Nc - i * AK;          // keys of this block that exist
-            if (valid < AK) {
+            const int valid = p.Nc - i * AK - off;    // of this thread's keys, how many exist
+            if (valid < KS) {
 #pragma unroll
-                for (int j = 0; j < AK; ++j) if (j >= valid) sv[j] = -INFINITY;
+                for (int j = 0; j < KS; ++j) if (j >= valid) sv[j] = -INFINITY;
             }
-            float mx = sv[0];
+            float mx4[4] = {sv[0], sv[1], sv[2], sv[3]};
 #pragma unroll
-            for (int j = 1; j < AK; ++j) mx = fmaxf(mx, sv[j]);
+            for (int j = 4; j < KS; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], sv[j]);
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            if (A_SPL > 1) {
+                mx_sm[sb][sub][r] = mx;
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * A_SPL) : "memory");
+#pragma unroll
+                for (int u = 0; u < A_SPL; ++u) mx = fmaxf(mx, mx_sm[sb][u][r]);
+            }
             const float m_new = fmaxf(m, mx);
             const float alpha = ex2_approx((m - m_new) * LOG2E);   // first block: exp2(-inf) = 0
             const float mc = m_new * LOG2E;
-            float sum = 0.f;
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < AK; ++j) { sv[j] = ex2_approx(fmaf(sv[j], LOG2E, -mc)); sum += sv[j]; }
-            l = fmaf(l, alpha, sum);
+            for (int j = 0; j < KS; ++j) { sv[j] = ex2_approx(fmaf(sv[j], LOG2E, -mc)); sum4[j & 3] += sv[j]; }
+            l = fmaf(l, alpha, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
             m = m_new;
 
             // P -> TMEM (hi, lo); the previous block's PV MMAs must have retired
+            DBG_T(d2);
             mbar_wait(p_free, (i & 1) ^ 1, 330 + i);
+            DBG_T(d3);
+            w_pfree += d3 - d2;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < KS / 16; ++c) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     hi[j] = tf32_hi(sv[16 * c + j]);
                     lo[j] = __float_as_uint(sv[16 * c + j] - __uint_as_float(hi[j]));
                 }
-                tmem_st16(tmem + lane_addr + C_PHI + 16 * c, hi);
-                tmem_st16(tmem + lane_addr + C_PLO + 16 * c, lo);
+                tmem_st16(tmem + lane_addr + C_PHI + off + 16 * c, hi);
+                tmem_st16(tmem + lane_addr + C_PLO + off + 16 * c, lo);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -265,37 +332,46 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             // fold in the PREVIOUS block's O (its MMAs ran while this block's softmax was computed)
             if (i > 0) {
                 const int ob = (i - 1) & 1;
+                float ov[KS];
+                DBG_T(d4);
                 mbar_wait(&o_ready[ob], ((i - 1) >> 1) & 1, 350 + i);
+                DBG_T(d5);
+                w_oready += d5 - d4;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t t32[32];
-                tmem_ld32(tmem + lane_addr + C_O + 64 * ob, t32);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = fmaf(o[j], alpha_prev, __uint_as_float(t32[j]));
-                tmem_ld32(tmem + lane_addr + C_O + 64 * ob + 32, t32);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) o[32 + j] = fmaf(o[32 + j], alpha_prev, __uint_as_float(t32[j]));
+                load_cols(C_O + 64 * ob + off, ov);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(&o_free[ob]);
+#pragma unroll
+                for (int j = 0; j < KS; ++j) o[j] = fmaf(o[j], alpha_prev, ov[j]);
             }
             alpha_prev = alpha;
         }
+        if (A_PHASE_TIMERS && p.debug && threadIdx.x == 64) {
+            atomicAdd(&fc_attn_dbg[7], (unsigned long long)w_sready); atomicAdd(&fc_attn_dbg[8], (unsigned long long)w_pfree);
+            atomicAdd(&fc_attn_dbg[9], (unsigned long long)w_oready); atomicAdd(&fc_attn_dbg[10], (unsigned long long)(clock64() - t_sm0));
+        }
         {
             const int ob = (nblk - 1) & 1;
+            float ov[KS];
             mbar_wait(&o_ready[ob], ((nblk - 1) >> 1) & 1, 390);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t t32[32];
-            tmem_ld32(tmem + lane_addr + C_O + 64 * ob, t32);
+            load_cols(C_O + 64 * ob + off, ov);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = fmaf(o[j], alpha_prev, __uint_as_float(t32[j]));
-            tmem_ld32(tmem + lane_addr + C_O + 64 * ob + 32, t32);
+            for (int j = 0; j < KS; ++j) o[j] = fmaf(o[j], alpha_prev, ov[j]);
+        }
+        if (A_SPL > 1) {
+            // all partial sums share the same running maximum: the row sum is their plain sum
+            mx_sm[nblk & 1][sub][r] = l;      // (the buffer the last block did not use)
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * A_SPL) : "memory");
+            l = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[32 + j] = fmaf(o[32 + j], alpha_prev, __uint_as_float(t32[j]));
+            for (int u = 0; u < A_SPL; ++u) l += mx_sm[nblk & 1][u][r];
         }
         if (q0 + r < p.N) {
             const float inv = 1.0f / l;
-            float4* dst = reinterpret_cast<float4*>(p.out + ((size_t)b * p.N + q0 + r) * p.ldo);
+            float4* dst = reinterpret_cast<float4*>(p.out + ((size_t)b * p.N + q0 + r) * p.ldo + off);
 #pragma unroll
-            for (int j = 0; j < AD / 4; ++j)
+            for (int j = 0; j < KS / 4; ++j)
                 dst[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
         }
     }
@@ -406,10 +482,21 @@ int fc_launch_cross_attention_tc(const float* q, int ldq, const float* kv, int l
     FcProfScope prof(FC_CLS_ATTENTION, 4.0 * B * (double)N * Nc * d, 4.0 * B * ((double)N * d * 2 + (double)Nc * d * 2), stream);
     kv_split_kernel<<<dim3((Ncp + 31) / 32, B), 256, 0, stream>>>(kv, ldkv, Nc, Ncp, khi, klo, vthi, vtlo);
     fc_count_launch();
-    AttnTcParams p{out, ldo, N, Nc, (Nc + AK - 1) / AK, scale};
+    static int dbg_loads = -1;
+    if (dbg_loads < 0) { const char* e = getenv("FC_ATTN_DBG_LOADS"); dbg_loads = (e && e[0] == '1') ? 1 : 0; }
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("FC_ATTN_DEBUG"); dbg = (e && e[0] == '1') ? 1 : 0; }
+    AttnTcParams p{out, ldo, N, Nc, (Nc + AK - 1) / AK, scale, dbg, dbg_loads};
     attention_tc_kernel<<<dim3((N + AQ - 1) / AQ, B), A_THREADS, A_SMEM, stream>>>(mQ, mKh, mKl, mVh, mVl, p);
     fc_count_launch();
     FC_LAUNCH_OK();
+    return FC_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fc_debug_attn_phases(unsigned long long* out16) {
+    if (cudaMemcpyFromSymbol(out16, fc_attn_dbg, 16 * sizeof(unsigned long long)) != cudaSuccess) return FC_ERR_CUDA;
+    unsigned long long z[16] = {};
+    if (cudaMemcpyToSymbol(fc_attn_dbg, z, sizeof(z)) != cudaSuccess) return FC_ERR_CUDA;
     return FC_OK;
 }
 

@@ -45,6 +45,15 @@ constexpr int TC_BK = 32;                      // 32 fp32 = one 128-byte swizzle
 constexpr int TC_STAGES = 2;                   // shared-memory stages (two CTAs per SM cover for each other)
 constexpr int TC_TSTAGES = 2;                  // TMEM stages of the A operand, each HALF a k-block
 constexpr int TC_THREADS = 320;
+// phase timers (scripts/tc_phases.py): compiled out by default, build a variant with -DTC_PHASE_TIMERS=1
+#ifndef TC_PHASE_TIMERS
+#define TC_PHASE_TIMERS 0
+#endif
+#if TC_PHASE_TIMERS
+#define TC_CLOCK() clock64()
+#else
+#define TC_CLOCK() 0ll
+#endif
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_TMEM_COLS = 256;                // half of TMEM: TWO CTAs are resident per SM
 constexpr int TC_COL_MAIN = 0;
@@ -55,15 +64,17 @@ struct TcParams {
     GemmArgs g;
     int BN;        // N tile (multiple of 16, <= 192)
     int T1, T2;    // k-blocks of segment 1 / 2
-    int passes;    // 3 = 3xTF32, 1 = plain TF32 (debug)
     int debug;     // 1: accumulate phase cycle counts into fc_tc_dbg
-    int merge_corr; // experiment: compensation products into the main accumulator
 };
 
 // phase timing (debug): [0] CTAs, [1] cycles setup->accumulator ready, [2] cycles of the epilogue, [3] cycles setup
 __device__ unsigned long long fc_tc_dbg[8];   // [4] tmem loads, [5] bias/act math, [6] staging + global stores
 
 // ----------------------------------------------------------------------------- kernel
+// One instantiation per (epilogue kind, activation, residual): with every variant inlined behind runtime branches the
+// kernel was 80 KB of SASS and ncu showed an 88 % instruction-cache hit rate with "no instruction" among the top
+// stall reasons of the epilogue warps.
+template <int EPI, int ACT, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
@@ -90,7 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     uint64_t* tfree = bars + 3 * TC_STAGES + TC_TSTAGES;     // [TC_TSTAGES] MMAs done reading A TMEM
     uint64_t* accum = bars + 3 * TC_STAGES + 2 * TC_TSTAGES;
 
-    const long long t_begin = clock64();
+    const long long t_begin = TC_CLOCK();
     long long t_accum_g = 0, dbg_ld = 0, dbg_math = 0, dbg_st = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TC_BM;
@@ -120,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_slot;
-    const long long t_setup = clock64();
+    const long long t_setup = TC_CLOCK();
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -130,19 +141,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 const uint32_t ph = (t / TC_STAGES) & 1;
                 mbar_wait(&a_free[s], ph ^ 1, 100 + t);
                 mbar_wait(&w_free[s], ph ^ 1, 150 + t);
-                mbar_expect_tx(&full[s], (uint32_t)(TC_A_BYTES + (p.passes == 3 ? 2 : 1) * w_bytes));
+                mbar_expect_tx(&full[s], (uint32_t)(TC_A_BYTES + 2 * w_bytes));
                 if (t < p.T1) tma_load_2d(&mapA1, a_raw(s), &full[s], t * TC_BK, m0);
                 else          tma_load_2d(&mapA2, a_raw(s), &full[s], (t - p.T1) * TC_BK, m0);
                 if (cs == 1) {
                     tma_load_2d(&mapWhi, w_hi(s), &full[s], t * TC_BK, n_tile * BN);
-                    if (p.passes == 3) tma_load_2d(&mapWlo, w_lo(s), &full[s], t * TC_BK, n_tile * BN);
+                    tma_load_2d(&mapWlo, w_lo(s), &full[s], t * TC_BK, n_tile * BN);
                 } else {
                     // my slice of the tile's rows (the W maps are built with box_outer = BN / cs)
                     const int slice = BN / (int)cs;
                     const int off = (int)cta_rank * slice;
                     tma_load_2d_mcast(&mapWhi, w_hi(s) + off * 128, &full[s], t * TC_BK, n_tile * BN + off, cmask);
-                    if (p.passes == 3)
-                        tma_load_2d_mcast(&mapWlo, w_lo(s) + off * 128, &full[s], t * TC_BK, n_tile * BN + off, cmask);
+                    tma_load_2d_mcast(&mapWlo, w_lo(s) + off * 128, &full[s], t * TC_BK, n_tile * BN + off, cmask);
                 }
             }
         }
@@ -174,10 +184,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         for (int kk = 0; kk < 2; ++kk) {
                             const int k = 2 * h + kk;
                             const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
-                            if (p.passes == 3) {
-                                umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (t | k) != 0);
-                                umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
-                            }
+                            umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                            umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
                             umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (t | k) != 0);
                         }
                         umma_commit(&tfree[ts]);     // TMEM A stage reusable once these MMAs retire
@@ -215,11 +223,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            uint32_t u;
                             // cvt.rna.tf32.f32 by hand (add half a TF32 ulp to the magnitude, clear the low 13 bits):
                             // 2 ALU ops instead of the 4 (add, inf test, select, mask) ptxas emits; inputs are finite
-                            if (p.passes == 3) u = (__float_as_uint(xv[e]) + 0x1000u) & 0xffffe000u;
-                            else u = __float_as_uint(xv[e]);
+                            const uint32_t u = (__float_as_uint(xv[e]) + 0x1000u) & 0xffffe000u;
                             hl[4 * jj + e] = u;
                             hl[16 + 4 * jj + e] = __float_as_uint(xv[e] - __uint_as_float(u));
                         }
@@ -248,7 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             for (int i = threadIdx.x - 192; i < BN; i += 128) {
                 const int col = n0p + i;
                 bias_sm[i] = (brow && one_group && col < a.N) ? brow[col] : 0.f;
-                csum_sm[i] = (a.epi == FC_EPI_LNQ && col < a.N) ? a.csum[col] : 0.f;
+                csum_sm[i] = (EPI == FC_EPI_LNQ && col < a.N) ? a.csum[col] : 0.f;
             }
             if (threadIdx.x == 192) bias_in_smem = (one_group && m0 < a.M) ? 1 : 0;
         }
@@ -256,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         // TMEM lane = row within the tile; the two warps of a quadrant take alternate 16-column chunks
         const int half = warp >= 6 ? 1 : 0;
         mbar_wait(accum, 0, 500);
-        t_accum_g = clock64();
+        t_accum_g = TC_CLOCK();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("bar.sync 2, 256;" ::: "memory");    // bias_sm / csum_sm visible to all 8 epilogue warps
         const bool bias_smem = bias_in_smem != 0;
@@ -266,7 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         const int n0 = n_tile * BN;
         float ldj = 0.f;
         float mu = 0.f, rstd = 0.f;
-        if (a.epi == FC_EPI_LNQ && row_ok) { mu = a.row_mu[row]; rstd = a.row_rstd[row]; }
+        if (EPI == FC_EPI_LNQ && row_ok) { mu = a.row_mu[row]; rstd = a.row_rstd[row]; }
         const float* bias_row = a.bias;
         if (a.bias && a.bias_group > 0 && row_ok) bias_row = a.bias + (size_t)(row / a.bias_group) * a.bias_ld;
         // per-warp staging tile [32 rows][16 + 4 pad] (rows 16-byte aligned; a thread's own-row float4 accesses are
@@ -274,27 +280,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 20);
         const int row0 = m0 + quad * 32;
         const bool vec_base = row0 + 32 <= a.M && (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0;
-        const bool vec_res = a.res && (a.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0 &&
+        const bool vec_res = RES && (a.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0 &&
                              (!a.res_scale || (reinterpret_cast<uintptr_t>(a.res_scale) & 15) == 0);
         long long d_ld = 0, d_math = 0, d_st = 0;
         for (int c0 = half * 16; c0 < BN; c0 += 32) {
             uint32_t r[16];
             float v[16];
             __syncwarp();
-            const long long q0 = clock64();
+            const long long q0 = TC_CLOCK();
             tmem_ld16(tmem + lane_addr + TC_COL_MAIN + (uint32_t)c0, r);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.passes == 3 && !p.merge_corr) {
+            {
                 tmem_ld16(tmem + lane_addr + TC_COL_CORR + (uint32_t)c0, r);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
             }
-            const long long q1 = clock64();
+            const long long q1 = TC_CLOCK();
             d_ld += q1 - q0;
             const int col = n0 + c0;
             if (col >= a.N) continue;                     // warp-uniform
-            if (a.epi == FC_EPI_LNQ) {
+            if (EPI == FC_EPI_LNQ) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (col + j < a.N) v[j] = rstd * (v[j] - mu * csum_sm[c0 + j]) + bias_sm[c0 + j];
@@ -315,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     for (int j = 0; j < 16; ++j) if (col + j < a.N) v[j] += bias_row[col + j];
                 }
             }
-            if (a.epi == FC_EPI_STORE || a.epi == FC_EPI_LNQ) {
+            if (EPI == FC_EPI_STORE || EPI == FC_EPI_LNQ) {
                 // Global traffic goes through a per-warp staging tile so that it is COALESCED: with one thread per
                 // row, direct loads/stores touch 32 different lines per instruction (ncu: the residual layers took 2x
                 // as long as the plain ones).  Each warp instruction below moves 2 rows x 64 contiguous bytes.
@@ -326,7 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 const bool vec = vec_base && col + 16 <= a.N;
                 const int r8 = lane >> 2, c4 = (lane & 3) * 4;
                 float4* my_row4 = reinterpret_cast<float4*>(stg + lane * 20);
-                if (a.res) {
+                if (RES) {
                     if (vec && vec_res) {
                         const float* rp = a.res + (size_t)(row0 + r8) * a.ldres + col + c4;
                         float4 rx4[4];
@@ -365,17 +371,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         __syncwarp();
                     }
                 }
-                if (a.act == FC_ACT_GELU) {
+                if (ACT == FC_ACT_GELU) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fc_gelu_erf_fast(v[j]);
-                } else if (a.act == FC_ACT_LRELU) {
+                } else if (ACT == FC_ACT_LRELU) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fc_leaky_relu02(v[j]);
-                } else if (a.act == FC_ACT_RELU) {
+                } else if (ACT == FC_ACT_RELU) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
-                const long long q2 = clock64();
+                const long long q2 = TC_CLOCK();
                 d_math += q2 - q1;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) my_row4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -398,10 +404,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     }
                 }
                 __syncwarp();
-                d_st += clock64() - q2;
+                d_st += TC_CLOCK() - q2;
             } else if (!row_ok) {
                 // nothing: out-of-range rows of the coupling / augment epilogues
-            } else if (a.epi == FC_EPI_COUPLING) {
+            } else if (EPI == FC_EPI_COUPLING) {
                 // reference models/affine_coupling.py:40-46 (see gemm.cu for the arithmetic notes)
                 float* xrow = a.x + (size_t)row * a.ldx + a.col0 + (col >> 1);
                 if (col + 16 <= a.N && (reinterpret_cast<uintptr_t>(xrow) & 7) == 0) {
@@ -434,7 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         }
                     }
                 }
-            } else if (a.epi == FC_EPI_AUGMENT) {
+            } else if (EPI == FC_EPI_AUGMENT) {
                 // reference models/distributions.py:128-153 + models/augmenter.py:49-63
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -448,19 +454,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             }
         }
         dbg_ld = d_ld; dbg_math = d_math; dbg_st = d_st;
-        if (a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) {
+        if (EPI == FC_EPI_COUPLING || EPI == FC_EPI_AUGMENT) {
             // the two threads that share a row combine their partial log-dets in a fixed order (deterministic)
             if (half == 1) ldj_sm[row_in_tile] = ldj;
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (half == 0 && row_ok) {
                 const float tot = ldj + ldj_sm[row_in_tile];
                 float* pp = a.part + (size_t)n_tile * a.M + row;
-                if (a.epi == FC_EPI_COUPLING) *pp += tot; else *pp = tot;
+                if (EPI == FC_EPI_COUPLING) *pp += tot; else *pp = tot;
             }
         }
     }
-    if (p.debug && threadIdx.x == 64) {
-        const long long t_end = clock64();
+    if (TC_PHASE_TIMERS && p.debug && threadIdx.x == 64) {
+        const long long t_end = TC_CLOCK();
         atomicAdd(&fc_tc_dbg[0], 1ull);
         atomicAdd(&fc_tc_dbg[1], (unsigned long long)(t_accum_g - t_setup));
         atomicAdd(&fc_tc_dbg[2], (unsigned long long)(t_end - t_accum_g));
@@ -535,6 +541,21 @@ bool fc_gemm_tc_supported(const GemmArgs& a) {
     return true;
 }
 
+namespace {
+template <int EPI, int ACT, bool RES>
+cudaError_t launch_tc(const cudaLaunchConfig_t& cfg, const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mWh,
+                      const CUtensorMap& mWl, const TcParams& p) {
+    static bool configured = false;   // one per instantiation
+    if (!configured) {
+        // 2 stages x (16 KB A + 2 x 12 KB W at BN=96) + 1 KB alignment slack; static smem (barriers) comes on top
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, ACT, RES>, mA1, mA2, mWh, mWl, p);
+}
+}  // namespace
+
 int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     FC_REQUIRE(fc_gemm_tc_supported(a));
     if (a.epi == FC_EPI_STORE || a.epi == FC_EPI_LNQ) FC_REQUIRE(a.C != nullptr);
@@ -545,15 +566,9 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     p.BN = fc_tc_bn(a.N);
     p.T1 = fc_tc_kpad(a.K1) / TC_BK;
     p.T2 = a.K2 ? fc_tc_kpad(a.K2) / TC_BK : 0;
-    static int passes_env = -1;
-    if (passes_env < 0) { const char* e = getenv("FC_TC_PASSES"); passes_env = (e && e[0] == '1') ? 1 : 3; }
-    p.passes = passes_env;
     static int dbg_env = -1;
     if (dbg_env < 0) { const char* e = getenv("FC_TC_DEBUG"); dbg_env = (e && e[0] == '1') ? 1 : 0; }
     p.debug = dbg_env;
-    static int mc_env = -1;
-    if (mc_env < 0) { const char* e = getenv("FC_TC_MERGE_CORR"); mc_env = (e && e[0] == '1') ? 1 : 0; }
-    (void)mc_env; p.merge_corr = 0;   // (experiment retired: a single accumulator degraded full-depth parity 1.5x)
     FC_REQUIRE(p.BN <= 96 && (p.BN & 15) == 0);
     FC_REQUIRE(a.ldk == (p.T1 + p.T2) * TC_BK);
     const int n_tiles = fc_tc_n_tiles(a.N);
@@ -574,12 +589,6 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     if (!get_map(a.Whi, (uint64_t)a.ldk, (uint64_t)n_tiles * p.BN, (uint64_t)a.ldk, wbox, &mWh)) return FC_ERR_CUDA;
     if (!get_map(a.Wlo, (uint64_t)a.ldk, (uint64_t)n_tiles * p.BN, (uint64_t)a.ldk, wbox, &mWl)) return FC_ERR_CUDA;
     const int smem = TC_STAGES * (TC_A_BYTES + 2 * p.BN * TC_BK * 4) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        // 3 stages x (16 KB A + 2 x 24 KB W at BN=192) + 1 KB alignment slack; static smem (barriers) comes on top
-        FC_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        configured = true;
-    }
     FcProfScope prof(FC_CLS_GEMM_TC, 2.0 * a.M * a.N * (a.K1 + a.K2),
                      4.0 * ((double)a.M * (a.K1 + a.K2) + (double)a.N * (a.K1 + a.K2) + (double)a.M * a.N), stream);
     cudaLaunchConfig_t cfg = {};
@@ -591,7 +600,27 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = cs; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    FC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel, mA1, mA2, mWh, mWl, p));
+    const bool res = a.res != nullptr;
+    cudaError_t le = cudaErrorInvalidValue;
+    if (a.epi == FC_EPI_STORE) {
+        if (a.act == FC_ACT_NONE)       le = res ? launch_tc<FC_EPI_STORE, FC_ACT_NONE, true>(cfg, mA1, mA2, mWh, mWl, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
+        else if (a.act == FC_ACT_GELU)  le = res ? launch_tc<FC_EPI_STORE, FC_ACT_GELU, true>(cfg, mA1, mA2, mWh, mWl, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_GELU, false>(cfg, mA1, mA2, mWh, mWl, p);
+        else if (a.act == FC_ACT_LRELU) le = res ? launch_tc<FC_EPI_STORE, FC_ACT_LRELU, true>(cfg, mA1, mA2, mWh, mWl, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_LRELU, false>(cfg, mA1, mA2, mWh, mWl, p);
+        else if (a.act == FC_ACT_RELU)  le = res ? launch_tc<FC_EPI_STORE, FC_ACT_RELU, true>(cfg, mA1, mA2, mWh, mWl, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_RELU, false>(cfg, mA1, mA2, mWh, mWl, p);
+    } else if (a.epi == FC_EPI_LNQ && a.act == FC_ACT_NONE && !res) {
+        le = launch_tc<FC_EPI_LNQ, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
+    } else if (a.epi == FC_EPI_COUPLING) {
+        le = launch_tc<FC_EPI_COUPLING, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
+    } else if (a.epi == FC_EPI_AUGMENT) {
+        le = launch_tc<FC_EPI_AUGMENT, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
+    } else {
+        return FC_ERR_UNSUPPORTED;
+    }
+    FC_CUDA_OK(le);
     fc_count_launch();
     FC_LAUNCH_OK();
     return FC_OK;

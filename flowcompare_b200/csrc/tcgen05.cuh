@@ -21,6 +21,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a pipeline bug must surface as a trapped kernel with a message, never as a hung GPU.
+// (kept inline: an out-of-line report cost 3 % of the step -- the call ABI pins registers around every wait)
+__device__ __forceinline__ void mbar_timeout(int tag, uint32_t parity) {
+    printf("flowcompare_b200 tcgen05 kernel: mbarrier wait timed out (tag %d, block %d,%d thread %d, parity %u)\n", tag,
+           blockIdx.x, blockIdx.y, threadIdx.x, parity);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
     uint32_t done = 0;
     for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
@@ -32,9 +38,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
             "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) return;
     }
-    printf("flowcompare_b200 gemm_tc: mbarrier wait timed out (tag %d, block %d,%d thread %d, parity %u)\n", tag,
-           blockIdx.x, blockIdx.y, threadIdx.x, parity);
-    __trap();
+    mbar_timeout(tag, parity);
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* smem_dst, uint64_t* bar, int c0, int c1) {
     asm volatile(
