@@ -10,8 +10,8 @@
 //     O   = O * alpha + O_i  in registers (fp32), so the tensor core never chains more than 24 accumulations
 // K and V arrive pre-split into TF32 hi/lo (kv_split_kernel below; V transposed to [dim][key] so that both MMAs
 // take K-major B operands through the same 128B-swizzle descriptors as the GEMM) by TMA into two 2-stage rings.
-//   warp 0      TMA producer            warp 1   TMEM allocator + MMA issuer (S_{i+1} is issued before P_i is awaited)
-//   warps 2-5   Q converter, softmax, O accumulation, output
+//   warp 0   TMA producer      warp 1   TMEM allocator + issuer of the S MMAs      warp 2   issuer of the PV MMAs
+//   warps 3..   Q converter, softmax, O accumulation, output: A_SPL threads per query row
 // TMEM (512 columns): Qhi [0,64) | Qlo [64,128) | S x2 [128,256) | Phi [256,320) | Plo [320,384) | O_i x2 [384,512).
 #include "common.cuh"
 #include "gemm.cuh"
@@ -28,7 +28,7 @@ constexpr int AD = 64;                  // head dim
 #ifndef A_SPL
 #define A_SPL 2                        // softmax threads per query row (1, 2 or 4)
 #endif
-constexpr int A_THREADS = 64 + 128 * A_SPL;
+constexpr int A_THREADS = 96 + 128 * A_SPL;
 constexpr int A_ATOM = 64 * 128;        // 64 rows x 128 B  (one swizzle atom of a 64-row tile)
 constexpr int A_TILE = 4 * A_ATOM;      // hi atom 0/1, lo atom 0/1 = 32 KB per K (or V) block
 constexpr int A_QBYTES = 2 * AQ * 128;  // raw fp32 Q tile: two atoms of 128 rows
@@ -160,43 +160,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (whole warp loops, one elected lane issues)
+        // ===================================================== MMA issuer 1: S_j = Q K_j^T  (whole warp loops, one elected lane issues)
         // instruction descriptor: D=f32, A=B=tf32, K-major, N=64 (>>3 at bit 17), M=128 (>>4 at bit 24)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AK >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
-        long long w_kfull = 0, w_sfree = 0, w_vfull = 0, w_ofree = 0, w_pready = 0;
+        long long w_kfull = 0, w_sfree = 0;
         DBG_T(t_start);
         mbar_wait(qready, 0, 200);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         DBG_T(t_q);
-        mbar_wait(&kfull[0], 0, 201);
-        if (elect_one()) {
-            issue_3xtf32(tmem + C_S, tmem + C_QHI, tmem + C_QLO, k_tile(0), idesc);
-            umma_commit(&s_ready[0]);
-            umma_commit(&kfree[0]);
-        }
-        __syncwarp();
-        for (int i = 0; i < nblk; ++i) {
-            if (i + 1 < nblk) {
-                const int j = i + 1, ks = j % A_STAGES, sb = j & 1;
-                DBG_T(c0);
-                mbar_wait(&kfull[ks], (j / A_STAGES) & 1, 210 + i);
-                DBG_T(c1);
-                mbar_wait(&s_free[sb], ((j >> 1) & 1) ^ 1, 220 + i);
-                DBG_T(c2);
-                w_kfull += c1 - c0; w_sfree += c2 - c1;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    issue_3xtf32(tmem + C_S + 64 * sb, tmem + C_QHI, tmem + C_QLO, k_tile(ks), idesc);
-                    umma_commit(&s_ready[sb]);
-                    umma_commit(&kfree[ks]);
-                }
-                __syncwarp();
+        for (int j = 0; j < nblk; ++j) {
+            const int ks = j % A_STAGES, sb = j & 1;
+            DBG_T(c0);
+            mbar_wait(&kfull[ks], (j / A_STAGES) & 1, 210 + j);
+            DBG_T(c1);
+            mbar_wait(&s_free[sb], ((j >> 1) & 1) ^ 1, 220 + j);     // softmax has S_{j-2} in registers
+            DBG_T(c2);
+            w_kfull += c1 - c0; w_sfree += c2 - c1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                issue_3xtf32(tmem + C_S + 64 * sb, tmem + C_QHI, tmem + C_QLO, k_tile(ks), idesc);
+                umma_commit(&s_ready[sb]);
+                umma_commit(&kfree[ks]);
             }
+            __syncwarp();
+        }
+        if (A_PHASE_TIMERS && p.debug && lane == 0) {
+            atomicAdd(&fc_attn_dbg[0], 1ull);
+            atomicAdd(&fc_attn_dbg[1], (unsigned long long)(clock64() - t_start));
+            atomicAdd(&fc_attn_dbg[2], (unsigned long long)w_kfull); atomicAdd(&fc_attn_dbg[3], (unsigned long long)w_sfree);
+            atomicAdd(&fc_attn_dbg[11], (unsigned long long)(t_q - t_start));
+        }
+    } else if (warp == 2) {
+        // ===================================================== MMA issuer 2: O_i = P_i V_i
+        // (its own warp: a wait for P_i must not hold back S_{i+1}, and the other way round; each warp's
+        // tcgen05.commit tracks the MMAs that warp issued)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AK >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
+        long long w_vfull = 0, w_ofree = 0, w_pready = 0;
+        for (int i = 0; i < nblk; ++i) {
             const int vs = i % A_STAGES, ob = i & 1;
             DBG_T(c3);
             mbar_wait(&vfull[vs], (i / A_STAGES) & 1, 230 + i);
             DBG_T(c4);
-            mbar_wait(&o_free[ob], ((i >> 1) & 1) ^ 1, 240 + i);
+            mbar_wait(&o_free[ob], ((i >> 1) & 1) ^ 1, 240 + i);       // O_{i-2} has been read back
             DBG_T(c5);
             mbar_wait(p_ready, i & 1, 250 + i);
             DBG_T(c6);
@@ -211,11 +216,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             __syncwarp();
         }
         if (A_PHASE_TIMERS && p.debug && lane == 0) {
-            atomicAdd(&fc_attn_dbg[0], 1ull);
-            atomicAdd(&fc_attn_dbg[1], (unsigned long long)(clock64() - t_start));
-            atomicAdd(&fc_attn_dbg[2], (unsigned long long)w_kfull); atomicAdd(&fc_attn_dbg[3], (unsigned long long)w_sfree);
             atomicAdd(&fc_attn_dbg[4], (unsigned long long)w_vfull); atomicAdd(&fc_attn_dbg[5], (unsigned long long)w_ofree);
-            atomicAdd(&fc_attn_dbg[6], (unsigned long long)w_pready); atomicAdd(&fc_attn_dbg[11], (unsigned long long)(t_q - t_start));
+            atomicAdd(&fc_attn_dbg[6], (unsigned long long)w_pready);
         }
     } else {
         // ===================================================== Q converter + softmax + O accumulation
@@ -224,7 +226,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         // memory + one named barrier per quadrant); the partial row sums are combined once at the end.
         constexpr int KS = AK / A_SPL;            // keys (and output dims) per thread
         const int quad = warp & 3;
-        const int sub = (warp - 2) >> 2;
+        const int sub = (warp - 3) >> 2;
         const int r = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const int off = sub * KS;                 // first key of the block / first output dim of this thread
@@ -346,7 +348,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             }
             alpha_prev = alpha;
         }
-        if (A_PHASE_TIMERS && p.debug && threadIdx.x == 64) {
+        if (A_PHASE_TIMERS && p.debug && threadIdx.x == 96) {
             atomicAdd(&fc_attn_dbg[7], (unsigned long long)w_sready); atomicAdd(&fc_attn_dbg[8], (unsigned long long)w_pfree);
             atomicAdd(&fc_attn_dbg[9], (unsigned long long)w_oready); atomicAdd(&fc_attn_dbg[10], (unsigned long long)(clock64() - t_sm0));
         }
