@@ -458,18 +458,27 @@ int64_t fc_attention_tc_scratch_floats(int B, int Nc) {
     return 2 * (int64_t)B * Nc * AD + 2 * (int64_t)B * AD * Ncp + 64;
 }
 
+void fc_attention_tc_scratch_layout(int B, int Nc, float* scratch, float** khi, float** klo, float** vthi, float** vtlo,
+                                    int* ncp) {
+    const int Ncp = fc_round_up(Nc, 4);
+    *khi = scratch;
+    *klo = *khi + fc_round_up_ll((int64_t)B * Nc * AD, 32);
+    *vthi = *klo + fc_round_up_ll((int64_t)B * Nc * AD, 32);
+    *vtlo = *vthi + (int64_t)B * AD * Ncp;
+    *ncp = Ncp;
+}
+
+// presplit != 0: the scratch already holds k / v^T hi/lo (written by the to_kv GEMM's FC_EPI_KVSPLIT epilogue), kv unused
 int fc_launch_cross_attention_tc(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo, int B, int N,
-                                 int Nc, int d, float scale, float* scratch, cudaStream_t stream) {
-    FC_REQUIRE(q && kv && out && scratch && B > 0 && N > 0 && Nc > 0);
+                                 int Nc, int d, float scale, float* scratch, int presplit, cudaStream_t stream) {
+    FC_REQUIRE(q && (kv || presplit) && out && scratch && B > 0 && N > 0 && Nc > 0);
     if (d != AD) return FC_ERR_UNSUPPORTED;
-    FC_REQUIRE((ldq & 3) == 0 && (ldo & 3) == 0 && ldkv >= 2 * AD && ldq >= AD && ldo >= AD && B <= 65535);
+    FC_REQUIRE((ldq & 3) == 0 && (ldo & 3) == 0 && (presplit || ldkv >= 2 * AD) && ldq >= AD && ldo >= AD && B <= 65535);
     FC_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(scratch) & 127) == 0);
-    const int Ncp = fc_round_up(Nc, 4);
-    float* khi = scratch;
-    float* klo = khi + fc_round_up_ll((int64_t)B * Nc * AD, 32);
-    float* vthi = klo + fc_round_up_ll((int64_t)B * Nc * AD, 32);
-    float* vtlo = vthi + (int64_t)B * AD * Ncp;
+    float *khi, *klo, *vthi, *vtlo;
+    int Ncp;
+    fc_attention_tc_scratch_layout(B, Nc, scratch, &khi, &klo, &vthi, &vtlo, &Ncp);
     CUtensorMap mQ, mKh, mKl, mVh, mVl;
     if (!get_amap(q, AD, (uint64_t)B * N, 0, (uint64_t)ldq, 0, 32, AQ, &mQ)) return FC_ERR_CUDA;
     if (!get_amap(khi, AD, (uint64_t)B * Nc, 0, AD, 0, 32, AK, &mKh)) return FC_ERR_CUDA;
@@ -482,8 +491,10 @@ int fc_launch_cross_attention_tc(const float* q, int ldq, const float* kv, int l
         configured = true;
     }
     FcProfScope prof(FC_CLS_ATTENTION, 4.0 * B * (double)N * Nc * d, 4.0 * B * ((double)N * d * 2 + (double)Nc * d * 2), stream);
-    kv_split_kernel<<<dim3((Ncp + 31) / 32, B), 256, 0, stream>>>(kv, ldkv, Nc, Ncp, khi, klo, vthi, vtlo);
-    fc_count_launch();
+    if (!presplit) {
+        kv_split_kernel<<<dim3((Ncp + 31) / 32, B), 256, 0, stream>>>(kv, ldkv, Nc, Ncp, khi, klo, vthi, vtlo);
+        fc_count_launch();
+    }
     static int dbg_loads = -1;
     if (dbg_loads < 0) { const char* e = getenv("FC_ATTN_DBG_LOADS"); dbg_loads = (e && e[0] == '1') ? 1 : 0; }
     static int dbg = -1;
@@ -512,6 +523,6 @@ extern "C" __attribute__((visibility("default"))) int fc_cross_attention_tc(cons
                                                                              float scale, void* scratch, int64_t scratch_bytes,
                                                                              fc_stream_t stream) {
     FC_REQUIRE(scratch && scratch_bytes >= fc_cross_attention_tc_scratch_bytes(B, Nc));
-    return fc_launch_cross_attention_tc(q, ldq, kv, ldkv, out, ldo, B, N, Nc, d, scale, static_cast<float*>(scratch),
+    return fc_launch_cross_attention_tc(q, ldq, kv, ldkv, out, ldo, B, N, Nc, d, scale, static_cast<float*>(scratch), 0,
                                         (cudaStream_t)stream);
 }

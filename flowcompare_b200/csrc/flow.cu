@@ -261,16 +261,27 @@ static int run_attention_block(const fc_flow* f, const FcMlp& pre, const FcAttn&
         rc = fc_launch_gemm(g, s);
         if (rc) return rc;
     }
+    // reference models/perceiver.py:104: scale = inner_dim ** -0.5
+    const float scale = 1.0f / sqrtf((float)f->inner);
+    static int attn_kind = -1;   // FC_ATTN=mma: warp-level MMA kernel; FC_ATTN=split: tcgen05 with a separate split pass (A/B runs)
+    if (attn_kind < 0) { const char* e = getenv("FC_ATTN"); attn_kind = !e ? 0 : (e[0] == 'm' ? 1 : (e[0] == 's' ? 2 : 0)); }
+    if (precision == 1 && attn_kind == 0 && at.kv.N == 128 && at.kv.whi) {
+        // to_kv writes the TF32 hi/lo copies of k and v^T the tcgen05 attention consumes, straight from its epilogue
+        GemmArgs g = fc_gemm_args_zero();
+        g.A1 = context; g.lda1 = f->E; g.K1 = at.kv.K1; g.Wt = at.kv.w; g.ldw = at.kv.ldw; g.bias = at.kv.b;
+        g.Whi = at.kv.whi; g.Wlo = at.kv.wlo; g.ldk = at.kv.ldk; g.M = B * Nc; g.N = 128; g.precision = 1;
+        g.epi = FC_EPI_KVSPLIT; g.ldc = 64; g.kv_nc = Nc;
+        fc_attention_tc_scratch_layout(B, Nc, w.kvs, &g.C, &g.kv_klo, &g.kv_vthi, &g.kv_vtlo, &g.kv_ncp);
+        rc = fc_launch_gemm(g, s);
+        if (rc) return rc;
+        return fc_launch_cross_attention_tc(w.q, 64, nullptr, 0, w.o, 64, B, N, Nc, f->inner, scale, w.kvs, 1, s);
+    }
     rc = gemm_plain(at.kv, context, f->E, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, w.kv, 128, B * Nc,
                     precision, s);
     if (rc) return rc;
-    // reference models/perceiver.py:104: scale = inner_dim ** -0.5
-    const float scale = 1.0f / sqrtf((float)f->inner);
     if (precision == 1) {
-        static int use_mma = -1;   // FC_ATTN=mma: the warp-level MMA kernel (A/B runs)
-        if (use_mma < 0) { const char* e = getenv("FC_ATTN"); use_mma = (e && e[0] == 'm') ? 1 : 0; }
-        if (use_mma) return fc_launch_cross_attention_mma(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
-        return fc_launch_cross_attention_tc(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, w.kvs, s);
+        if (attn_kind == 1) return fc_launch_cross_attention_mma(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
+        return fc_launch_cross_attention_tc(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, w.kvs, 0, s);
     }
     return fc_launch_cross_attention(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
 }

@@ -237,6 +237,7 @@ int fc_gemm_n_tiles(int N) { return N <= 64 ? 1 : (N + 127) / 128; }
 
 int fc_launch_gemm_ffma(const GemmArgs& a, cudaStream_t stream) {
     FC_REQUIRE(a.M > 0 && a.N > 0 && a.K1 > 0 && a.A1 && a.Wt);
+    if (a.epi == FC_EPI_KVSPLIT) return FC_ERR_UNSUPPORTED;   // tcgen05 path only
     FC_REQUIRE(a.K2 == 0 || a.A2);
     FC_REQUIRE(a.ldw >= fc_gemm_ldw(a.N) && (a.ldw & 3) == 0);
     FC_REQUIRE((reinterpret_cast<uintptr_t>(a.Wt) & 15) == 0);

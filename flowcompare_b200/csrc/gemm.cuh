@@ -13,6 +13,8 @@ enum {
     FC_EPI_LNQ = 1,       // C = rstd[row]*(acc - mu[row]*csum[n]) + bias[n]   (LayerNorm folded into to_q)
     FC_EPI_COUPLING = 2,  // affine coupling: columns interleaved (s_raw_j, t_j); x2 updated in place; ldj partial
     FC_EPI_AUGMENT = 3,   // augment: columns interleaved (mean_j, log_std_j); z2 written; ldj partial
+    FC_EPI_KVSPLIT = 4,   // to_kv for the tcgen05 attention (N = 128): k -> TF32 hi/lo [M][64]; v -> hi/lo TRANSPOSED
+                          // per cloud [B][64][kv_ncp]  (tcgen05 path only)
 };
 
 struct GemmArgs {
@@ -35,6 +37,8 @@ struct GemmArgs {
     float* x; int ldx; int col0;
     float* part;                   // [gridDim.x][M] partial log-det sums (deterministic, no atomics)
     const float* eps; int ld_eps;  // FC_EPI_AUGMENT
+    // FC_EPI_KVSPLIT: C = k hi (ldc = 64), kv_klo = k lo; v^T hi / lo; rows are (cloud, key) = (row / kv_nc, row % kv_nc)
+    float* kv_klo; float* kv_vthi; float* kv_vtlo; int kv_nc; int kv_ncp;
     int precision;                 // 0 fp32 FFMA, 1 3xTF32 tcgen05 (where available)
     // tcgen05 path: the same weight pre-split into TF32 hi / lo parts, N-major rows, K contiguous:
     // [n_tiles*BN][ldk] with ldk = round32(K1) + round32(K2) (zero padded); null -> FFMA only
@@ -60,6 +64,7 @@ static inline GemmArgs fc_gemm_args_zero() {
     a.res = nullptr; a.ldres = 0; a.res_scale = nullptr; a.act = FC_ACT_NONE; a.C = nullptr; a.ldc = 0; a.M = 0; a.N = 0;
     a.epi = FC_EPI_STORE; a.row_mu = nullptr; a.row_rstd = nullptr; a.csum = nullptr;
     a.x = nullptr; a.ldx = 0; a.col0 = 0; a.part = nullptr; a.eps = nullptr; a.ld_eps = 0;
+    a.kv_klo = nullptr; a.kv_vthi = nullptr; a.kv_vtlo = nullptr; a.kv_nc = 0; a.kv_ncp = 0;
     a.precision = 0; a.Whi = nullptr; a.Wlo = nullptr; a.ldk = 0;
     return a;
 }

@@ -405,6 +405,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 }
                 __syncwarp();
                 d_st += TC_CLOCK() - q2;
+            } else if (EPI == FC_EPI_KVSPLIT) {
+                // to_kv feeding the tcgen05 attention (attention_tc.cu): TF32 hi/lo copies, v transposed per cloud.
+                // BN = 64, so N-tile 0 is k and N-tile 1 is v.
+                float lo16[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float h = __uint_as_float((__float_as_uint(v[j]) + 0x1000u) & 0xffffe000u);
+                    lo16[j] = v[j] - h;
+                    v[j] = h;
+                }
+                if (col < 64) {
+                    // k: rows stay rows; two staged, coalesced 16-byte passes (hi, then lo)
+                    const int r8 = lane >> 2, c4 = (lane & 3) * 4;
+                    float4* my_row4 = reinterpret_cast<float4*>(stg + lane * 20);
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        float* dstbase = pass == 0 ? a.C : a.kv_klo;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            my_row4[q] = pass == 0 ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3])
+                                                   : make_float4(lo16[4 * q], lo16[4 * q + 1], lo16[4 * q + 2], lo16[4 * q + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int gr = row0 + r8 + 8 * i;
+                            if (gr < a.M)
+                                *reinterpret_cast<float4*>(dstbase + (size_t)gr * 64 + col + c4) =
+                                    *reinterpret_cast<const float4*>(stg + (r8 + 8 * i) * 20 + c4);
+                        }
+                        __syncwarp();
+                    }
+                } else if (row_ok) {
+                    // v: transposed; the 32 lanes of a warp hold 32 consecutive keys -> each store instruction writes
+                    // one contiguous run per cloud
+                    const int bcl = row / a.kv_nc, key = row - bcl * a.kv_nc;
+                    float* th = a.kv_vthi + ((size_t)bcl * 64 + (col - 64)) * a.kv_ncp + key;
+                    float* tl = a.kv_vtlo + ((size_t)bcl * 64 + (col - 64)) * a.kv_ncp + key;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { th[(size_t)j * a.kv_ncp] = v[j]; tl[(size_t)j * a.kv_ncp] = lo16[j]; }
+                }
             } else if (!row_ok) {
                 // nothing: out-of-range rows of the coupling / augment epilogues
             } else if (EPI == FC_EPI_COUPLING) {
@@ -561,6 +601,10 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     if (a.epi == FC_EPI_STORE || a.epi == FC_EPI_LNQ) FC_REQUIRE(a.C != nullptr);
     if (a.epi == FC_EPI_LNQ) FC_REQUIRE(a.row_mu && a.row_rstd && a.csum && a.bias && a.bias_group == 0);
     if (a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) FC_REQUIRE(a.x && a.part && (a.N % 4) == 0);
+    if (a.epi == FC_EPI_KVSPLIT)
+        FC_REQUIRE(a.N == 128 && fc_tc_bn(a.N) == 64 && a.C && a.kv_klo && a.kv_vthi && a.kv_vtlo && a.kv_nc > 0 &&
+                   a.kv_ncp >= a.kv_nc && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(a.kv_klo) & 15) == 0);
     TcParams p;
     p.g = a;
     p.BN = fc_tc_bn(a.N);
@@ -617,6 +661,8 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
         le = launch_tc<FC_EPI_COUPLING, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
     } else if (a.epi == FC_EPI_AUGMENT) {
         le = launch_tc<FC_EPI_AUGMENT, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
+    } else if (a.epi == FC_EPI_KVSPLIT && a.act == FC_ACT_NONE && !res) {
+        le = launch_tc<FC_EPI_KVSPLIT, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
     } else {
         return FC_ERR_UNSUPPORTED;
     }
