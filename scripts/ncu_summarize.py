@@ -37,7 +37,7 @@ def launches(src, dst):
     with open(dst, "w") as f:
         f.write("kernel,launches,total_us,share,avg_us\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            f.write(f"{k},{n},{t:.1f},{t / tot:.4f},{t / n:.2f}\n")
+            f.write(f"\"{k}\",{n},{t:.1f},{t / tot:.4f},{t / n:.2f}\n")
         f.write(f"TOTAL,{sum(a[0] for a in agg.values())},{tot:.1f},1.0,\n")
 
 
@@ -50,7 +50,7 @@ def full(src, dst):
     with open(dst, "w") as f:
         f.write("launch,kernel,grid,block," + ",".join(f"{m} [{units[col[m]]}]" for m in keep) + "\n")
         for i, r in enumerate(body):
-            f.write(f"{i},{short(r[col['Kernel Name']])},\"{r[col['Grid Size']]}\",\"{r[col['Block Size']]}\"," +
+            f.write(f"{i},\"{short(r[col['Kernel Name']])}\",\"{r[col['Grid Size']]}\",\"{r[col['Block Size']]}\"," +
                     ",".join(r[col[m]].replace(",", "") for m in keep) + "\n")
 
 
