@@ -88,7 +88,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024 B alignment
-    const int BN = p.BN;
+    const int BN = p.BN;                    // widest tile of this launch: shared-memory layout and TMA box
     const int w_bytes = BN * TC_BK * 4;
     const int stage_bytes = TC_A_BYTES + 2 * w_bytes;
     auto a_raw = [&](int s) { return smem + s * stage_bytes; };
@@ -106,6 +106,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TC_BM;
     const int n_tile = blockIdx.x;
+    // N is cut into gridDim.x tiles whose widths are multiples of 16 and differ by at most 16 (512 -> 96,96,80,80,80,80):
+    // no padded columns go through the tensor core.  The TMA box stays BN rows (the extra rows are the next tile's).
+    const int n_units = (p.g.N + 15) >> 4, n_base = n_units / (int)gridDim.x, n_rem = n_units % (int)gridDim.x;
+    const int tile_n0 = 16 * (n_tile * n_base + min(n_tile, n_rem));
+    const int tile_bn = 16 * (n_base + (n_tile < n_rem ? 1 : 0));
     const int T = p.T1 + p.T2;
 
     // Thread-block cluster along M (1 x cs x 1): the cs CTAs of a cluster work on the SAME weight tile, so each
@@ -145,14 +150,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 if (t < p.T1) tma_load_2d(&mapA1, a_raw(s), &full[s], t * TC_BK, m0);
                 else          tma_load_2d(&mapA2, a_raw(s), &full[s], (t - p.T1) * TC_BK, m0);
                 if (cs == 1) {
-                    tma_load_2d(&mapWhi, w_hi(s), &full[s], t * TC_BK, n_tile * BN);
-                    tma_load_2d(&mapWlo, w_lo(s), &full[s], t * TC_BK, n_tile * BN);
+                    tma_load_2d(&mapWhi, w_hi(s), &full[s], t * TC_BK, tile_n0);
+                    tma_load_2d(&mapWlo, w_lo(s), &full[s], t * TC_BK, tile_n0);
                 } else {
                     // my slice of the tile's rows (the W maps are built with box_outer = BN / cs)
                     const int slice = BN / (int)cs;
                     const int off = (int)cta_rank * slice;
-                    tma_load_2d_mcast(&mapWhi, w_hi(s) + off * 128, &full[s], t * TC_BK, n_tile * BN + off, cmask);
-                    tma_load_2d_mcast(&mapWlo, w_lo(s) + off * 128, &full[s], t * TC_BK, n_tile * BN + off, cmask);
+                    tma_load_2d_mcast(&mapWhi, w_hi(s) + off * 128, &full[s], t * TC_BK, tile_n0 + off, cmask);
+                    tma_load_2d_mcast(&mapWlo, w_lo(s) + off * 128, &full[s], t * TC_BK, tile_n0 + off, cmask);
                 }
             }
         }
@@ -163,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         // moves (~90 cycles per MMA, above the 88-cycle tensor time of a 128x176x8 TF32 MMA).
         {
             // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2), K-major, N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t d_main = tmem + TC_COL_MAIN, d_corr = tmem + TC_COL_CORR;
             for (int t = 0; t < T; ++t) {
                 const int s = t % TC_STAGES;
@@ -246,12 +251,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             // epilogue-only warps are idle during the main loop: fetch this tile's bias row (a cold L2 miss per
             // 16-column chunk otherwise -- measured ~600 cycles each) into shared memory
             const GemmArgs& a = p.g;
-            const int n0p = n_tile * BN;
+            const int n0p = tile_n0;
             const int last_row = min(m0 + TC_BM, a.M) - 1;
             const bool one_group = a.bias_group <= 0 || (m0 / a.bias_group) == (last_row / a.bias_group);
             const float* brow = a.bias;
             if (a.bias && a.bias_group > 0) brow = a.bias + (size_t)(m0 / a.bias_group) * a.bias_ld;
-            for (int i = threadIdx.x - 192; i < BN; i += 128) {
+            for (int i = threadIdx.x - 192; i < tile_bn; i += 128) {
                 const int col = n0p + i;
                 bias_sm[i] = (brow && one_group && col < a.N) ? brow[col] : 0.f;
                 csum_sm[i] = (EPI == FC_EPI_LNQ && col < a.N) ? a.csum[col] : 0.f;
@@ -269,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         const GemmArgs& a = p.g;
         const int row = m0 + row_in_tile;
         const bool row_ok = row < a.M;
-        const int n0 = n_tile * BN;
+        const int n0 = tile_n0;
         float ldj = 0.f;
         float mu = 0.f, rstd = 0.f;
         if (EPI == FC_EPI_LNQ && row_ok) { mu = a.row_mu[row]; rstd = a.row_rstd[row]; }
@@ -283,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         const bool vec_res = RES && (a.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0 &&
                              (!a.res_scale || (reinterpret_cast<uintptr_t>(a.res_scale) & 15) == 0);
         long long d_ld = 0, d_math = 0, d_st = 0;
-        for (int c0 = half * 16; c0 < BN; c0 += 32) {
+        for (int c0 = half * 16; c0 < tile_bn; c0 += 32) {
             uint32_t r[16];
             float v[16];
             __syncwarp();
