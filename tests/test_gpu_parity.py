@@ -386,3 +386,50 @@ def test_point_count_sweep_matches_port(n_points):
     want = port.flow_log_prob(fsd, configs.derive(cfg), batch["extract_1"], want_emb, None, batch["eps"])
     got = e.log_prob(batch["extract_1"].to(DEV), emb, None, eps=batch["eps"].to(DEV))
     assert (got.cpu() - want).abs().max().item() < 1e-3
+
+
+# ----------------------------------------------------------------------------- guard-band checks (no sanitizer here)
+def _guarded(shape_rows, ld, guard=4096):
+    """A [rows, ld] fp32 view inside a larger buffer pre-filled with a sentinel; returns (whole, view)."""
+    whole = torch.full((guard + shape_rows * ld + guard,), -12345.0, device=DEV)
+    return whole, whole[guard:guard + shape_rows * ld].view(shape_rows, ld)
+
+
+@pytest.mark.parametrize("M,N,K,ldc", [(1000, 300, 150, 304), (129, 512, 512, 512), (4099, 64, 256, 72), (77, 588, 512, 592)])
+def test_gemm_tc_writes_only_its_output(lib, M, N, K, ldc):
+    """Vectorised epilogue stores: nothing outside C[:M, :N] may be touched (rows past M, columns N..ldc, guard bands)."""
+    g = torch.Generator().manual_seed(M)
+    A = torch.randn(M, (K + 3) // 4 * 4, generator=g).to(DEV)
+    rows, ldk = packing.tc_n_tiles(N) * packing.tc_bn(N), packing.tc_kpad(K)
+    W32 = torch.zeros(rows, ldk)
+    W32[:N, :K] = torch.randn(N, K, generator=g) / math.sqrt(K)
+    hi = packing.tf32_round(W32)
+    lo = packing.tf32_round(W32 - hi)
+    hi, lo, b = hi.to(DEV), lo.to(DEV), torch.randn(N, generator=g).to(DEV)
+    whole, C = _guarded(M, ldc)
+    rc = lib.fc_gemm_tf32x3(A.data_ptr(), A.shape[1], hi.data_ptr(), lo.data_ptr(), ldk, b.data_ptr(), C.data_ptr(), ldc, M, N,
+                            K, 1, _stream())
+    assert rc == 0, fclib.load().fc_last_error()
+    torch.cuda.synchronize()
+    assert (whole[:4096] == -12345.0).all() and (whole[-4096:] == -12345.0).all()
+    assert (C[:, N:] == -12345.0).all()
+    assert torch.isfinite(C[:, :N]).all() and not (C[:, :N] == -12345.0).any()
+
+
+@pytest.mark.parametrize("B,N,Nc", [(2, 130, 70), (1, 1024, 1250), (3, 17, 5)])
+def test_attention_tc_writes_only_its_output(lib, B, N, Nc):
+    g = torch.Generator().manual_seed(N + Nc)
+    q = torch.randn(B, N, 64, generator=g).to(DEV)
+    kv = torch.randn(B, Nc, 128, generator=g).to(DEV)
+    whole, out = _guarded(B * N, 64)
+    nbytes = lib.fc_cross_attention_tc_scratch_bytes(B, Nc)
+    sw = torch.full((1024 + nbytes // 4 + 1024,), -12345.0, device=DEV)
+    scratch = sw[1024:1024 + nbytes // 4]
+    assert scratch.data_ptr() % 128 == 0
+    rc = lib.fc_cross_attention_tc(q.data_ptr(), 64, kv.data_ptr(), 128, out.data_ptr(), 64, B, N, Nc, 64, 0.125,
+                                   scratch.data_ptr(), nbytes, _stream())
+    assert rc == 0, fclib.load().fc_last_error()
+    torch.cuda.synchronize()
+    assert (whole[:4096] == -12345.0).all() and (whole[-4096:] == -12345.0).all()
+    assert (sw[:1024] == -12345.0).all() and (sw[-1024:] == -12345.0).all()
+    assert torch.isfinite(out).all()
