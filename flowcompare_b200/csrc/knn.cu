@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restric
                                                            const float* __restrict__ t, int ldt, long long t_bstride,
                                                            int Nq, int Nt, int C, int k, int mode,
                                                            int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
-    __shared__ float Qs[CK][QT + 1];
+    __shared__ __align__(16) float Qs[CK][QT + 4];   // rows 16-byte aligned: a warp's 4 query values are one broadcast LDS.128
     __shared__ float Cs[CK][CT + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -100,9 +100,9 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restric
             __syncthreads();
             const int cmax = min(CK, C - c0);
             for (int c = 0; c < cmax; ++c) {
-                float qv[4], cv[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) qv[i] = Qs[c][warp * 4 + i];
+                float cv[4];
+                const float4 q4 = *reinterpret_cast<const float4*>(&Qs[c][warp * 4]);
+                const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
                 for (int s = 0; s < 4; ++s) cv[s] = Cs[c][lane + 32 * s];
 #pragma unroll
