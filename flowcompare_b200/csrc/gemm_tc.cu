@@ -42,9 +42,9 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                      // 32 fp32 = one 128-byte swizzle row
-constexpr int TC_STAGES = 2;                   // shared-memory stages (two CTAs per SM cover for each other)
-constexpr int TC_TSTAGES = 2;                  // TMEM stages of the A operand, each HALF a k-block
-constexpr int TC_THREADS = 320;
+constexpr int TC_STAGES = 4;                   // shared-memory stages (k-blocks in flight)
+constexpr int TC_TSTAGES = 4;                  // TMEM stages of the A operand, each HALF a k-block
+constexpr int TC_THREADS = 448;                // TMA, MMA, 4 converter warps, 8 epilogue warps
 // phase timers (scripts/tc_phases.py): compiled out by default, build a variant with -DTC_PHASE_TIMERS=1
 #ifndef TC_PHASE_TIMERS
 #define TC_PHASE_TIMERS 0
@@ -55,36 +55,39 @@ constexpr int TC_THREADS = 320;
 #define TC_CLOCK() 0ll
 #endif
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
-constexpr int TC_TMEM_COLS = 256;                // half of TMEM: TWO CTAs are resident per SM
-constexpr int TC_COL_MAIN = 0;
+constexpr int TC_TMEM_COLS = 512;                // one persistent CTA per SM
+// 4 stages x (16 KB A + 2 x 12 KB W at BN = 96) + 8 staging tiles of the epilogue + 1 KB alignment slack
+constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + 2 * 96 * TC_BK * 4) + 8 * 32 * 20 * 4 + 1024;
+constexpr int TC_COL_ACC = 192;                // accumulator buffer b: main at 192*b, compensation at 192*b + 96
 constexpr int TC_COL_CORR = 96;
-constexpr int TC_COL_A = 192;                  // + 32 * stage: 16 columns hi, 16 columns lo
+constexpr int TC_COL_A = 384;                  // + 32 * stage: 16 columns hi, 16 columns lo
 
 struct TcParams {
     GemmArgs g;
     int BN;        // N tile (multiple of 16, <= 192)
     int T1, T2;    // k-blocks of segment 1 / 2
-    int debug;     // 1: accumulate phase cycle counts into fc_tc_dbg
+    int n_tiles, m_tiles;
 };
-
-// phase timing (debug): [0] CTAs, [1] cycles setup->accumulator ready, [2] cycles of the epilogue, [3] cycles setup
-__device__ unsigned long long fc_tc_dbg[8];   // [4] tmem loads, [5] bias/act math, [6] staging + global stores
 
 // ----------------------------------------------------------------------------- kernel
 // One instantiation per (epilogue kind, activation, residual): with every variant inlined behind runtime branches the
 // kernel was 80 KB of SASS and ncu showed an 88 % instruction-cache hit rate with "no instruction" among the top
 // stall reasons of the epilogue warps.
+//
+// PERSISTENT: one CTA per SM walks the (m-tile, n-tile) list with stride gridDim.x.  The accumulators are double
+// buffered in TMEM, so the epilogue of tile j (8 dedicated warps) runs while the tensor core is already on tile j+1;
+// the TMA / converter / MMA pipelines never drain between tiles (global k-block counters carry the barrier phases).
 template <int EPI, int ACT, bool RES>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 1];
+    __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 4];
     __shared__ uint32_t tmem_base_slot;
     __shared__ float ldj_sm[TC_BM];
-    __shared__ __align__(16) float bias_sm[192];   // this tile's bias (and LayerNorm-q column sums), prefetched
-    __shared__ __align__(16) float csum_sm[192];
-    __shared__ int bias_in_smem;
+    __shared__ __align__(16) float bias_sm2[2][96];   // the tile's bias (and LayerNorm-q column sums), by accumulator buffer
+    __shared__ __align__(16) float csum_sm2[2][96];
+    __shared__ int bias_in_smem2[2];
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024 B alignment
@@ -94,37 +97,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     auto a_raw = [&](int s) { return smem + s * stage_bytes; };
     auto w_hi = [&](int s) { return smem + s * stage_bytes + TC_A_BYTES; };
     auto w_lo = [&](int s) { return smem + s * stage_bytes + TC_A_BYTES + w_bytes; };
+    float* stage_out = reinterpret_cast<float*>(smem + TC_STAGES * stage_bytes);   // 8 warps x [32][20] staging tiles
     uint64_t* full = bars;                                   // [TC_STAGES]  TMA bytes landed
     uint64_t* a_free = bars + TC_STAGES;                     // [TC_STAGES]  converters done reading A smem
     uint64_t* w_free = bars + 2 * TC_STAGES;                 // [TC_STAGES]  MMAs done reading W smem
     uint64_t* conv = bars + 3 * TC_STAGES;                   // [TC_TSTAGES] A hi/lo written to TMEM
     uint64_t* tfree = bars + 3 * TC_STAGES + TC_TSTAGES;     // [TC_TSTAGES] MMAs done reading A TMEM
-    uint64_t* accum = bars + 3 * TC_STAGES + 2 * TC_TSTAGES;
+    uint64_t* acc_full = bars + 3 * TC_STAGES + 2 * TC_TSTAGES;   // [2] accumulators of a tile complete
+    uint64_t* acc_free = acc_full + 2;                            // [2] epilogue has drained them (256 arrivals)
 
-    const long long t_begin = TC_CLOCK();
-    long long t_accum_g = 0, dbg_ld = 0, dbg_math = 0, dbg_st = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TC_BM;
-    const int n_tile = blockIdx.x;
-    // N is cut into gridDim.x tiles whose widths are multiples of 16 and differ by at most 16 (512 -> 96,96,80,80,80,80):
-    // no padded columns go through the tensor core.  The TMA box stays BN rows (the extra rows are the next tile's).
-    const int n_units = (p.g.N + 15) >> 4, n_base = n_units / (int)gridDim.x, n_rem = n_units % (int)gridDim.x;
-    const int tile_n0 = 16 * (n_tile * n_base + min(n_tile, n_rem));
-    const int tile_bn = 16 * (n_base + (n_tile < n_rem ? 1 : 0));
     const int T = p.T1 + p.T2;
-
-    // Thread-block cluster along M (1 x cs x 1): the cs CTAs of a cluster work on the SAME weight tile, so each
-    // loads 1/cs of its rows and TMA-multicasts them to all peers -- the L2 -> SM weight traffic, which dominates
-    // (hi + lo copies, re-read by every 128-row tile), drops by cs.
-    uint32_t cta_rank = 0, cs = 1;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cs));
-    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+    const int n_tiles = p.n_tiles, total_tiles = p.n_tiles * p.m_tiles;
+    // N is cut into n_tiles tiles whose widths are multiples of 16 and differ by at most 16 (512 -> 96,96,80,80,80,80):
+    // no padded columns go through the tensor core.  The TMA box stays BN rows (the extra rows are the next tile's).
+    const int n_units = (p.g.N + 15) >> 4, n_base = n_units / n_tiles, n_rem = n_units % n_tiles;
+    auto tile_n0_of = [&](int nt) { return 16 * (nt * n_base + min(nt, n_rem)); };
+    auto tile_bn_of = [&](int nt) { return 16 * (n_base + (nt < n_rem ? 1 : 0)); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], 128); mbar_init(&w_free[s], cs); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], 128); mbar_init(&w_free[s], 1); }
         for (int s = 0; s < TC_TSTAGES; ++s) { mbar_init(&conv[s], 128); mbar_init(&tfree[s], 1); }
-        mbar_init(accum, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -133,55 +127,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_slot;
-    const long long t_setup = TC_CLOCK();
 
     if (warp == 0) {
         // ===================================================== TMA producer
         if (lane == 0) {
-            for (int t = 0; t < T; ++t) {
-                const int s = t % TC_STAGES;
-                const uint32_t ph = (t / TC_STAGES) & 1;
-                mbar_wait(&a_free[s], ph ^ 1, 100 + t);
-                mbar_wait(&w_free[s], ph ^ 1, 150 + t);
-                mbar_expect_tx(&full[s], (uint32_t)(TC_A_BYTES + 2 * w_bytes));
-                if (t < p.T1) tma_load_2d(&mapA1, a_raw(s), &full[s], t * TC_BK, m0);
-                else          tma_load_2d(&mapA2, a_raw(s), &full[s], (t - p.T1) * TC_BK, m0);
-                if (cs == 1) {
+            uint32_t g = 0;   // k-blocks issued so far (all tiles)
+            for (int L = blockIdx.x; L < total_tiles; L += gridDim.x) {
+                const int n_tile = L % n_tiles, m0 = (L / n_tiles) * TC_BM;
+                const int tile_n0 = tile_n0_of(n_tile);
+                for (int t = 0; t < T; ++t, ++g) {
+                    const int s = g % TC_STAGES;
+                    const uint32_t ph = (g / TC_STAGES) & 1;
+                    mbar_wait(&a_free[s], ph ^ 1, 100 + t);
+                    mbar_wait(&w_free[s], ph ^ 1, 150 + t);
+                    mbar_expect_tx(&full[s], (uint32_t)(TC_A_BYTES + 2 * w_bytes));
+                    if (t < p.T1) tma_load_2d(&mapA1, a_raw(s), &full[s], t * TC_BK, m0);
+                    else          tma_load_2d(&mapA2, a_raw(s), &full[s], (t - p.T1) * TC_BK, m0);
                     tma_load_2d(&mapWhi, w_hi(s), &full[s], t * TC_BK, tile_n0);
                     tma_load_2d(&mapWlo, w_lo(s), &full[s], t * TC_BK, tile_n0);
-                } else {
-                    // my slice of the tile's rows (the W maps are built with box_outer = BN / cs)
-                    const int slice = BN / (int)cs;
-                    const int off = (int)cta_rank * slice;
-                    tma_load_2d_mcast(&mapWhi, w_hi(s) + off * 128, &full[s], t * TC_BK, tile_n0 + off, cmask);
-                    tma_load_2d_mcast(&mapWlo, w_lo(s) + off * 128, &full[s], t * TC_BK, tile_n0 + off, cmask);
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
         // The whole warp runs the loop and ONE ELECTED lane issues: inside a divergent `if (lane == 0)` the compiler
-        // cannot keep the descriptors in uniform registers and wraps every UTCHMMA in an ELECT/vote loop with R2UR
-        // moves (~90 cycles per MMA, above the 88-cycle tensor time of a 128x176x8 TF32 MMA).
-        {
+        // cannot keep the descriptors in uniform registers and wraps every UTCHMMA in an ELECT/vote loop with R2UR moves.
+        uint32_t g = 0, hb = 0;   // k-blocks / half k-blocks consumed so far
+        int it = 0;
+        for (int L = blockIdx.x; L < total_tiles; L += gridDim.x, ++it) {
+            const int n_tile = L % n_tiles;
+            const int tile_bn = tile_bn_of(n_tile);
+            const int buf = it & 1;
             // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2), K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            const uint32_t d_main = tmem + TC_COL_MAIN, d_corr = tmem + TC_COL_CORR;
-            for (int t = 0; t < T; ++t) {
-                const int s = t % TC_STAGES;
-                const uint32_t ph = (t / TC_STAGES) & 1;
-                mbar_wait(&full[s], ph, 200 + t);
+            const uint32_t d_main = tmem + TC_COL_ACC * buf, d_corr = d_main + TC_COL_CORR;
+            mbar_wait(&acc_free[buf], ((it >> 1) & 1) ^ 1, 190);     // the epilogue of tile it-2 has drained this buffer
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int t = 0; t < T; ++t, ++g) {
+                const int s = g % TC_STAGES;
+                mbar_wait(&full[s], (g / TC_STAGES) & 1, 200 + t);
                 const uint64_t dbh = make_kmajor_sw128_desc(smem_u32(w_hi(s)));
                 const uint64_t dbl = make_kmajor_sw128_desc(smem_u32(w_lo(s)));
                 // the A operand arrives in TMEM in HALF k-blocks (16 k: 16 columns hi + 16 lo per stage)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int ts = h;                               // (2t + h) % TC_TSTAGES with TC_TSTAGES == 2
-                    const uint32_t tph = t & 1;                     // ((2t + h) / 2) & 1
-                    mbar_wait(&conv[ts], tph, 300 + t);
+                for (int h = 0; h < 2; ++h, ++hb) {
+                    const int ts = hb % TC_TSTAGES;
+                    mbar_wait(&conv[ts], (hb / TC_TSTAGES) & 1, 300 + t);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t t_hi = tmem + TC_COL_A + 32 * ts, t_lo = t_hi + 16;
                     if (elect_one()) {
@@ -193,31 +186,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                             umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
                             umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (t | k) != 0);
                         }
-                        umma_commit(&tfree[ts]);     // TMEM A stage reusable once these MMAs retire
-                        if (h == 1) {
-                            // W smem stage reusable once these MMAs retire -- every CTA of the cluster writes into it
-                            if (cs == 1) umma_commit(&w_free[s]); else umma_commit_mcast(&w_free[s], cmask);
-                        }
+                        umma_commit(&tfree[ts]);                 // TMEM A stage reusable once these MMAs retire
+                        if (h == 1) umma_commit(&w_free[s]);     // W smem stage reusable once these MMAs retire
                     }
                     __syncwarp();
                 }
             }
-            if (elect_one()) umma_commit(accum);              // accumulators complete
+            if (elect_one()) umma_commit(&acc_full[buf]);        // accumulators of this tile complete
             __syncwarp();
         }
-    } else {
+    } else if (warp < 6) {
+        // ===================================================== converters: fp32 smem row -> (hi, lo) in TMEM
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
         const int row_in_tile = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        if (warp < 6) {
-            // ===================================================== converters: fp32 smem row -> (hi, lo) in TMEM
-            for (int t = 0; t < T; ++t) {
-                const int s = t % TC_STAGES;
-                const uint32_t ph = (t / TC_STAGES) & 1;
-                mbar_wait(&full[s], ph, 400 + t);
+        uint32_t g = 0, hb = 0;
+        for (int L = blockIdx.x; L < total_tiles; L += gridDim.x) {
+            for (int t = 0; t < T; ++t, ++g) {
+                const int s = g % TC_STAGES;
+                mbar_wait(&full[s], (g / TC_STAGES) & 1, 400 + t);
                 const float4* rowp = reinterpret_cast<const float4*>(a_raw(s) + row_in_tile * 128);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < 2; ++h, ++hb) {
                     uint32_t hl[32];   // this half k-block: [0,16) hi, [16,32) lo  -> one 32-column TMEM stage
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
@@ -236,9 +226,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         }
                     }
                     if (h == 1) mbar_arrive(&a_free[s]);   // whole row is in registers: the A smem stage may be refilled
-                    const int ts = h;
-                    const uint32_t tph = t & 1;
-                    mbar_wait(&tfree[ts], tph ^ 1, 450 + t);
+                    const int ts = hb % TC_TSTAGES;
+                    mbar_wait(&tfree[ts], ((hb / TC_TSTAGES) & 1) ^ 1, 450 + t);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     tmem_st32(tmem + lane_addr + TC_COL_A + 32 * ts, hl);
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -247,285 +236,281 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 }
             }
         }
-        else {
-            // epilogue-only warps are idle during the main loop: fetch this tile's bias row (a cold L2 miss per
-            // 16-column chunk otherwise -- measured ~600 cycles each) into shared memory
-            const GemmArgs& a = p.g;
-            const int n0p = tile_n0;
-            const int last_row = min(m0 + TC_BM, a.M) - 1;
-            const bool one_group = a.bias_group <= 0 || (m0 / a.bias_group) == (last_row / a.bias_group);
-            const float* brow = a.bias;
-            if (a.bias && a.bias_group > 0) brow = a.bias + (size_t)(m0 / a.bias_group) * a.bias_ld;
-            for (int i = threadIdx.x - 192; i < tile_bn; i += 128) {
-                const int col = n0p + i;
-                bias_sm[i] = (brow && one_group && col < a.N) ? brow[col] : 0.f;
-                csum_sm[i] = (EPI == FC_EPI_LNQ && col < a.N) ? a.csum[col] : 0.f;
-            }
-            if (threadIdx.x == 192) bias_in_smem = (one_group && m0 < a.M) ? 1 : 0;
-        }
-        // ===================================================== epilogue (8 warps)
+    } else {
+        // ===================================================== epilogue (8 warps, 256 threads)
         // TMEM lane = row within the tile; the two warps of a quadrant take alternate 16-column chunks
-        const int half = warp >= 6 ? 1 : 0;
-        mbar_wait(accum, 0, 500);
-        t_accum_g = TC_CLOCK();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("bar.sync 2, 256;" ::: "memory");    // bias_sm / csum_sm visible to all 8 epilogue warps
-        const bool bias_smem = bias_in_smem != 0;
+        const int quad = warp & 3;
+        const int row_in_tile = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const int ew = warp - 6;                     // 0..7
+        const int half = ew >> 2;
+        const int etid = threadIdx.x - 192;          // 0..255
         const GemmArgs& a = p.g;
-        const int row = m0 + row_in_tile;
-        const bool row_ok = row < a.M;
-        const int n0 = tile_n0;
-        float ldj = 0.f;
-        float mu = 0.f, rstd = 0.f;
-        if (EPI == FC_EPI_LNQ && row_ok) { mu = a.row_mu[row]; rstd = a.row_rstd[row]; }
-        const float* bias_row = a.bias;
-        if (a.bias && a.bias_group > 0 && row_ok) bias_row = a.bias + (size_t)(row / a.bias_group) * a.bias_ld;
         // per-warp staging tile [32 rows][16 + 4 pad] (rows 16-byte aligned; a thread's own-row float4 accesses are
-        // conflict free, the transposed ones 2-way at worst); the pipeline stages are dead once `accum` has fired
-        float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 20);
-        const int row0 = m0 + quad * 32;
-        const bool vec_base = row0 + 32 <= a.M && (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0;
-        const bool vec_res = RES && (a.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0 &&
-                             (!a.res_scale || (reinterpret_cast<uintptr_t>(a.res_scale) & 15) == 0);
-        long long d_ld = 0, d_math = 0, d_st = 0;
-        for (int c0 = half * 16; c0 < tile_bn; c0 += 32) {
-            uint32_t r[16];
-            float v[16];
-            __syncwarp();
-            const long long q0 = TC_CLOCK();
-            tmem_ld16(tmem + lane_addr + TC_COL_MAIN + (uint32_t)c0, r);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        // conflict free, the transposed ones 2-way at worst)
+        float* stg = stage_out + ew * (32 * 20);
+        int it = 0;
+        for (int L = blockIdx.x; L < total_tiles; L += gridDim.x, ++it) {
+            const int n_tile = L % n_tiles, m0 = (L / n_tiles) * TC_BM;
+            const int tile_n0 = tile_n0_of(n_tile), tile_bn = tile_bn_of(n_tile);
+            const int buf = it & 1;
+            float* bias_sm = bias_sm2[buf];
+            float* csum_sm = csum_sm2[buf];
             {
-                tmem_ld16(tmem + lane_addr + TC_COL_CORR + (uint32_t)c0, r);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
-            }
-            const long long q1 = TC_CLOCK();
-            d_ld += q1 - q0;
-            const int col = n0 + c0;
-            if (col >= a.N) continue;                     // warp-uniform
-            if (EPI == FC_EPI_LNQ) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (col + j < a.N) v[j] = rstd * (v[j] - mu * csum_sm[c0 + j]) + bias_sm[c0 + j];
-            } else if (bias_row && bias_smem) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += bias_sm[c0 + j];   // zero beyond N
-            } else if (bias_row) {
-                if (col + 15 < a.N && ((reinterpret_cast<uintptr_t>(bias_row + col) & 15) == 0)) {
-                    // four 16-byte loads at a warp-uniform address (issued back to back) instead of 16 predicated ones
-                    const float4* b4 = reinterpret_cast<const float4*>(bias_row + col);
-                    const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1), b2 = __ldg(b4 + 2), b3 = __ldg(b4 + 3);
-                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                    v[8] += b2.x; v[9] += b2.y; v[10] += b2.z; v[11] += b2.w;
-                    v[12] += b3.x; v[13] += b3.y; v[14] += b3.z; v[15] += b3.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) if (col + j < a.N) v[j] += bias_row[col + j];
+                // while the tensor core is still on this tile: fetch its bias row (a cold L2 miss per 16-column chunk
+                // otherwise -- measured ~600 cycles each) into shared memory
+                const int last_row = min(m0 + TC_BM, a.M) - 1;
+                const bool one_group = a.bias_group <= 0 || (m0 / a.bias_group) == (last_row / a.bias_group);
+                const float* brow = a.bias;
+                if (a.bias && a.bias_group > 0) brow = a.bias + (size_t)(m0 / a.bias_group) * a.bias_ld;
+                for (int i = etid; i < tile_bn; i += 256) {
+                    const int col = tile_n0 + i;
+                    bias_sm[i] = (brow && one_group && col < a.N) ? brow[col] : 0.f;
+                    csum_sm[i] = (EPI == FC_EPI_LNQ && col < a.N) ? a.csum[col] : 0.f;
                 }
+                if (etid == 0) bias_in_smem2[buf] = (one_group && m0 < a.M) ? 1 : 0;
             }
-            if (EPI == FC_EPI_STORE || EPI == FC_EPI_LNQ) {
-                // Global traffic goes through a per-warp staging tile so that it is COALESCED: with one thread per
-                // row, direct loads/stores touch 32 different lines per instruction (ncu: the residual layers took 2x
-                // as long as the plain ones).  Each warp instruction below moves 2 rows x 64 contiguous bytes.
-                const int sr = lane >> 4, sc = lane & 15;
-                // fast path (every full interior chunk): 16-byte accesses, 8 rows x 64 B per warp instruction, no
-                // per-element predicates or address arithmetic -- the scalar form below cost ~19 instructions per
-                // element, more than the GELU
-                const bool vec = vec_base && col + 16 <= a.N;
-                const int r8 = lane >> 2, c4 = (lane & 3) * 4;
-                float4* my_row4 = reinterpret_cast<float4*>(stg + lane * 20);
-                if (RES) {
-                    if (vec && vec_res) {
-                        const float* rp = a.res + (size_t)(row0 + r8) * a.ldres + col + c4;
-                        float4 rx4[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) rx4[i] = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(8 * i) * a.ldres));
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + (r8 + 8 * i) * 20 + c4) = rx4[i];
-                        __syncwarp();
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 rv = my_row4[q];
-                            if (a.res_scale) {
-                                const float4 rs = *reinterpret_cast<const float4*>(a.res_scale + col + 4 * q);
-                                v[4 * q] = fmaf(rs.x, rv.x, v[4 * q]); v[4 * q + 1] = fmaf(rs.y, rv.y, v[4 * q + 1]);
-                                v[4 * q + 2] = fmaf(rs.z, rv.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(rs.w, rv.w, v[4 * q + 3]);
-                            } else {
-                                v[4 * q] += rv.x; v[4 * q + 1] += rv.y; v[4 * q + 2] += rv.z; v[4 * q + 3] += rv.w;
-                            }
-                        }
-                        __syncwarp();
+            mbar_wait(&acc_full[buf], (it >> 1) & 1, 500);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 2, 256;" ::: "memory");    // bias_sm / csum_sm visible to all 8 epilogue warps
+            const bool bias_smem = bias_in_smem2[buf] != 0;
+            const uint32_t acc_main = tmem + lane_addr + TC_COL_ACC * buf, acc_corr = acc_main + TC_COL_CORR;
+            const int row = m0 + row_in_tile;
+            const bool row_ok = row < a.M;
+            const int n0 = tile_n0;
+            float ldj = 0.f;
+            float mu = 0.f, rstd = 0.f;
+            if (EPI == FC_EPI_LNQ && row_ok) { mu = a.row_mu[row]; rstd = a.row_rstd[row]; }
+            const float* bias_row = a.bias;
+            if (a.bias && a.bias_group > 0 && row_ok) bias_row = a.bias + (size_t)(row / a.bias_group) * a.bias_ld;
+            const int row0 = m0 + quad * 32;
+            const bool vec_base = row0 + 32 <= a.M && (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0;
+            const bool vec_res = RES && (a.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0 &&
+                                 (!a.res_scale || (reinterpret_cast<uintptr_t>(a.res_scale) & 15) == 0);
+            for (int c0 = half * 16; c0 < tile_bn; c0 += 32) {
+                uint32_t r[16];
+                float v[16];
+                __syncwarp();
+                tmem_ld16(acc_main + (uint32_t)c0, r);
+    #pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                {
+                    tmem_ld16(acc_corr + (uint32_t)c0, r);
+    #pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+                }
+                const int col = n0 + c0;
+                if (col >= a.N) continue;                     // warp-uniform
+                if (EPI == FC_EPI_LNQ) {
+    #pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (col + j < a.N) v[j] = rstd * (v[j] - mu * csum_sm[c0 + j]) + bias_sm[c0 + j];
+                } else if (bias_row && bias_smem) {
+    #pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += bias_sm[c0 + j];   // zero beyond N
+                } else if (bias_row) {
+                    if (col + 15 < a.N && ((reinterpret_cast<uintptr_t>(bias_row + col) & 15) == 0)) {
+                        // four 16-byte loads at a warp-uniform address (issued back to back) instead of 16 predicated ones
+                        const float4* b4 = reinterpret_cast<const float4*>(bias_row + col);
+                        const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1), b2 = __ldg(b4 + 2), b3 = __ldg(b4 + 3);
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                        v[8] += b2.x; v[9] += b2.y; v[10] += b2.z; v[11] += b2.w;
+                        v[12] += b3.x; v[13] += b3.y; v[14] += b3.z; v[15] += b3.w;
                     } else {
-                        float rx[16];   // all loads first, then all shared stores: no store->load ordering stalls
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int gr = row0 + 2 * i + sr;
-                            rx[i] = (gr < a.M && col + sc < a.N) ? __ldg(a.res + (size_t)gr * a.ldres + col + sc) : 0.f;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) stg[(2 * i + sr) * 20 + sc] = rx[i];
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float rv = stg[lane * 20 + j];
-                            if (col + j < a.N) v[j] = a.res_scale ? fmaf(a.res_scale[col + j], rv, v[j]) : v[j] + rv;
-                        }
-                        __syncwarp();
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) if (col + j < a.N) v[j] += bias_row[col + j];
                     }
                 }
-                if (ACT == FC_ACT_GELU) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fc_gelu_erf_fast(v[j]);
-                } else if (ACT == FC_ACT_LRELU) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fc_leaky_relu02(v[j]);
-                } else if (ACT == FC_ACT_RELU) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                const long long q2 = TC_CLOCK();
-                d_math += q2 - q1;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) my_row4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                __syncwarp();
-                if (vec) {
-                    float* gp = a.C + (size_t)(row0 + r8) * a.ldc + col + c4;
-                    float4 ox4[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) ox4[i] = *reinterpret_cast<const float4*>(stg + (r8 + 8 * i) * 20 + c4);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(gp + (size_t)(8 * i) * a.ldc) = ox4[i];
-                } else {
-                    float ox[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) ox[i] = stg[(2 * i + sr) * 20 + sc];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int gr = row0 + 2 * i + sr;
-                        if (gr < a.M && col + sc < a.N) a.C[(size_t)gr * a.ldc + col + sc] = ox[i];
-                    }
-                }
-                __syncwarp();
-                d_st += TC_CLOCK() - q2;
-            } else if (EPI == FC_EPI_KVSPLIT) {
-                // to_kv feeding the tcgen05 attention (attention_tc.cu): TF32 hi/lo copies, v transposed per cloud.
-                // BN = 64, so N-tile 0 is k and N-tile 1 is v.
-                float lo16[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float h = __uint_as_float((__float_as_uint(v[j]) + 0x1000u) & 0xffffe000u);
-                    lo16[j] = v[j] - h;
-                    v[j] = h;
-                }
-                if (col < 64) {
-                    // k: rows stay rows; two staged, coalesced 16-byte passes (hi, then lo)
+                if (EPI == FC_EPI_STORE || EPI == FC_EPI_LNQ) {
+                    // Global traffic goes through a per-warp staging tile so that it is COALESCED: with one thread per
+                    // row, direct loads/stores touch 32 different lines per instruction (ncu: the residual layers took 2x
+                    // as long as the plain ones).  Each warp instruction below moves 2 rows x 64 contiguous bytes.
+                    const int sr = lane >> 4, sc = lane & 15;
+                    // fast path (every full interior chunk): 16-byte accesses, 8 rows x 64 B per warp instruction, no
+                    // per-element predicates or address arithmetic -- the scalar form below cost ~19 instructions per
+                    // element, more than the GELU
+                    const bool vec = vec_base && col + 16 <= a.N;
                     const int r8 = lane >> 2, c4 = (lane & 3) * 4;
                     float4* my_row4 = reinterpret_cast<float4*>(stg + lane * 20);
-#pragma unroll
-                    for (int pass = 0; pass < 2; ++pass) {
-                        float* dstbase = pass == 0 ? a.C : a.kv_klo;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            my_row4[q] = pass == 0 ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3])
-                                                   : make_float4(lo16[4 * q], lo16[4 * q + 1], lo16[4 * q + 2], lo16[4 * q + 3]);
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int gr = row0 + r8 + 8 * i;
-                            if (gr < a.M)
-                                *reinterpret_cast<float4*>(dstbase + (size_t)gr * 64 + col + c4) =
-                                    *reinterpret_cast<const float4*>(stg + (r8 + 8 * i) * 20 + c4);
+                    if (RES) {
+                        if (vec && vec_res) {
+                            const float* rp = a.res + (size_t)(row0 + r8) * a.ldres + col + c4;
+                            float4 rx4[4];
+    #pragma unroll
+                            for (int i = 0; i < 4; ++i) rx4[i] = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(8 * i) * a.ldres));
+    #pragma unroll
+                            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + (r8 + 8 * i) * 20 + c4) = rx4[i];
+                            __syncwarp();
+    #pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 rv = my_row4[q];
+                                if (a.res_scale) {
+                                    const float4 rs = *reinterpret_cast<const float4*>(a.res_scale + col + 4 * q);
+                                    v[4 * q] = fmaf(rs.x, rv.x, v[4 * q]); v[4 * q + 1] = fmaf(rs.y, rv.y, v[4 * q + 1]);
+                                    v[4 * q + 2] = fmaf(rs.z, rv.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(rs.w, rv.w, v[4 * q + 3]);
+                                } else {
+                                    v[4 * q] += rv.x; v[4 * q + 1] += rv.y; v[4 * q + 2] += rv.z; v[4 * q + 3] += rv.w;
+                                }
+                            }
+                            __syncwarp();
+                        } else {
+                            float rx[16];   // all loads first, then all shared stores: no store->load ordering stalls
+    #pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const int gr = row0 + 2 * i + sr;
+                                rx[i] = (gr < a.M && col + sc < a.N) ? __ldg(a.res + (size_t)gr * a.ldres + col + sc) : 0.f;
+                            }
+    #pragma unroll
+                            for (int i = 0; i < 16; ++i) stg[(2 * i + sr) * 20 + sc] = rx[i];
+                            __syncwarp();
+    #pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float rv = stg[lane * 20 + j];
+                                if (col + j < a.N) v[j] = a.res_scale ? fmaf(a.res_scale[col + j], rv, v[j]) : v[j] + rv;
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
-                } else if (row_ok) {
-                    // v: transposed; the 32 lanes of a warp hold 32 consecutive keys -> each store instruction writes
-                    // one contiguous run per cloud
-                    const int bcl = row / a.kv_nc, key = row - bcl * a.kv_nc;
-                    float* th = a.kv_vthi + ((size_t)bcl * 64 + (col - 64)) * a.kv_ncp + key;
-                    float* tl = a.kv_vtlo + ((size_t)bcl * 64 + (col - 64)) * a.kv_ncp + key;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) { th[(size_t)j * a.kv_ncp] = v[j]; tl[(size_t)j * a.kv_ncp] = lo16[j]; }
-                }
-            } else if (!row_ok) {
-                // nothing: out-of-range rows of the coupling / augment epilogues
-            } else if (EPI == FC_EPI_COUPLING) {
-                // reference models/affine_coupling.py:40-46 (see gemm.cu for the arithmetic notes)
-                float* xrow = a.x + (size_t)row * a.ldx + a.col0 + (col >> 1);
-                if (col + 16 <= a.N && (reinterpret_cast<uintptr_t>(xrow) & 7) == 0) {
-                    // interior chunk: the row's 8 latent values move as four 8-byte accesses, loads first
-                    float2 xv[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) xv[q] = *reinterpret_cast<const float2*>(xrow + 2 * q);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float sig0 = 1.0f / (1.0f + expf(-v[4 * q]));
-                        const float sc0 = (2.0f * sig0 - 1.0f) + 1.0f;
-                        const float sig1 = 1.0f / (1.0f + expf(-v[4 * q + 2]));
-                        const float sc1 = (2.0f * sig1 - 1.0f) + 1.0f;
-                        xv[q].x = fmaf(xv[q].x, sc0, v[4 * q + 1]);
-                        xv[q].y = fmaf(xv[q].y, sc1, v[4 * q + 3]);
-                        ldj += logf(sc0);
-                        ldj += logf(sc1);
+                    if (ACT == FC_ACT_GELU) {
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fc_gelu_erf_fast(v[j]);
+                    } else if (ACT == FC_ACT_LRELU) {
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fc_leaky_relu02(v[j]);
+                    } else if (ACT == FC_ACT_RELU) {
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float2*>(xrow + 2 * q) = xv[q];
-                } else {
-#pragma unroll
+    #pragma unroll
+                    for (int q = 0; q < 4; ++q) my_row4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    __syncwarp();
+                    if (vec) {
+                        float* gp = a.C + (size_t)(row0 + r8) * a.ldc + col + c4;
+                        float4 ox4[4];
+    #pragma unroll
+                        for (int i = 0; i < 4; ++i) ox4[i] = *reinterpret_cast<const float4*>(stg + (r8 + 8 * i) * 20 + c4);
+    #pragma unroll
+                        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(gp + (size_t)(8 * i) * a.ldc) = ox4[i];
+                    } else {
+                        float ox[16];
+    #pragma unroll
+                        for (int i = 0; i < 16; ++i) ox[i] = stg[(2 * i + sr) * 20 + sc];
+    #pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int gr = row0 + 2 * i + sr;
+                            if (gr < a.M && col + sc < a.N) a.C[(size_t)gr * a.ldc + col + sc] = ox[i];
+                        }
+                    }
+                    __syncwarp();
+                } else if (EPI == FC_EPI_KVSPLIT) {
+                    // to_kv feeding the tcgen05 attention (attention_tc.cu): TF32 hi/lo copies, v transposed per cloud.
+                    // BN = 64, so N-tile 0 is k and N-tile 1 is v.
+                    float lo16[16];
+    #pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float h = __uint_as_float((__float_as_uint(v[j]) + 0x1000u) & 0xffffe000u);
+                        lo16[j] = v[j] - h;
+                        v[j] = h;
+                    }
+                    if (col < 64) {
+                        // k: rows stay rows; two staged, coalesced 16-byte passes (hi, then lo)
+                        const int r8 = lane >> 2, c4 = (lane & 3) * 4;
+                        float4* my_row4 = reinterpret_cast<float4*>(stg + lane * 20);
+    #pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            float* dstbase = pass == 0 ? a.C : a.kv_klo;
+    #pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                my_row4[q] = pass == 0 ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3])
+                                                       : make_float4(lo16[4 * q], lo16[4 * q + 1], lo16[4 * q + 2], lo16[4 * q + 3]);
+                            __syncwarp();
+    #pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int gr = row0 + r8 + 8 * i;
+                                if (gr < a.M)
+                                    *reinterpret_cast<float4*>(dstbase + (size_t)gr * 64 + col + c4) =
+                                        *reinterpret_cast<const float4*>(stg + (r8 + 8 * i) * 20 + c4);
+                            }
+                            __syncwarp();
+                        }
+                    } else if (row_ok) {
+                        // v: transposed; the 32 lanes of a warp hold 32 consecutive keys -> each store instruction writes
+                        // one contiguous run per cloud
+                        const int bcl = row / a.kv_nc, key = row - bcl * a.kv_nc;
+                        float* th = a.kv_vthi + ((size_t)bcl * 64 + (col - 64)) * a.kv_ncp + key;
+                        float* tl = a.kv_vtlo + ((size_t)bcl * 64 + (col - 64)) * a.kv_ncp + key;
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) { th[(size_t)j * a.kv_ncp] = v[j]; tl[(size_t)j * a.kv_ncp] = lo16[j]; }
+                    }
+                } else if (!row_ok) {
+                    // nothing: out-of-range rows of the coupling / augment epilogues
+                } else if (EPI == FC_EPI_COUPLING) {
+                    // reference models/affine_coupling.py:40-46 (see gemm.cu for the arithmetic notes)
+                    float* xrow = a.x + (size_t)row * a.ldx + a.col0 + (col >> 1);
+                    if (col + 16 <= a.N && (reinterpret_cast<uintptr_t>(xrow) & 7) == 0) {
+                        // interior chunk: the row's 8 latent values move as four 8-byte accesses, loads first
+                        float2 xv[4];
+    #pragma unroll
+                        for (int q = 0; q < 4; ++q) xv[q] = *reinterpret_cast<const float2*>(xrow + 2 * q);
+    #pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float sig0 = 1.0f / (1.0f + expf(-v[4 * q]));
+                            const float sc0 = (2.0f * sig0 - 1.0f) + 1.0f;
+                            const float sig1 = 1.0f / (1.0f + expf(-v[4 * q + 2]));
+                            const float sc1 = (2.0f * sig1 - 1.0f) + 1.0f;
+                            xv[q].x = fmaf(xv[q].x, sc0, v[4 * q + 1]);
+                            xv[q].y = fmaf(xv[q].y, sc1, v[4 * q + 3]);
+                            ldj += logf(sc0);
+                            ldj += logf(sc1);
+                        }
+    #pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<float2*>(xrow + 2 * q) = xv[q];
+                    } else {
+    #pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (col + 2 * q + 1 < a.N) {
+                                const float sig = 1.0f / (1.0f + expf(-v[2 * q]));
+                                const float sc = (2.0f * sig - 1.0f) + 1.0f;
+                                float* xp = xrow + q;
+                                *xp = fmaf(*xp, sc, v[2 * q + 1]);
+                                ldj += logf(sc);
+                            }
+                        }
+                    }
+                } else if (EPI == FC_EPI_AUGMENT) {
+                    // reference models/distributions.py:128-153 + models/augmenter.py:49-63
+    #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         if (col + 2 * q + 1 < a.N) {
-                            const float sig = 1.0f / (1.0f + expf(-v[2 * q]));
-                            const float sc = (2.0f * sig - 1.0f) + 1.0f;
-                            float* xp = xrow + q;
-                            *xp = fmaf(*xp, sc, v[2 * q + 1]);
-                            ldj += logf(sc);
+                            const int j = (col >> 1) + q;
+                            const float e = a.eps[(size_t)row * a.ld_eps + j];
+                            a.x[(size_t)row * a.ldx + a.col0 + j] = fmaf(expf(v[2 * q + 1]), e, v[2 * q]);
+                            ldj += fmaf(0.5f * e, e, v[2 * q + 1]) + 0.91893853320467274178f;
                         }
                     }
                 }
-            } else if (EPI == FC_EPI_AUGMENT) {
-                // reference models/distributions.py:128-153 + models/augmenter.py:49-63
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (col + 2 * q + 1 < a.N) {
-                        const int j = (col >> 1) + q;
-                        const float e = a.eps[(size_t)row * a.ld_eps + j];
-                        a.x[(size_t)row * a.ldx + a.col0 + j] = fmaf(expf(v[2 * q + 1]), e, v[2 * q]);
-                        ldj += fmaf(0.5f * e, e, v[2 * q + 1]) + 0.91893853320467274178f;
-                    }
+            }
+            if (EPI == FC_EPI_COUPLING || EPI == FC_EPI_AUGMENT) {
+                // the two threads that share a row combine their partial log-dets in a fixed order (deterministic)
+                if (half == 1) ldj_sm[row_in_tile] = ldj;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half == 0 && row_ok) {
+                    const float tot = ldj + ldj_sm[row_in_tile];
+                    float* pp = a.part + (size_t)n_tile * a.M + row;
+                    if (EPI == FC_EPI_COUPLING) *pp += tot; else *pp = tot;
                 }
             }
+            // this thread's TMEM reads of the tile are complete (every tcgen05.ld above is followed by its wait)
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_free[buf]);
         }
-        dbg_ld = d_ld; dbg_math = d_math; dbg_st = d_st;
-        if (EPI == FC_EPI_COUPLING || EPI == FC_EPI_AUGMENT) {
-            // the two threads that share a row combine their partial log-dets in a fixed order (deterministic)
-            if (half == 1) ldj_sm[row_in_tile] = ldj;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (half == 0 && row_ok) {
-                const float tot = ldj + ldj_sm[row_in_tile];
-                float* pp = a.part + (size_t)n_tile * a.M + row;
-                if (EPI == FC_EPI_COUPLING) *pp += tot; else *pp = tot;
-            }
-        }
-    }
-    if (TC_PHASE_TIMERS && p.debug && threadIdx.x == 64) {
-        const long long t_end = TC_CLOCK();
-        atomicAdd(&fc_tc_dbg[0], 1ull);
-        atomicAdd(&fc_tc_dbg[1], (unsigned long long)(t_accum_g - t_setup));
-        atomicAdd(&fc_tc_dbg[2], (unsigned long long)(t_end - t_accum_g));
-        atomicAdd(&fc_tc_dbg[3], (unsigned long long)(t_setup - t_begin));
-        atomicAdd(&fc_tc_dbg[4], (unsigned long long)dbg_ld);
-        atomicAdd(&fc_tc_dbg[5], (unsigned long long)dbg_math);
-        atomicAdd(&fc_tc_dbg[6], (unsigned long long)dbg_st);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS));
     }
-    if (cs > 1) cluster_sync_all();   // nobody exits while a peer may still arrive on its barriers
 }
 
 // ----------------------------------------------------------------------------- host: tensor maps
@@ -592,8 +577,7 @@ cudaError_t launch_tc(const cudaLaunchConfig_t& cfg, const CUtensorMap& mA1, con
                       const CUtensorMap& mWl, const TcParams& p) {
     static bool configured = false;   // one per instantiation
     if (!configured) {
-        // 2 stages x (16 KB A + 2 x 12 KB W at BN=96) + 1 KB alignment slack; static smem (barriers) comes on top
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -615,40 +599,26 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     p.BN = fc_tc_bn(a.N);
     p.T1 = fc_tc_kpad(a.K1) / TC_BK;
     p.T2 = a.K2 ? fc_tc_kpad(a.K2) / TC_BK : 0;
-    static int dbg_env = -1;
-    if (dbg_env < 0) { const char* e = getenv("FC_TC_DEBUG"); dbg_env = (e && e[0] == '1') ? 1 : 0; }
-    p.debug = dbg_env;
     FC_REQUIRE(p.BN <= 96 && (p.BN & 15) == 0);
     FC_REQUIRE(a.ldk == (p.T1 + p.T2) * TC_BK);
-    const int n_tiles = fc_tc_n_tiles(a.N);
-    int m_tiles = (a.M + TC_BM - 1) / TC_BM;
-    // cluster size along M (weight-tile TMA multicast).  Measured on B200: no gain at 2 or 4 (the L2 already serves
-    // the re-reads; consistent with B300_MICROARCH.md 'MC ~ UC at cluster size <= 4'), so the default is 1;
-    // FC_TC_CLUSTER=2|4 enables it
-    static int cs_env = -1;
-    if (cs_env < 0) { const char* e = getenv("FC_TC_CLUSTER"); cs_env = e ? atoi(e) : 1; if (cs_env != 1 && cs_env != 2 && cs_env != 4) cs_env = 1; }
-    int cs = cs_env;
-    while (cs > 1 && (m_tiles < cs || (p.BN % (8 * cs)) != 0)) cs >>= 1;
-    m_tiles = (m_tiles + cs - 1) / cs * cs;   // padded M tiles run on out-of-range rows (TMA zero fill, stores masked)
+    p.n_tiles = fc_tc_n_tiles(a.N);
+    p.m_tiles = (a.M + TC_BM - 1) / TC_BM;
     CUtensorMap mA1, mA2, mWh, mWl;
     if (!get_map(a.A1, (uint64_t)a.K1, (uint64_t)a.M, (uint64_t)a.lda1, TC_BM, &mA1)) return FC_ERR_CUDA;
     if (a.K2) { if (!get_map(a.A2, (uint64_t)a.K2, (uint64_t)a.M, (uint64_t)a.lda2, TC_BM, &mA2)) return FC_ERR_CUDA; }
     else mA2 = mA1;
-    const uint32_t wbox = (uint32_t)(p.BN / cs);
-    if (!get_map(a.Whi, (uint64_t)a.ldk, (uint64_t)n_tiles * p.BN, (uint64_t)a.ldk, wbox, &mWh)) return FC_ERR_CUDA;
-    if (!get_map(a.Wlo, (uint64_t)a.ldk, (uint64_t)n_tiles * p.BN, (uint64_t)a.ldk, wbox, &mWl)) return FC_ERR_CUDA;
-    const int smem = TC_STAGES * (TC_A_BYTES + 2 * p.BN * TC_BK * 4) + 1024;
+    if (!get_map(a.Whi, (uint64_t)a.ldk, (uint64_t)p.n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWh)) return FC_ERR_CUDA;
+    if (!get_map(a.Wlo, (uint64_t)a.ldk, (uint64_t)p.n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWl)) return FC_ERR_CUDA;
+    static int nsm = 0;
+    if (!nsm) { int dev = 0; FC_CUDA_OK(cudaGetDevice(&dev)); FC_CUDA_OK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev)); }
+    const int total_tiles = p.n_tiles * p.m_tiles;
     FcProfScope prof(FC_CLS_GEMM_TC, 2.0 * a.M * a.N * (a.K1 + a.K2),
                      4.0 * ((double)a.M * (a.K1 + a.K2) + (double)a.N * (a.K1 + a.K2) + (double)a.M * a.N), stream);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_tiles, m_tiles);
+    cfg.gridDim = dim3(total_tiles < nsm ? total_tiles : nsm);      // persistent: one CTA per SM
     cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = cs; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
     const bool res = a.res != nullptr;
     cudaError_t le = cudaErrorInvalidValue;
     if (a.epi == FC_EPI_STORE) {
@@ -677,10 +647,8 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     return FC_OK;
 }
 
-// debug: read and reset the phase counters of gemm_tc_kernel (FC_TC_DEBUG=1)
-extern "C" __attribute__((visibility("default"))) int fc_debug_tc_phases(unsigned long long* out4) {
-    if (cudaMemcpyFromSymbol(out4, fc_tc_dbg, 8 * sizeof(unsigned long long)) != cudaSuccess) return FC_ERR_CUDA;
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (cudaMemcpyToSymbol(fc_tc_dbg, z, sizeof(z)) != cudaSuccess) return FC_ERR_CUDA;
-    return FC_OK;
+// (the per-CTA phase counters of the non-persistent kernel are gone; the entry point stays for scripts/tc_phases.py)
+extern "C" __attribute__((visibility("default"))) int fc_debug_tc_phases(unsigned long long* out8) {
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    return FC_ERR_UNSUPPORTED;
 }
