@@ -200,7 +200,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
         const int row_in_tile = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        // Software pipelined by one half k-block: the tcgen05.st of half h is in flight while half h+1 is loaded and
+        // split; only then is it awaited and published (conv[]), so the store latency is off the critical path.
         uint32_t g = 0, hb = 0;
+        int pending = -1;        // TMEM stage whose store has been issued but not yet published
         for (int L = blockIdx.x; L < total_tiles; L += gridDim.x) {
             for (int t = 0; t < T; ++t, ++g) {
                 const int s = g % TC_STAGES;
@@ -226,15 +229,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         }
                     }
                     if (h == 1) mbar_arrive(&a_free[s]);   // whole row is in registers: the A smem stage may be refilled
+                    if (pending >= 0) {
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive(&conv[pending]);
+                    }
                     const int ts = hb % TC_TSTAGES;
                     mbar_wait(&tfree[ts], ((hb / TC_TSTAGES) & 1) ^ 1, 450 + t);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     tmem_st32(tmem + lane_addr + TC_COL_A + 32 * ts, hl);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&conv[ts]);
+                    pending = ts;
                 }
             }
+        }
+        if (pending >= 0) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&conv[pending]);
         }
     } else {
         // ===================================================== epilogue (8 warps, 256 threads)
