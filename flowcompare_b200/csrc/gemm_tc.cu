@@ -42,7 +42,7 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                      // 32 fp32 = one 128-byte swizzle row
-constexpr int TC_STAGES = 4;                   // shared-memory stages (k-blocks in flight)
+constexpr int TC_STAGES = 5;                   // shared-memory stages: a load is issued 4 k-blocks of tensor time (~1.4 us) ahead
 constexpr int TC_TSTAGES = 4;                  // TMEM stages of the A operand, each HALF a k-block
 constexpr int TC_THREADS = 448;                // TMA, MMA, 4 converter warps, 8 epilogue warps
 // phase timers (scripts/tc_phases.py): compiled out by default, build a variant with -DTC_PHASE_TIMERS=1
@@ -56,7 +56,7 @@ constexpr int TC_THREADS = 448;                // TMA, MMA, 4 converter warps, 8
 #endif
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_TMEM_COLS = 512;                // one persistent CTA per SM
-// 4 stages x (16 KB A + 2 x 12 KB W at BN = 96) + 8 staging tiles of the epilogue + 1 KB alignment slack
+// 5 stages x (16 KB A + 2 x 12 KB W at BN = 96) + 8 staging tiles of the epilogue + 1 KB alignment slack
 constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + 2 * 96 * TC_BK * 4) + 8 * 32 * 20 * 4 + 1024;
 constexpr int TC_COL_ACC = 192;                // accumulator buffer b: main at 192*b, compensation at 192*b + 96
 constexpr int TC_COL_CORR = 96;
@@ -68,6 +68,18 @@ struct TcParams {
     int T1, T2;    // k-blocks of segment 1 / 2
     int n_tiles, m_tiles;
 };
+
+// phase counters (a -DTC_PHASE_TIMERS=1 build, scripts/tc_phases.py): per CTA, cycles
+//  [0] CTAs  [1] MMA warp total  [2] MMA waits on full[]  [3] on conv[]  [4] on acc_free[]
+//  [5] converter total  [6] converter waits on full[]  [7] on tfree[]  [8] epilogue total  [9] epilogue waits on acc_full[]
+__device__ unsigned long long fc_tc_dbg[16];
+#if TC_PHASE_TIMERS
+#define TC_T(v) const long long v = clock64()
+#define TC_ACC(dst, a, b) dst += (b) - (a)
+#else
+#define TC_T(v) const int v = 0
+#define TC_ACC(dst, a, b) (void)0
+#endif
 
 // ----------------------------------------------------------------------------- kernel
 // One instantiation per (epilogue kind, activation, residual): with every variant inlined behind runtime branches the
@@ -156,6 +168,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         // cannot keep the descriptors in uniform registers and wraps every UTCHMMA in an ELECT/vote loop with R2UR moves.
         uint32_t g = 0, hb = 0;   // k-blocks / half k-blocks consumed so far
         int it = 0;
+        long long m_full = 0, m_conv = 0, m_acc = 0;
+        bool full_seen = false, conv_seen = false;   // the next stage's barriers were seen complete by the probe
+        TC_T(m_t0);
         for (int L = blockIdx.x; L < total_tiles; L += gridDim.x, ++it) {
             const int n_tile = L % n_tiles;
             const int tile_bn = tile_bn_of(n_tile);
@@ -163,19 +178,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2), K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t d_main = tmem + TC_COL_ACC * buf, d_corr = d_main + TC_COL_CORR;
+            TC_T(ma0);
             mbar_wait(&acc_free[buf], ((it >> 1) & 1) ^ 1, 190);     // the epilogue of tile it-2 has drained this buffer
+            TC_T(ma1);
+            TC_ACC(m_acc, ma0, ma1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int t = 0; t < T; ++t, ++g) {
                 const int s = g % TC_STAGES;
-                mbar_wait(&full[s], (g / TC_STAGES) & 1, 200 + t);
+                TC_T(mf0);
+                if (!full_seen) mbar_wait(&full[s], (g / TC_STAGES) & 1, 200 + t);
+                TC_T(mf1);
+                TC_ACC(m_full, mf0, mf1);
+                full_seen = false;
                 const uint64_t dbh = make_kmajor_sw128_desc(smem_u32(w_hi(s)));
                 const uint64_t dbl = make_kmajor_sw128_desc(smem_u32(w_lo(s)));
                 // the A operand arrives in TMEM in HALF k-blocks (16 k: 16 columns hi + 16 lo per stage)
 #pragma unroll
                 for (int h = 0; h < 2; ++h, ++hb) {
                     const int ts = hb % TC_TSTAGES;
-                    mbar_wait(&conv[ts], (hb / TC_TSTAGES) & 1, 300 + t);
+                    TC_T(mc0);
+                    if (!conv_seen) mbar_wait(&conv[ts], (hb / TC_TSTAGES) & 1, 300 + t);
+                    TC_T(mc1);
+                    TC_ACC(m_conv, mc0, mc1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // Issuing blocks while the tensor queue is full, and a wait after it is dead time for the tensor
+                    // pipe: probe the NEXT half's barriers now (the converters run ahead, so they have usually fired).
+                    conv_seen = mbar_test(&conv[(hb + 1) % TC_TSTAGES], ((hb + 1) / TC_TSTAGES) & 1);
+                    if (h == 1) full_seen = mbar_test(&full[(g + 1) % TC_STAGES], ((g + 1) / TC_STAGES) & 1);
                     const uint32_t t_hi = tmem + TC_COL_A + 32 * ts, t_lo = t_hi + 16;
                     if (elect_one()) {
 #pragma unroll
@@ -195,6 +224,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             if (elect_one()) umma_commit(&acc_full[buf]);        // accumulators of this tile complete
             __syncwarp();
         }
+#if TC_PHASE_TIMERS
+        if (lane == 0) {
+            atomicAdd(&fc_tc_dbg[0], 1ull); atomicAdd(&fc_tc_dbg[1], (unsigned long long)(clock64() - m_t0));
+            atomicAdd(&fc_tc_dbg[2], (unsigned long long)m_full); atomicAdd(&fc_tc_dbg[3], (unsigned long long)m_conv);
+            atomicAdd(&fc_tc_dbg[4], (unsigned long long)m_acc);
+        }
+#endif
     } else if (warp < 6) {
         // ===================================================== converters: fp32 smem row -> (hi, lo) in TMEM
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
@@ -204,10 +240,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         // split; only then is it awaited and published (conv[]), so the store latency is off the critical path.
         uint32_t g = 0, hb = 0;
         int pending = -1;        // TMEM stage whose store has been issued but not yet published
+        long long c_full = 0, c_tfree = 0;
+        TC_T(c_t0);
         for (int L = blockIdx.x; L < total_tiles; L += gridDim.x) {
             for (int t = 0; t < T; ++t, ++g) {
                 const int s = g % TC_STAGES;
+                if (pending >= 0) {      // never hold a finished stage back while waiting for the next k-block's data
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&conv[pending]);
+                    pending = -1;
+                }
+                TC_T(cf0);
                 mbar_wait(&full[s], (g / TC_STAGES) & 1, 400 + t);
+                TC_T(cf1);
+                TC_ACC(c_full, cf0, cf1);
                 const float4* rowp = reinterpret_cast<const float4*>(a_raw(s) + row_in_tile * 128);
 #pragma unroll
                 for (int h = 0; h < 2; ++h, ++hb) {
@@ -235,7 +282,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         mbar_arrive(&conv[pending]);
                     }
                     const int ts = hb % TC_TSTAGES;
+                    TC_T(ct0);
                     mbar_wait(&tfree[ts], ((hb / TC_TSTAGES) & 1) ^ 1, 450 + t);
+                    TC_T(ct1);
+                    TC_ACC(c_tfree, ct0, ct1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     tmem_st32(tmem + lane_addr + TC_COL_A + 32 * ts, hl);
                     pending = ts;
@@ -247,6 +297,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&conv[pending]);
         }
+#if TC_PHASE_TIMERS
+        if (threadIdx.x == 64) {
+            atomicAdd(&fc_tc_dbg[5], (unsigned long long)(clock64() - c_t0));
+            atomicAdd(&fc_tc_dbg[6], (unsigned long long)c_full); atomicAdd(&fc_tc_dbg[7], (unsigned long long)c_tfree);
+        }
+#endif
     } else {
         // ===================================================== epilogue (8 warps, 256 threads)
         // TMEM lane = row within the tile; the two warps of a quadrant take alternate 16-column chunks
@@ -261,6 +317,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         // conflict free, the transposed ones 2-way at worst)
         float* stg = stage_out + ew * (32 * 20);
         int it = 0;
+        long long e_wait = 0;
+        TC_T(e_t0);
         for (int L = blockIdx.x; L < total_tiles; L += gridDim.x, ++it) {
             const int n_tile = L % n_tiles, m0 = (L / n_tiles) * TC_BM;
             const int tile_n0 = tile_n0_of(n_tile), tile_bn = tile_bn_of(n_tile);
@@ -281,7 +339,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 }
                 if (etid == 0) bias_in_smem2[buf] = (one_group && m0 < a.M) ? 1 : 0;
             }
+            TC_T(ea0);
             mbar_wait(&acc_full[buf], (it >> 1) & 1, 500);
+            TC_T(ea1);
+            TC_ACC(e_wait, ea0, ea1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             asm volatile("bar.sync 2, 256;" ::: "memory");    // bias_sm / csum_sm visible to all 8 epilogue warps
             const bool bias_smem = bias_in_smem2[buf] != 0;
@@ -516,6 +577,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_free[buf]);
         }
+#if TC_PHASE_TIMERS
+        if (threadIdx.x == 192) {
+            atomicAdd(&fc_tc_dbg[8], (unsigned long long)(clock64() - e_t0)); atomicAdd(&fc_tc_dbg[9], (unsigned long long)e_wait);
+        }
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -658,8 +724,10 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     return FC_OK;
 }
 
-// (the per-CTA phase counters of the non-persistent kernel are gone; the entry point stays for scripts/tc_phases.py)
-extern "C" __attribute__((visibility("default"))) int fc_debug_tc_phases(unsigned long long* out8) {
-    for (int i = 0; i < 8; ++i) out8[i] = 0;
-    return FC_ERR_UNSUPPORTED;
+// phase counters: valid only in a -DTC_PHASE_TIMERS=1 build (scripts/build_variant.sh timers gemm_tc "-DTC_PHASE_TIMERS=1")
+extern "C" __attribute__((visibility("default"))) int fc_debug_tc_phases(unsigned long long* out16) {
+    if (cudaMemcpyFromSymbol(out16, fc_tc_dbg, 16 * sizeof(unsigned long long)) != cudaSuccess) return FC_ERR_CUDA;
+    unsigned long long z[16] = {};
+    if (cudaMemcpyToSymbol(fc_tc_dbg, z, sizeof(z)) != cudaSuccess) return FC_ERR_CUDA;
+    return TC_PHASE_TIMERS ? FC_OK : FC_ERR_UNSUPPORTED;
 }

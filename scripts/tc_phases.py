@@ -1,4 +1,6 @@
-"""Per-CTA phase cycle counts of the tcgen05 GEMM (FC_TC_DEBUG=1): setup / main loop / epilogue (tmem ld, math, stores)."""
+"""Per-CTA phase cycle counts of the persistent tcgen05 GEMM.  Needs a timers build:
+    scripts/build_variant.sh timers gemm_tc "-DTC_PHASE_TIMERS=1"
+    FLOWCOMPARE_B200_LIB=flowcompare_b200/variants/lib_timers.so python scripts/tc_phases.py"""
 import ctypes, math, os, sys
 os.environ["FC_TC_DEBUG"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,11 +24,14 @@ for (M, N, K, act) in shapes:
         assert rc == 0
     for _ in range(3): run()
     torch.cuda.synchronize()
-    out = (ctypes.c_ulonglong * 8)()
+    out = (ctypes.c_ulonglong * 16)()
     lib.fc_debug_tc_phases(out)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record(); torch.cuda.synchronize()
-    lib.fc_debug_tc_phases(out)
+    rc = lib.fc_debug_tc_phases(out)
     n = max(1, out[0])
-    print(f"M={M} N={N} K={K} act={act} BN={packing.tc_bn(N)} ctas={out[0]} us={e0.elapsed_time(e1)*1e3:.1f} per-CTA cycles: setup={out[3]/n:.0f} "
-          f"mainloop={out[1]/n:.0f} epilogue={out[2]/n:.0f} (tmem_ld={out[4]/n:.0f} math={out[5]/n:.0f} store={out[6]/n:.0f})", flush=True)
+    tiles = ((M + 127) // 128) * packing.tc_n_tiles(N)
+    kb = tiles * ((K + 31) // 32) / n
+    print(f"M={M} N={N} K={K} act={act} ctas={out[0]} rc={rc} us={e0.elapsed_time(e1)*1e3:.1f} k-blocks/CTA={kb:.0f} | MMA warp: total {out[1]/n:.0f} "
+          f"(/kb {out[1]/n/kb:.0f}) wait full {out[2]/n:.0f} conv {out[3]/n:.0f} acc_free {out[4]/n:.0f} | converter: total {out[5]/n:.0f} wait full {out[6]/n:.0f} "
+          f"tfree {out[7]/n:.0f} | epilogue: total {out[8]/n:.0f} wait acc_full {out[9]/n:.0f}", flush=True)
