@@ -14,22 +14,29 @@
 // of the magnitude), and the one GEMM whose output is the latent itself (ActNorm+LinearLU) applies its
 // diagonal in fp32 in the epilogue (flow.cu), so the residual bias is below the fp32 noise of the reference.
 //
-// CTA = one 128 x BN output tile (BN <= 96, runtime), 10 warps, TWO CTAs RESIDENT PER SM (93 registers, 81 KB of
-// shared memory and 256 of the 512 TMEM columns each), so that one CTA's epilogue (exact-erf GELU is ~45
-// instructions per element and issue-bound) runs under the other CTA's main loop:
-//   warp 0      TMA producer (one lane)
-//   warp 1      TMEM allocator + MMA issuer (whole warp loops, one elected lane issues: keeps UTCHMMA operands uniform)
-//   warps 2-5   converters (one thread per tile row) during the main loop, then epilogue
-//   warps 6-9   prefetch the tile's bias row, then epilogue (each TMEM lane quadrant is drained by two warps)
-// TMEM (256 columns): [0,96) main accumulator | [96,192) compensation accumulator |
-//                     [192,256) two stages of A, each HALF a k-block: 16 columns hi + 16 columns lo.
-// Pipeline (mbarriers): full[s] (TMA bytes landed, 2 smem stages) -> converter -> a_free[s] (A smem reusable) and
-//   conv[ts] (A half-block in TMEM stage ts) -> MMA -> tcgen05.commit -> tfree[ts], w_free[s] (W smem reusable).
-// Global traffic of the epilogue goes through a per-warp shared-memory staging tile so it is coalesced.
-// What was measured and dropped (B200, see profiles/): a 4-accumulator split of the main product (no accuracy gain
-// once the compensation terms had their own accumulator), TMA multicast of the weight tile over clusters of 2/4
-// (no gain), one N=2*BN MMA for Ahi*[Whi;Wlo] (no gain), decoupled A/W rings (slower), 128x176 tiles with one
-// CTA per SM (epilogue not hidden: 16k of 42k cycles per tile).
+// PERSISTENT kernel, one CTA per SM (15 warps, all 512 TMEM columns, ~225 KB of shared memory).  The CTA walks the
+// list of 128 x BN output tiles (BN <= 96; N is cut into equal-ish multiples of 16, no padded columns) with stride
+// gridDim.x.  The accumulators are DOUBLE BUFFERED in TMEM, so the epilogue of tile j runs while the tensor core is
+// on tile j+1, and the TMA / converter / MMA pipelines never drain between tiles:
+//   warp 0       TMA producer (one lane): 5 shared-memory stages of (A raw 16 KB, Whi, Wlo)
+//   warps 1-2    TMEM allocator + the two MMA issuers, one per half k-block (whole warp loops, one elected lane
+//                issues).  Issue is effectively synchronous (the queue is a couple of MMAs deep), so each issuer
+//                PROBES its next stage's barriers before it blocks, and the other covers its waits / commits.
+//   warps 3-6    converters (one thread per tile row): fp32 smem row -> TF32 hi/lo -> tcgen05.st, published one half
+//                k-block late so the store latency overlaps the next split
+//   warps 7-14   epilogue (two warps per TMEM lane quadrant, alternate 16-column chunks): bias row prefetched while the
+//                tile is still being accumulated; global traffic staged per warp through shared memory (16-byte
+//                coalesced accesses)
+// TMEM (512 columns): accumulator buffer b = [192b, 192b+96) main | [192b+96, 192b+192) compensation;
+//                     [384,512) four stages of A, each HALF a k-block: 16 columns hi + 16 columns lo.
+// Pipeline (mbarriers): full[s] (TMA bytes landed) -> converter -> a_free[s] (A smem reusable) and conv[ts] (A half
+//   block in TMEM) -> MMA -> tcgen05.commit -> tfree[ts], w_free[s] (2 arrivals), acc_full[b] (2 arrivals) -> epilogue
+//   -> acc_free[b] (256 arrivals); tile_started[b] orders the two issuers at the first MMA of a tile (accumulate = 0).
+// Measured on the way here (B200; numbers in DESIGN.md section 4): two CTAs per SM with single-buffered accumulators
+// (the previous design: 372 -> 390 pairs/s going persistent), the barrier probe (+6 %), a branch-free GELU, hand TF32
+// rounding and 16-byte staged stores (+23 %); dropped: a 4-accumulator split of the main product (no accuracy gain),
+// TMA multicast of the weight tile over clusters of 2/4 and halving the weight bytes (no effect: not L2 bound), one
+// N=2*BN MMA for Ahi*[Whi;Wlo], decoupled A/W rings, 64/80-wide tiles, all-warps converters, a staggered start.
 #include "gemm.cuh"
 #include "tcgen05.cuh"
 #include <cuda.h>
@@ -43,7 +50,10 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                      // 32 fp32 = one 128-byte swizzle row
 constexpr int TC_STAGES = 5;                   // shared-memory stages: a load is issued 4 k-blocks of tensor time (~1.4 us) ahead
-constexpr int TC_TSTAGES = 4;                  // TMEM stages of the A operand, each HALF a k-block
+#ifndef TC_BN_CAP
+#define TC_BN_CAP 96                           // widest tile (accumulator width); 80 leaves room for 6 A stages
+#endif
+constexpr int TC_TSTAGES = (512 - 4 * TC_BN_CAP) / 32;   // TMEM stages of the A operand, each HALF a k-block
 constexpr int TC_THREADS = 480;                // TMA, 2 MMA issuers, 4 converter warps, 8 epilogue warps
 // phase timers (scripts/tc_phases.py): compiled out by default, build a variant with -DTC_PHASE_TIMERS=1
 #ifndef TC_PHASE_TIMERS
@@ -58,9 +68,9 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_TMEM_COLS = 512;                // one persistent CTA per SM
 // 5 stages x (16 KB A + 2 x 12 KB W at BN = 96) + 8 staging tiles of the epilogue + 1 KB alignment slack
 constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + 2 * 96 * TC_BK * 4) + 8 * 32 * 20 * 4 + 1024;
-constexpr int TC_COL_ACC = 192;                // accumulator buffer b: main at 192*b, compensation at 192*b + 96
-constexpr int TC_COL_CORR = 96;
-constexpr int TC_COL_A = 384;                  // + 32 * stage: 16 columns hi, 16 columns lo
+constexpr int TC_COL_ACC = 2 * TC_BN_CAP;      // accumulator buffer b: main at 192*b, compensation at 192*b + 96
+constexpr int TC_COL_CORR = TC_BN_CAP;
+constexpr int TC_COL_A = 4 * TC_BN_CAP;        // + 32 * stage: 16 columns hi, 16 columns lo
 
 struct TcParams {
     GemmArgs g;
@@ -682,7 +692,7 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     p.BN = fc_tc_bn(a.N);
     p.T1 = fc_tc_kpad(a.K1) / TC_BK;
     p.T2 = a.K2 ? fc_tc_kpad(a.K2) / TC_BK : 0;
-    FC_REQUIRE(p.BN <= 96 && (p.BN & 15) == 0);
+    FC_REQUIRE(p.BN <= TC_BN_CAP && (p.BN & 15) == 0);
     FC_REQUIRE(a.ldk == (p.T1 + p.T2) * TC_BK);
     p.n_tiles = fc_tc_n_tiles(a.N);
     p.m_tiles = (a.M + TC_BM - 1) / TC_BM;
