@@ -327,7 +327,7 @@ def main():
 
     note("e2e + instrumented step done")
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # the CPU baseline is measured at N=1 only
         v, dt = cpu_baseline(cfg, args.cpu_pairs)
         cpu = {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": f"{args.cpu_pairs} pairs (B=1 per call, Nc=1250, N=1024, same architecture and weights), {dt:.1f} s of "

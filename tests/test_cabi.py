@@ -42,3 +42,10 @@ def test_create_rejects_bad_header():
     h = ctypes.c_void_p()
     rc = lib.fc_flow_create(header.ctypes.data, 19, table.ctypes.data, 4, arena.ctypes.data, 64, h)
     assert rc == -6  # FC_ERR_MODEL (bad magic); nothing touches the device
+
+
+def test_bench_reads_traffic_from_committed_profile():
+    """bench.py's roofline.traffic comes from the committed ncu capture; make sure the file is there and parses."""
+    import bench
+    traffic, note = bench.ncu_traffic()
+    assert isinstance(traffic, int) and traffic > 0, note
