@@ -14,24 +14,26 @@
 // of the magnitude), and the one GEMM whose output is the latent itself (ActNorm+LinearLU) applies its
 // diagonal in fp32 in the epilogue (flow.cu), so the residual bias is below the fp32 noise of the reference.
 //
-// PERSISTENT kernel, one CTA per SM (15 warps, all 512 TMEM columns, ~225 KB of shared memory).  The CTA walks the
+// PERSISTENT kernel, one CTA per SM (14 warps, all 512 TMEM columns, ~225 KB of shared memory).  The CTA walks the
 // list of 128 x BN output tiles (BN <= 96; N is cut into equal-ish multiples of 16, no padded columns) with stride
 // gridDim.x.  The accumulators are DOUBLE BUFFERED in TMEM, so the epilogue of tile j runs while the tensor core is
 // on tile j+1, and the TMA / converter / MMA pipelines never drain between tiles:
 //   warp 0       TMA producer (one lane): 5 shared-memory stages of (A raw 16 KB, Whi, Wlo)
-//   warps 1-2    TMEM allocator + the two MMA issuers, one per half k-block (whole warp loops, one elected lane
-//                issues).  Issue is effectively synchronous (the queue is a couple of MMAs deep), so each issuer
-//                PROBES its next stage's barriers before it blocks, and the other covers its waits / commits.
-//   warps 3-6    converters (one thread per tile row): fp32 smem row -> TF32 hi/lo -> tcgen05.st, published one half
+//   warp 1       TMEM allocator + MMA issuer (whole warp loops, one elected lane issues).  Issue is effectively
+//                synchronous (the tensor queue is a couple of MMAs deep), so the warp PROBES the next stage's barriers
+//                before it blocks in the issue and skips the wait when they have fired.  ONE issuer, in program
+//                order: the accumulation order, and with it every output bit, is the same on every run (two issuer
+//                warps sharing a k-block were 3-5 % faster on single GEMMs, equal on the whole step, and measurably
+//                non-deterministic; one warp per accumulator was deterministic but 5 % slower).
+//   warps 2-5    converters (one thread per tile row): fp32 smem row -> TF32 hi/lo -> tcgen05.st, published one half
 //                k-block late so the store latency overlaps the next split
-//   warps 7-14   epilogue (two warps per TMEM lane quadrant, alternate 16-column chunks): bias row prefetched while the
+//   warps 6-13   epilogue (two warps per TMEM lane quadrant, alternate 16-column chunks): bias row prefetched while the
 //                tile is still being accumulated; global traffic staged per warp through shared memory (16-byte
 //                coalesced accesses)
 // TMEM (512 columns): accumulator buffer b = [192b, 192b+96) main | [192b+96, 192b+192) compensation;
 //                     [384,512) four stages of A, each HALF a k-block: 16 columns hi + 16 columns lo.
 // Pipeline (mbarriers): full[s] (TMA bytes landed) -> converter -> a_free[s] (A smem reusable) and conv[ts] (A half
-//   block in TMEM) -> MMA -> tcgen05.commit -> tfree[ts], w_free[s] (2 arrivals), acc_full[b] (2 arrivals) -> epilogue
-//   -> acc_free[b] (256 arrivals); tile_started[b] orders the two issuers at the first MMA of a tile (accumulate = 0).
+//   block in TMEM) -> MMA -> tcgen05.commit -> tfree[ts], w_free[s], acc_full[b] -> epilogue -> acc_free[b].
 // Measured on the way here (B200; numbers in DESIGN.md section 4): two CTAs per SM with single-buffered accumulators
 // (the previous design: 372 -> 390 pairs/s going persistent), the barrier probe (+6 %), a branch-free GELU, hand TF32
 // rounding and 16-byte staged stores (+23 %); dropped: a 4-accumulator split of the main product (no accuracy gain),
@@ -51,10 +53,10 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                      // 32 fp32 = one 128-byte swizzle row
 constexpr int TC_STAGES = 5;                   // shared-memory stages: a load is issued 4 k-blocks of tensor time (~1.4 us) ahead
 #ifndef TC_BN_CAP
-#define TC_BN_CAP 96                           // widest tile (accumulator width); 80 leaves room for 6 A stages
+#define TC_BN_CAP 96                           // widest tile (accumulator width); 80 leaves room for 6 A stages (measured slower)
 #endif
 constexpr int TC_TSTAGES = (512 - 4 * TC_BN_CAP) / 32;   // TMEM stages of the A operand, each HALF a k-block
-constexpr int TC_THREADS = 480;                // TMA, 2 MMA issuers, 4 converter warps, 8 epilogue warps
+constexpr int TC_THREADS = 448;                // TMA, MMA, 4 converter warps, 8 epilogue warps
 // phase timers (scripts/tc_phases.py): compiled out by default, build a variant with -DTC_PHASE_TIMERS=1
 #ifndef TC_PHASE_TIMERS
 #define TC_PHASE_TIMERS 0
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 6];
+    __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 4];
     __shared__ uint32_t tmem_base_slot;
     __shared__ float ldj_sm[TC_BM];
     __shared__ __align__(16) float bias_sm2[2][96];   // the tile's bias (and LayerNorm-q column sums), by accumulator buffer
@@ -127,8 +129,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     uint64_t* tfree = bars + 3 * TC_STAGES + TC_TSTAGES;     // [TC_TSTAGES] MMAs done reading A TMEM
     uint64_t* acc_full = bars + 3 * TC_STAGES + 2 * TC_TSTAGES;   // [2] accumulators of a tile complete
     uint64_t* acc_free = acc_full + 2;                            // [2] epilogue has drained them (256 arrivals)
-    uint64_t* tile_started = acc_free + 2;                        // [2] MMA warp 1 has issued the first half k-block of the tile
-                                                                  //     (per accumulator buffer: warp 1 can never be two tiles ahead in one)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T1 + p.T2;
@@ -140,10 +140,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     auto tile_bn_of = [&](int nt) { return 16 * (n_base + (nt < n_rem ? 1 : 0)); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], 128); mbar_init(&w_free[s], 2); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], 128); mbar_init(&w_free[s], 1); }
         for (int s = 0; s < TC_TSTAGES; ++s) { mbar_init(&conv[s], 128); mbar_init(&tfree[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 2); mbar_init(&acc_free[s], 256); }
-        mbar_init(&tile_started[0], 1); mbar_init(&tile_started[1], 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -175,16 +174,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 }
             }
         }
-    } else if (warp <= 2) {
-        // ===================================================== MMA issuers (two warps)
-        // Warp 1 issues the first half of every k-block, warp 2 the second: while one is blocked on the tensor queue
-        // (issue is effectively synchronous, the queue is a couple of MMAs deep) the other does its barrier waits,
-        // fences and commits, so the tensor pipe always has the next MMA waiting.  Each warp's tcgen05.commit tracks
-        // the MMAs that warp issued, hence w_free / acc_full take one arrival from each.
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
         // The whole warp runs the loop and ONE ELECTED lane issues: inside a divergent `if (lane == 0)` the compiler
         // cannot keep the descriptors in uniform registers and wraps every UTCHMMA in an ELECT/vote loop with R2UR moves.
-        const int h = warp - 1;   // which half of a k-block this warp owns
-        uint32_t g = 0;           // k-blocks consumed so far
+        uint32_t g = 0, hb = 0;   // k-blocks / half k-blocks consumed so far
         int it = 0;
         long long m_full = 0, m_conv = 0, m_acc = 0;
         bool full_seen = false, conv_seen = false;   // the next stage's barriers were seen complete by the probe
@@ -198,56 +192,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             const uint32_t d_main = tmem + TC_COL_ACC * buf, d_corr = d_main + TC_COL_CORR;
             TC_T(ma0);
             mbar_wait(&acc_free[buf], ((it >> 1) & 1) ^ 1, 190);     // the epilogue of tile it-2 has drained this buffer
-            // the tile's very first MMAs (warp 1, accumulate = 0) must be in the queue before warp 2 adds to them
-            if (h == 1) mbar_wait(&tile_started[buf], (it >> 1) & 1, 195);
             TC_T(ma1);
             TC_ACC(m_acc, ma0, ma1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int t = 0; t < T; ++t, ++g) {
                 const int s = g % TC_STAGES;
-                const uint32_t hb = 2 * g + h;
-                const int ts = hb % TC_TSTAGES;
                 TC_T(mf0);
                 if (!full_seen) mbar_wait(&full[s], (g / TC_STAGES) & 1, 200 + t);
                 TC_T(mf1);
                 TC_ACC(m_full, mf0, mf1);
-                if (!conv_seen) mbar_wait(&conv[ts], (hb / TC_TSTAGES) & 1, 300 + t);
-                TC_T(mc1);
-                TC_ACC(m_conv, mf1, mc1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // probe this warp's NEXT half now, before blocking on the tensor queue (the converters run ahead)
-                full_seen = mbar_test(&full[(g + 1) % TC_STAGES], ((g + 1) / TC_STAGES) & 1);
-                conv_seen = mbar_test(&conv[(hb + 2) % TC_TSTAGES], ((hb + 2) / TC_TSTAGES) & 1);
+                full_seen = false;
                 const uint64_t dbh = make_kmajor_sw128_desc(smem_u32(w_hi(s)));
                 const uint64_t dbl = make_kmajor_sw128_desc(smem_u32(w_lo(s)));
                 // the A operand arrives in TMEM in HALF k-blocks (16 k: 16 columns hi + 16 lo per stage)
-                const uint32_t t_hi = tmem + TC_COL_A + 32 * ts, t_lo = t_hi + 16;
-                if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const int k = 2 * h + kk;
-                        const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
-                        umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (t | k) != 0);
-                        umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
-                        umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                for (int h = 0; h < 2; ++h, ++hb) {
+                    const int ts = hb % TC_TSTAGES;
+                    TC_T(mc0);
+                    if (!conv_seen) mbar_wait(&conv[ts], (hb / TC_TSTAGES) & 1, 300 + t);
+                    TC_T(mc1);
+                    TC_ACC(m_conv, mc0, mc1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // Issuing blocks while the tensor queue is full, and a wait after it is dead time for the tensor
+                    // pipe: probe the NEXT half's barriers now (the converters run ahead, so they have usually fired).
+                    conv_seen = mbar_test(&conv[(hb + 1) % TC_TSTAGES], ((hb + 1) / TC_TSTAGES) & 1);
+                    if (h == 1) full_seen = mbar_test(&full[(g + 1) % TC_STAGES], ((g + 1) / TC_STAGES) & 1);
+                    const uint32_t t_hi = tmem + TC_COL_A + 32 * ts, t_lo = t_hi + 16;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const int k = 2 * h + kk;
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
+                            umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                            umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
+                            umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                        }
+                        umma_commit(&tfree[ts]);                 // TMEM A stage reusable once these MMAs retire
+                        if (h == 1) umma_commit(&w_free[s]);     // W smem stage reusable once these MMAs retire
                     }
-                    umma_commit(&tfree[ts]);        // TMEM A stage reusable once these MMAs retire
-                    umma_commit(&w_free[s]);        // W smem stage reusable once both warps' MMAs retire (2 arrivals)
-                    if (h == 0 && t == 0) mbar_arrive(&tile_started[buf]);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
-            if (elect_one()) umma_commit(&acc_full[buf]);        // accumulators of this tile complete (2 arrivals)
+            if (elect_one()) umma_commit(&acc_full[buf]);        // accumulators of this tile complete
             __syncwarp();
         }
 #if TC_PHASE_TIMERS
-        if (lane == 0 && h == 0) {
+        if (lane == 0) {
             atomicAdd(&fc_tc_dbg[0], 1ull); atomicAdd(&fc_tc_dbg[1], (unsigned long long)(clock64() - m_t0));
             atomicAdd(&fc_tc_dbg[2], (unsigned long long)m_full); atomicAdd(&fc_tc_dbg[3], (unsigned long long)m_conv);
             atomicAdd(&fc_tc_dbg[4], (unsigned long long)m_acc);
         }
 #endif
-    } else if (warp < 7) {
+    } else if (warp < 6) {
         // ===================================================== converters: fp32 smem row -> (hi, lo) in TMEM
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
         const int row_in_tile = quad * 32 + lane;
@@ -314,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             mbar_arrive(&conv[pending]);
         }
 #if TC_PHASE_TIMERS
-        if (threadIdx.x == 96) {
+        if (threadIdx.x == 64) {
             atomicAdd(&fc_tc_dbg[5], (unsigned long long)(clock64() - c_t0));
             atomicAdd(&fc_tc_dbg[6], (unsigned long long)c_full); atomicAdd(&fc_tc_dbg[7], (unsigned long long)c_tfree);
         }
@@ -325,9 +321,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         const int quad = warp & 3;
         const int row_in_tile = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const int ew = warp - 7;                     // 0..7
+        const int ew = warp - 6;                     // 0..7
         const int half = ew >> 2;
-        const int etid = threadIdx.x - 224;          // 0..255
+        const int etid = threadIdx.x - 192;          // 0..255
         const GemmArgs& a = p.g;
         // per-warp staging tile [32 rows][16 + 4 pad] (rows 16-byte aligned; a thread's own-row float4 accesses are
         // conflict free, the transposed ones 2-way at worst)
@@ -594,7 +590,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             mbar_arrive(&acc_free[buf]);
         }
 #if TC_PHASE_TIMERS
-        if (threadIdx.x == 224) {
+        if (threadIdx.x == 192) {
             atomicAdd(&fc_tc_dbg[8], (unsigned long long)(clock64() - e_t0)); atomicAdd(&fc_tc_dbg[9], (unsigned long long)e_wait);
         }
 #endif
