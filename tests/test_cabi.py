@@ -49,3 +49,21 @@ def test_bench_reads_traffic_from_committed_profile():
     import bench
     traffic, note = bench.ncu_traffic()
     assert isinstance(traffic, int) and traffic > 0, note
+
+
+def test_argument_validation_happens_before_any_gpu_work():
+    """Invalid arguments are rejected with FC_ERR_INVALID_ARG / FC_ERR_UNSUPPORTED on the host, before a single CUDA
+    call: these run without a GPU."""
+    lib = fclib.load()
+    INVALID, UNSUPPORTED = -1, -5
+    assert lib.fc_knn_self(0, 6, 1, 10, 6, 4, 0, 0, 0) == INVALID                       # null input
+    assert lib.fc_cross_attention(0, 64, 0, 128, 0, 64, 1, 8, 8, 64, 0.125, 0) == INVALID
+    assert lib.fc_cross_attention_tf32x3(0, 64, 0, 128, 0, 64, 1, 8, 8, 64, 0.125, 0) == INVALID
+    assert lib.fc_cross_attention_tc(0, 64, 0, 128, 0, 64, 1, 8, 8, 64, 0.125, 0, 0, 0) == INVALID   # no scratch
+    assert lib.fc_cross_attention_tc_scratch_bytes(0, 8) == INVALID
+    # 2 clouds x 1250 keys: hi/lo copies of k [B*Nc, 64] and of v^T [B, 64, round4(Nc)]
+    assert lib.fc_cross_attention_tc_scratch_bytes(2, 1250) >= 4 * (2 * 2 * 1250 * 64 + 2 * 2 * 64 * 1252)
+    assert lib.fc_flow_workspace_bytes(0, 1, 8, 8) == INVALID
+    assert lib.fc_gemm(0, 0, 0, 0, 0, 0, 0, 4, 4, 4, 0, 0, 0) == INVALID
+    msg = lib.fc_last_error()
+    assert isinstance(msg, bytes)
