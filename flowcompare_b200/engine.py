@@ -213,6 +213,36 @@ class FlowCompareB200:
         return out_stats[0], out_log_prob, out_stats[1]
 
     # ------------------------------------------------------------------ consumers
+    def change_maps(self, batch_1_0, batch_0_0, batch_0_1, batch_1_1, multiple=3.0, hard_cutoff=None, eps=None):
+        """The four `inner_loop` passes + two `log_prob_to_change` calls of `DatasetViewer.view_index`
+        (reference test_flow.py:39-62) as ONE batched pass: the four batches (1|0, 0|0, 0|1, 1|1; each
+        (extract_0, extract_1, extra_context)) are stacked along the batch axis -- cloud pairs are independent and a
+        pair's result does not depend on what else is in the batch (tested bitwise) -- and the change scores are then
+        formed per direction exactly as the reference does.  eps: optional [4B, N, latent-input_dim] noise.
+        Returns a dict of CUDA tensors: log_prob_{1_0,0_0,0_1,1_1} [B,N], change_1_0, change_0_1 [B,N],
+        nats_{1_0,...} (= -mean log_prob, the reference's `loss`)."""
+        batches = (batch_1_0, batch_0_0, batch_0_1, batch_1_1)
+        B = batches[0][0].shape[0]
+        for b in batches:
+            if b[0].shape[0] != B or b[0].shape[1] != batches[0][0].shape[1] or b[1].shape[1] != batches[0][1].shape[1]:
+                raise _lib.FlowCompareError("change_maps: the four batches must have the same batch size and cloud sizes")
+        e0 = torch.cat([b[0][:, :, :self.d_in].to(self.device, torch.float32) for b in batches], dim=0)
+        e1 = torch.cat([b[1][:, :, :self.d_in].to(self.device, torch.float32) for b in batches], dim=0)
+        extra = None
+        if self.has_extra:
+            if any(b[2] is None for b in batches):
+                raise _lib.FlowCompareError("this config uses extra context but a batch has none")
+            extra = torch.cat([b[2].reshape(B).to(self.device, torch.float32) for b in batches], dim=0)
+        _, lp, _ = self.inner_loop((e0, e1, extra), eps=eps)
+        names = ("1_0", "0_0", "0_1", "1_1")
+        out = {}
+        for i, nm in enumerate(names):
+            out["log_prob_" + nm] = lp[i * B:(i + 1) * B]
+            out["nats_" + nm] = -out["log_prob_" + nm].mean()
+        out["change_1_0"] = log_prob_to_change(out["log_prob_1_0"], out["log_prob_0_0"], multiple, hard_cutoff)
+        out["change_0_1"] = log_prob_to_change(out["log_prob_0_1"], out["log_prob_1_1"], multiple, hard_cutoff)
+        return out
+
     def log_prob_to_change(self, log_prob_1_given_0, log_prob_0_given_0, multiple, hard_cutoff=None):
         """`log_prob_to_change` (+ `clamp_infs`), reference test_flow.py:241-275."""
         return log_prob_to_change(log_prob_1_given_0, log_prob_0_given_0, multiple, hard_cutoff)

@@ -315,6 +315,26 @@ def test_inner_loop_deterministic_and_batch_invariant(precision):
     assert torch.equal(one[0], a[1])  # a cloud pair's result does not depend on what else is in the batch
 
 
+def test_change_maps_equals_the_four_separate_passes():
+    """engine.change_maps = the four inner_loop passes + two log_prob_to_change calls of test_flow.py:39-62."""
+    cfg, fsd, esd, batch, e = _engine("tiny_dgcnn_attn_extra", "tf32x3")
+    g = torch.Generator().manual_seed(11)
+    B = batch["extract_0"].shape[0]
+    batches, epss = [], []
+    for i in range(4):
+        b = spec.synthetic_batch(cfg, B, seed=40 + i)
+        batches.append((b["extract_0"].to(DEV), b["extract_1"].to(DEV), b["extra_context"].to(DEV)))
+        epss.append(b["eps"].to(DEV))
+    got = e.change_maps(*batches, multiple=1.5, eps=torch.cat(epss, dim=0))
+    lps = [e.inner_loop(batches[i], eps=epss[i])[1] for i in range(4)]
+    for i, nm in enumerate(("1_0", "0_0", "0_1", "1_1")):
+        assert torch.equal(got["log_prob_" + nm], lps[i])
+    assert torch.equal(got["change_1_0"], eng.log_prob_to_change(lps[0], lps[1], 1.5))
+    assert torch.equal(got["change_0_1"], eng.log_prob_to_change(lps[2], lps[3], 1.5))
+    want = port.log_prob_to_change(lps[0].cpu(), lps[1].cpu(), 1.5)
+    assert (got["change_1_0"].cpu() - want).abs().max().item() < 1e-6
+
+
 def test_drop_in_adapters_follow_reference_call_signature():
     """The reference's inner_loop body (model_initialization.py:206-228) re-stated against the adapters."""
     import einops
