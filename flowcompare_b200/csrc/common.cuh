@@ -31,24 +31,24 @@ __device__ __forceinline__ float fc_gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 // Branch-free GELU for the tensor-core GEMM's epilogue (the epilogue is issue-bound: erff() costs ~30 instructions
-// with both of its branches executed in a divergent warp, this costs 14).
-//   gelu(x) = relu(x) - 0.5*|x|*erfc(|x|/sqrt2),   erfc(t) ~= 2^(t*r(t)),  r = degree-7 fit on [0, 4.6]
-// (beyond 4.6 the term is < 1e-9).  Max absolute error of gelu vs the exact form: 5e-8 (fp32 evaluation), i.e.
-// below one ulp of the O(1) activations; unlike 0.5*x*(1+erf) it has no cancellation for negative x.
+// with both of its branches executed in a divergent warp, this costs 12).
+//   gelu(x) = relu(x) - |x| * (0.5*erfc(|x|/sqrt2)),   0.5*erfc(u/sqrt2) ~= 2^(u*r(u) - 1),  r = degree-7 fit on [0, 6.6]
+// (beyond 6.6 the term is < 1e-10; the 1/sqrt2 and the 0.5 are folded into the fit and the exponent).  Max absolute
+// error of gelu vs the exact form: 6e-8 (fp32 evaluation), i.e. below one ulp of the O(1) activations; unlike
+// 0.5*x*(1+erf) it has no cancellation for negative x.
 __device__ __forceinline__ float fc_gelu_erf_fast(float x) {
-    const float ax = fabsf(x);
-    const float t = fminf(ax * 0.70710678118654752440f, 4.6f);
-    float r = -3.394682255634122e-05f;
-    r = fmaf(r, t, 0.00035083278789423654f);
-    r = fmaf(r, t, -0.0011795264998048192f);
-    r = fmaf(r, t, -0.001286360001046406f);
-    r = fmaf(r, t, 0.028705087965716445f);
-    r = fmaf(r, t, -0.14868816447011296f);
-    r = fmaf(r, t, -0.9183731881190814f);
-    r = fmaf(r, t, -1.6279114817964138f);
+    const float u = fminf(fabsf(x), 6.6f);
+    float r = -2.107304487601092e-06f;
+    r = fmaf(r, u, 3.082007880290574e-05f);
+    r = fmaf(r, u, -0.00014644312103818846f);
+    r = fmaf(r, u, -0.0002300897957034123f);
+    r = fmaf(r, u, 0.007180221614911477f);
+    r = fmaf(r, u, -0.052572273431757154f);
+    r = fmaf(r, u, -0.4591854841684466f);
+    r = fmaf(r, u, -1.1511073739593443f);
     float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r * t));
-    return fmaf(-0.5f * ax, e, fmaxf(x, 0.f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(r, u, -1.0f)));
+    return fmaf(-fabsf(x), e, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float fc_leaky_relu02(float x) { return x > 0.f ? x : 0.2f * x; }
 
