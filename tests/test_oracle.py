@@ -73,6 +73,51 @@ def test_port_matches_live_reference_with_reference_init():
     assert (lp - out["log_prob"]).abs().max().item() < 1e-3
 
 
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("label", ["dgcnn_attn_extra", "dgcnn_global"])
+def test_port_sampling_pass_matches_live_reference(label):
+    """SURVEY 8f rank 1 (oracle side only so far): `Flow.sample` / `make_sample` (reference models/transform.py:79-84,
+    model_initialization.py:231-245) against port.flow_sample, with the base draw injected; and the round trip
+    inverse(forward(x)) = x of the port."""
+    import einops
+    cfg = configs.get_config(label, n_flow_layers=3, sample_size=64, n_samples_context=80)
+    models, mi = refload.load()
+    fsd, esd = spec.random_state_dicts(cfg, seed=3)
+    torch.manual_seed(0)
+    md = mi.initialize_flow(dict(cfg), "cpu", "test")
+    md["flow"].load_state_dict(fsd)
+    md["input_embedder"].load_state_dict(esd)
+    dcfg = configs.derive(cfg)
+    batch = spec.synthetic_batch(cfg, 1, seed=4)
+    n_points = 50
+    z0 = torch.randn(1, n_points, cfg["latent_dim"], generator=torch.Generator().manual_seed(8))
+
+    class Injected(torch.nn.Module):        # stands in for sample_distrib: returns the injected base draw
+        def sample(self, num_samples, context=None, n_points=None):
+            return z0.clone()
+
+    with torch.no_grad():
+        extra = batch["extra_context"]
+        want = mi.make_sample(n_points, batch["extract_0"], md, dcfg, sample_distrib=Injected(), extra_context=extra)
+        if dcfg["global"]:
+            emb, _ = port.dgcnn_embed_global(esd, batch["extract_0"][:, :, :6], cfg["n_neighbors"])
+            ctx = einops.repeat(emb, "b e -> b p e", p=n_points)
+        else:
+            ctx, _ = port.dgcnn_embed(esd, batch["extract_0"][:, :, :6], cfg["n_neighbors"])
+        ex = None if extra is None else einops.repeat(extra, "b c -> b n c", n=n_points)
+        got = port.flow_sample(fsd, dcfg, z0, ctx, ex)
+        assert got.shape == (1, n_points, 6)
+        assert (got.squeeze() - want).abs().max().item() < 1e-3
+        # round trip through the port: sample -> forward reproduces the latent's first columns' pre-image
+        x = got
+        eps = torch.randn(1, n_points, cfg["latent_dim"] - 6, generator=torch.Generator().manual_seed(9))
+        trace = []
+        lp = port.flow_log_prob(fsd, dcfg, x, ctx, ex, eps, trace=trace)
+        assert torch.isfinite(lp).all()
+        x_back = port.flow_sample(fsd, dcfg, trace[-1][1], ctx, ex)     # inverse(forward(x)) == x
+        assert (x_back - x).abs().max().item() < 1e-4
+
+
 # ----------------------------------------------------------------------------- kNN oracle
 def _tie_safe_mismatches(x, idx_a, idx_b, k):
     """Rows where the neighbour SETS differ must be rounding ties: the fp64 distances of the symmetric
