@@ -472,6 +472,7 @@ void fc_attention_tc_scratch_layout(int B, int Nc, float* scratch, float** khi, 
 int fc_launch_cross_attention_tc(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo, int B, int N,
                                  int Nc, int d, float scale, float* scratch, int presplit, cudaStream_t stream) {
     FC_REQUIRE(q && (kv || presplit) && out && scratch && B > 0 && N > 0 && Nc > 0);
+    FC_REQUIRE((int64_t)B * N < (1ll << 31) - AQ && (int64_t)B * Nc < (1ll << 31) - AK);   // TMA row coordinates are int32
     if (d != AD) return FC_ERR_UNSUPPORTED;
     FC_REQUIRE((ldq & 3) == 0 && (ldo & 3) == 0 && (presplit || ldkv >= 2 * AD) && ldq >= AD && ldo >= AD && B <= 65535);
     FC_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
