@@ -178,6 +178,41 @@ def _conditioner_first_layer(sd, mlp_prefix, attn_prefix, k_x, ex, is_global, E)
     return w_x, b_in, w_e, w_c
 
 
+def fold_inverse_actnorm_lu(flow_sd, config):
+    """Pack-time algebra of the inverse / sampling pass (reference models/permuters.py:171-177 followed by
+    models/act_norm.py:45-46, i.e. the inverse of one ActNorm + LinearLU pair): with the forward fold
+    z' = Wp z - Wp shift, Wp = L U diag(exp(-log_scale)), the inverse is z = Wp^-1 z' + shift.  Returned per pair, in
+    forward layer order, as (off-diagonal part of Wp^-1, its diagonal, bias) in fp64 -- the same split the forward GEMM
+    uses so that the latent's own column is applied in fp32 in the epilogue.  (Host side of SURVEY 8f rank 1; the
+    kernels of the inverse pass are not built yet.)"""
+    cfg = derive(config)
+    D, L = cfg["latent_dim"], cfg["n_flow_layers"]
+    out = []
+    t = 1
+    for layer in range(L):
+        t += 1
+        if layer != L - 1:
+            shift, log_scale = _d(flow_sd, f"transforms.{t}.shift")[0], _d(flow_sd, f"transforms.{t}.log_scale")[0]
+            t += 1
+            lo, up = _d(flow_sd, f"transforms.{t}.lower_entries"), _d(flow_sd, f"transforms.{t}.upper_entries")
+            dg = _d(flow_sd, f"transforms.{t}.unconstrained_upper_diag")
+            Lm = torch.eye(D, dtype=torch.float64)
+            il = np.tril_indices(D, k=-1)
+            Lm[il[0], il[1]] = lo
+            Um = torch.zeros(D, D, dtype=torch.float64)
+            iu = np.triu_indices(D, k=1)
+            Um[iu[0], iu[1]] = up
+            Um[range(D), range(D)] = F.softplus(dg) + cfg["linear_lu_eps"]
+            # Wp^-1 = diag(exp(log_scale)) U^-1 L^-1 by two triangular solves (no general inverse of a 300x300 product)
+            Linv = torch.linalg.solve_triangular(Lm, torch.eye(D, dtype=torch.float64), upper=False, unitriangular=True)
+            ULinv = torch.linalg.solve_triangular(Um, Linv, upper=True)
+            Winv = torch.diag(torch.exp(log_scale)) @ ULinv
+            wdiag = torch.diagonal(Winv).clone()
+            out.append((Winv - torch.diag(wdiag), wdiag, shift.clone()))
+            t += 1
+    return out
+
+
 def pack_flow(flow_sd, config):
     cfg = derive(config)
     from .spec import _check_supported

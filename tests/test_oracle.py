@@ -118,6 +118,27 @@ def test_port_sampling_pass_matches_live_reference(label):
         assert (x_back - x).abs().max().item() < 1e-4
 
 
+def test_inverse_actnorm_lu_fold_matches_port():
+    """packing.fold_inverse_actnorm_lu (pack-time algebra of the sampling pass) against the port's two inverse steps."""
+    cfg = configs.get_config("dgcnn_attn", n_flow_layers=4)
+    fsd, _ = spec.random_state_dicts(cfg, seed=6)
+    folds = packing.fold_inverse_actnorm_lu(fsd, cfg)
+    assert len(folds) == 3
+    sd64 = port.to_dtype(fsd, torch.float64)
+    g = torch.Generator().manual_seed(1)
+    zp = torch.randn(2, 17, cfg["latent_dim"], generator=g, dtype=torch.float64)
+    t = 1
+    for layer, (w_off, wdiag, bias) in enumerate(folds):
+        t += 1                                  # the coupling layer
+        want = port.actnorm_inverse(sd64, t, port.linear_lu_inverse(sd64, t + 1, zp, cfg["linear_lu_eps"]))
+        got = zp * wdiag + zp @ w_off.t() + bias
+        assert (got - want).abs().max().item() < 1e-9
+        # and it undoes the forward pair
+        fwd, _ = port.linear_lu_forward(sd64, t + 1, port.actnorm_forward(sd64, t, got)[0], cfg["linear_lu_eps"])
+        assert (fwd - zp).abs().max().item() < 1e-9
+        t += 2
+
+
 # ----------------------------------------------------------------------------- kNN oracle
 def _tie_safe_mismatches(x, idx_a, idx_b, k):
     """Rows where the neighbour SETS differ must be rounding ties: the fp64 distances of the symmetric
