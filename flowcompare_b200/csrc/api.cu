@@ -83,6 +83,16 @@ extern "C" int fc_gemm_tf32x3(const float* A, int lda, const float* Whi, const f
     return fc_launch_gemm_tc(g, (cudaStream_t)stream);
 }
 
+extern "C" int fc_gemm_f16x3(const float* A, int lda, const void* Whi16, const void* Wlo16, int ldk, const float* bias,
+                             float* C, int ldc, int M, int N, int K, int act, fc_stream_t stream) {
+    GemmArgs g = fc_gemm_args_zero();
+    g.A1 = A; g.lda1 = lda; g.K1 = K; g.Whi = static_cast<const float*>(Whi16); g.Wlo = static_cast<const float*>(Wlo16);
+    g.ldk = ldk; g.tc_fmt = 1; g.bias = bias; g.act = act; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.precision = 1;
+    FC_REQUIRE(act >= 0 && act <= 3 && A && Whi16 && Wlo16 && C);
+    if (!fc_gemm_tc_supported(g)) return FC_ERR_UNSUPPORTED;
+    return fc_launch_gemm_tc(g, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------ stats
 namespace {
 // loss = -mean(log_prob), bpd = loss*log2(e)/input_dim  (reference model_initialization.py:225-227)

@@ -65,7 +65,7 @@ EmbWs carve_emb_ws(const fc_embedder* e, int B, int Nc, void* base) {
 extern "C" int fc_embedder_create(const int32_t* header, int n_header, const int64_t* table, int n_table,
                                   const float* arena, int64_t arena_floats, fc_embedder** out) {
     FC_REQUIRE(header && table && arena && out && n_header >= 8);
-    if (header[0] != FC_EMB_MAGIC || header[1] != FC_ARENA_VERSION) return FC_ERR_MODEL;
+    if (header[0] != FC_EMB_MAGIC || (header[1] != FC_ARENA_VERSION && header[1] != FC_ARENA_VERSION_F16)) return FC_ERR_MODEL;
     if (reinterpret_cast<uintptr_t>(arena) & 15) return FC_ERR_MODEL;
     fc_embedder* e = new (std::nothrow) fc_embedder();
     if (!e) return FC_ERR_MODEL;
@@ -73,6 +73,7 @@ extern "C" int fc_embedder_create(const int32_t* header, int n_header, const int
     e->out_hid = header[6]; e->n_out_hid = header[7];
     e->arena = arena; e->arena_floats = arena_floats;
     FcCursor c{table, n_table, 0, arena, arena_floats, true};
+    c.tc_fmt = header[1] == FC_ARENA_VERSION_F16 ? 1 : 0;
     if (e->kind == 0 || e->kind == 1) {
         if (e->k < 1 || e->k > 64 || e->out_hid > 512 || e->d_in < 1) { delete e; return FC_ERR_UNSUPPORTED; }
         const int cin[4] = {e->d_in, 64, 64, 128};
@@ -107,7 +108,7 @@ extern "C" int64_t fc_embedder_workspace_bytes(const fc_embedder* e, int B, int 
 static int gemm_simple(const FcLinear& l, const float* A, int lda, int act, float* C, int ldc, int M, int precision,
                        cudaStream_t s) {
     GemmArgs g = fc_gemm_args_zero();
-    g.A1 = A; g.lda1 = lda; g.K1 = l.K1; g.Wt = l.w; g.ldw = l.ldw; g.bias = l.b; g.act = act; g.Whi = l.whi; g.Wlo = l.wlo; g.ldk = l.ldk;
+    g.A1 = A; g.lda1 = lda; g.K1 = l.K1; g.Wt = l.w; g.ldw = l.ldw; g.bias = l.b; g.act = act; g.Whi = l.whi; g.Wlo = l.wlo; g.ldk = l.ldk; g.tc_fmt = l.tc_fmt;
     g.C = C; g.ldc = ldc; g.M = M; g.N = l.N; g.precision = precision;
     return fc_launch_gemm(g, s);
 }

@@ -128,7 +128,7 @@ static int gemm_plain(const FcLinear& l, const float* A1, int lda1, const float*
                       int precision, cudaStream_t stream) {
     GemmArgs g = fc_gemm_args_zero();
     g.A1 = A1; g.lda1 = lda1; g.K1 = l.K1; g.A2 = A2; g.lda2 = lda2; g.K2 = l.K2;
-    g.Wt = l.w; g.ldw = l.ldw; g.Whi = l.whi; g.Wlo = l.wlo; g.ldk = l.ldk;
+    g.Wt = l.w; g.ldw = l.ldw; g.Whi = l.whi; g.Wlo = l.wlo; g.ldk = l.ldk; g.tc_fmt = l.tc_fmt;
     if (bias) { g.bias = bias; g.bias_ld = bias_ld; g.bias_group = bias_group; }
     else { g.bias = l.b; }
     g.res = res; g.ldres = ldres; g.act = act; g.C = C; g.ldc = ldc; g.M = M; g.N = l.N;
@@ -174,7 +174,7 @@ static FcAttn read_attn(FcCursor& c, const fc_flow& f) {
 extern "C" int fc_flow_create(const int32_t* header, int n_header, const int64_t* table, int n_table,
                               const float* arena, int64_t arena_floats, fc_flow** out) {
     FC_REQUIRE(header && table && arena && out && n_header >= 19);
-    if (header[0] != FC_FLOW_MAGIC || header[1] != FC_ARENA_VERSION) return FC_ERR_MODEL;
+    if (header[0] != FC_FLOW_MAGIC || (header[1] != FC_ARENA_VERSION && header[1] != FC_ARENA_VERSION_F16)) return FC_ERR_MODEL;
     if (reinterpret_cast<uintptr_t>(arena) & 15) return FC_ERR_MODEL;
     fc_flow* f = new (std::nothrow) fc_flow();
     if (!f) return FC_ERR_MODEL;
@@ -191,6 +191,7 @@ extern "C" int fc_flow_create(const int32_t* header, int n_header, const int64_t
     if (!f->layers) { delete f; return FC_ERR_MODEL; }
 
     FcCursor c{table, n_table, 0, arena, arena_floats, true};
+    c.tc_fmt = header[1] == FC_ARENA_VERSION_F16 ? 1 : 0;
     const int64_t cbits = c.next();
     memcpy(&f->ldj_const, &cbits, sizeof(double));
     const int attn_k2 = f->is_global ? 0 : f->inner;
@@ -284,7 +285,7 @@ static int run_attention_block(const fc_flow* f, const FcMlp& pre, const FcAttn&
     if (rc) return rc;
     {
         GemmArgs g = fc_gemm_args_zero();
-        g.A1 = h4; g.lda1 = w.ldh; g.K1 = f->attn_in; g.Wt = at.q.w; g.ldw = at.q.ldw; g.bias = at.qbias; g.Whi = at.q.whi; g.Wlo = at.q.wlo; g.ldk = at.q.ldk;
+        g.A1 = h4; g.lda1 = w.ldh; g.K1 = f->attn_in; g.Wt = at.q.w; g.ldw = at.q.ldw; g.bias = at.qbias; g.Whi = at.q.whi; g.Wlo = at.q.wlo; g.ldk = at.q.ldk; g.tc_fmt = at.q.tc_fmt;
         g.C = w.q; g.ldc = 64; g.M = M; g.N = f->inner; g.epi = FC_EPI_LNQ; g.row_mu = w.mu; g.row_rstd = w.rstd;
         g.csum = at.csum; g.precision = precision;
         rc = fc_launch_gemm(g, s);
@@ -298,7 +299,7 @@ static int run_attention_block(const fc_flow* f, const FcMlp& pre, const FcAttn&
         // to_kv writes the TF32 hi/lo copies of k and v^T the tcgen05 attention consumes, straight from its epilogue
         GemmArgs g = fc_gemm_args_zero();
         g.A1 = context; g.lda1 = f->E; g.K1 = at.kv.K1; g.Wt = at.kv.w; g.ldw = at.kv.ldw; g.bias = at.kv.b;
-        g.Whi = at.kv.whi; g.Wlo = at.kv.wlo; g.ldk = at.kv.ldk; g.M = B * Nc; g.N = 128; g.precision = 1;
+        g.Whi = at.kv.whi; g.Wlo = at.kv.wlo; g.ldk = at.kv.ldk; g.tc_fmt = at.kv.tc_fmt; g.M = B * Nc; g.N = 128; g.precision = 1;
         g.epi = FC_EPI_KVSPLIT; g.ldc = 64; g.kv_nc = Nc;
         fc_attention_tc_scratch_layout(B, Nc, w.kvs, &g.C, &g.kv_klo, &g.kv_vthi, &g.kv_vtlo, &g.kv_ncp);
         rc = fc_launch_gemm(g, s);
@@ -363,7 +364,7 @@ extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* c
         rc = fc_run_mlp_hidden(f->aug, in, M, w.hA, w.hB, w.ldh, precision, s, &last);
         if (rc) return rc;
         GemmArgs g = fc_gemm_args_zero();
-        g.A1 = last; g.lda1 = w.ldh; g.K1 = f->aug_hid; g.Wt = f->aug.out.w; g.ldw = f->aug.out.ldw; g.bias = f->aug.out.b; g.Whi = f->aug.out.whi; g.Wlo = f->aug.out.wlo; g.ldk = f->aug.out.ldk;
+        g.A1 = last; g.lda1 = w.ldh; g.K1 = f->aug_hid; g.Wt = f->aug.out.w; g.ldw = f->aug.out.ldw; g.bias = f->aug.out.b; g.Whi = f->aug.out.whi; g.Wlo = f->aug.out.wlo; g.ldk = f->aug.out.ldk; g.tc_fmt = f->aug.out.tc_fmt;
         g.M = M; g.N = f->aug.out.N; g.epi = FC_EPI_AUGMENT; g.x = w.lat0; g.ldx = w.ldx; g.col0 = f->d_in;
         g.part = w.apart; g.eps = eps; g.ld_eps = f->D - f->d_in; g.precision = precision;
         rc = fc_launch_gemm(g, s);
@@ -385,7 +386,7 @@ extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* c
         if (rc) return rc;
         {
             GemmArgs g = fc_gemm_args_zero();
-            g.A1 = last; g.lda1 = w.ldh; g.K1 = f->hid; g.Wt = y.cpl.out.w; g.ldw = y.cpl.out.ldw; g.bias = y.cpl.out.b; g.Whi = y.cpl.out.whi; g.Wlo = y.cpl.out.wlo; g.ldk = y.cpl.out.ldk;
+            g.A1 = last; g.lda1 = w.ldh; g.K1 = f->hid; g.Wt = y.cpl.out.w; g.ldw = y.cpl.out.ldw; g.bias = y.cpl.out.b; g.Whi = y.cpl.out.whi; g.Wlo = y.cpl.out.wlo; g.ldk = y.cpl.out.ldk; g.tc_fmt = y.cpl.out.tc_fmt;
             g.M = M; g.N = y.cpl.out.N; g.epi = FC_EPI_COUPLING; g.x = lat; g.ldx = w.ldx; g.col0 = f->half;
             g.part = w.cpart; g.precision = precision;
             rc = fc_launch_gemm(g, s);
@@ -397,7 +398,7 @@ extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* c
             // truncation) acts on the small part instead of shrinking z itself 114 times in a row.
             GemmArgs g = fc_gemm_args_zero();
             g.A1 = lat; g.lda1 = w.ldx; g.K1 = y.lu.K1; g.Wt = y.lu.w; g.ldw = y.lu.ldw; g.Whi = y.lu.whi; g.Wlo = y.lu.wlo;
-            g.ldk = y.lu.ldk; g.bias = y.lu.b; g.res = lat; g.ldres = w.ldx; g.res_scale = y.lu_diag;
+            g.ldk = y.lu.ldk; g.tc_fmt = y.lu.tc_fmt; g.bias = y.lu.b; g.res = lat; g.ldres = w.ldx; g.res_scale = y.lu_diag;
             g.C = lat_next; g.ldc = w.ldx; g.M = M; g.N = y.lu.N; g.precision = precision;
             rc = fc_launch_gemm(g, s);
             if (rc) return rc;

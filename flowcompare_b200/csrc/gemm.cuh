@@ -43,10 +43,13 @@ struct GemmArgs {
     // tcgen05 path: the same weight pre-split into TF32 hi / lo parts, N-major rows, K contiguous:
     // [n_tiles*BN][ldk] with ldk = round32(K1) + round32(K2) (zero padded); null -> FFMA only
     const float* Whi; const float* Wlo; int ldk;
+    // format of Whi / Wlo: 0 = TF32 hi / lo parts stored as fp32 (3xTF32 kernel); 1 = fp16 hi and fp16 (W - hi) * 2^11
+    // (3xFP16 kernel: same 11-bit significands, twice the tensor rate and half the operand bytes; see gemm_tc.cu)
+    int tc_fmt;
 };
 
-// tcgen05 tiling of the N dimension: n_tiles = ceil(N/192), BN = ceil(N/n_tiles) rounded up to 16.
-// BN <= 192: two accumulators (main + compensation) take 384 of the 512 TMEM columns, the A operand the rest.
+// tcgen05 tiling of the N dimension: n_tiles = ceil(N/96), BN = ceil(N/n_tiles) rounded up to 16.
+// BN <= 96: two double-buffered accumulators (main + compensation) take 384 of the 512 TMEM columns, the A operand the rest.
 // (FC_TC_BNMAX=64|80: A/B knob; any value <= 96 reads the same packed weights, rows are indexed by output column)
 static inline int fc_tc_bnmax() {
     static int v = 0;
@@ -65,7 +68,7 @@ static inline GemmArgs fc_gemm_args_zero() {
     a.epi = FC_EPI_STORE; a.row_mu = nullptr; a.row_rstd = nullptr; a.csum = nullptr;
     a.x = nullptr; a.ldx = 0; a.col0 = 0; a.part = nullptr; a.eps = nullptr; a.ld_eps = 0;
     a.kv_klo = nullptr; a.kv_vthi = nullptr; a.kv_vtlo = nullptr; a.kv_nc = 0; a.kv_ncp = 0;
-    a.precision = 0; a.Whi = nullptr; a.Wlo = nullptr; a.ldk = 0;
+    a.precision = 0; a.Whi = nullptr; a.Wlo = nullptr; a.ldk = 0; a.tc_fmt = 0;
     return a;
 }
 

@@ -44,6 +44,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -55,8 +56,19 @@ constexpr int TC_STAGES = 5;                   // shared-memory stages: a load i
 #ifndef TC_BN_CAP
 #define TC_BN_CAP 96                           // widest tile (accumulator width); 80 leaves room for 6 A stages (measured slower)
 #endif
-constexpr int TC_TSTAGES = (512 - 4 * TC_BN_CAP) / 32;   // TMEM stages of the A operand, each HALF a k-block
+#ifndef TC_STAGES_F16
+#define TC_STAGES_F16 7                        // 3xFP16 mode: a stage is 16 KB of A + 2 x 6 KB of W, tensor time per k-block is halved
+#endif
 constexpr int TC_THREADS = 448;                // TMA, MMA, 4 converter warps, 8 epilogue warps
+// Per operand format: F16 = false 3xTF32 (weights as fp32 TF32 hi/lo), true 3xFP16 (weights as fp16 hi / 2^11-scaled lo)
+template <bool F16> struct TcCfg {
+    static constexpr int STAGES = F16 ? TC_STAGES_F16 : TC_STAGES;
+    static constexpr int W_ELT = F16 ? 2 : 4;                         // bytes per weight element in shared memory
+    static constexpr int TS_COLS = F16 ? 16 : 32;                     // TMEM columns of one A stage (HALF a k-block: hi | lo)
+    static constexpr int TSTAGES = (512 - 4 * TC_BN_CAP) / TS_COLS;   // TMEM stages of the A operand
+    // stages x (16 KB A + Whi + Wlo at BN = 96) + 8 staging tiles of the epilogue + 1 KB alignment slack
+    static constexpr int SMEM_BYTES = STAGES * (TC_BM * TC_BK * 4 + 2 * 96 * TC_BK * W_ELT) + 8 * 32 * 20 * 4 + 1024;
+};
 // phase timers (scripts/tc_phases.py): compiled out by default, build a variant with -DTC_PHASE_TIMERS=1
 #ifndef TC_PHASE_TIMERS
 #define TC_PHASE_TIMERS 0
@@ -68,11 +80,9 @@ constexpr int TC_THREADS = 448;                // TMA, MMA, 4 converter warps, 8
 #endif
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_TMEM_COLS = 512;                // one persistent CTA per SM
-// 5 stages x (16 KB A + 2 x 12 KB W at BN = 96) + 8 staging tiles of the epilogue + 1 KB alignment slack
-constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + 2 * 96 * TC_BK * 4) + 8 * 32 * 20 * 4 + 1024;
 constexpr int TC_COL_ACC = 2 * TC_BN_CAP;      // accumulator buffer b: main at 192*b, compensation at 192*b + 96
 constexpr int TC_COL_CORR = TC_BN_CAP;
-constexpr int TC_COL_A = 4 * TC_BN_CAP;        // + 32 * stage: 16 columns hi, 16 columns lo
+constexpr int TC_COL_A = 4 * TC_BN_CAP;        // + TS_COLS * stage: first half hi, second half lo
 
 struct TcParams {
     GemmArgs g;
@@ -102,10 +112,11 @@ __device__ unsigned long long fc_tc_dbg[16];
 // PERSISTENT: one CTA per SM walks the (m-tile, n-tile) list with stride gridDim.x.  The accumulators are double
 // buffered in TMEM, so the epilogue of tile j (8 dedicated warps) runs while the tensor core is already on tile j+1;
 // the TMA / converter / MMA pipelines never drain between tiles (global k-block counters carry the barrier phases).
-template <int EPI, int ACT, bool RES>
+template <int EPI, int ACT, bool RES, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
+    constexpr int TC_STAGES = TcCfg<F16>::STAGES, TC_TSTAGES = TcCfg<F16>::TSTAGES, TS_COLS = TcCfg<F16>::TS_COLS;   // shadow the globals
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 4];
     __shared__ uint32_t tmem_base_slot;
@@ -117,7 +128,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024 B alignment
     const int BN = p.BN;                    // widest tile of this launch: shared-memory layout and TMA box
-    const int w_bytes = BN * TC_BK * 4;
+    const int w_bytes = BN * TC_BK * TcCfg<F16>::W_ELT;
     const int stage_bytes = TC_A_BYTES + 2 * w_bytes;
     auto a_raw = [&](int s) { return smem + s * stage_bytes; };
     auto w_hi = [&](int s) { return smem + s * stage_bytes + TC_A_BYTES; };
@@ -196,7 +207,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             const int tile_bn = tile_bn_of(n_tile);
             const int buf = it & 1;
             // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2), K-major, N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            // (kind::f16: A = B = fp16 is format 0)
+            const uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(tile_bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t d_main = tmem + TC_COL_ACC * buf, d_corr = d_main + TC_COL_CORR;
             TC_T(ma0);
             mbar_wait(&acc_free[buf], ((it >> 1) & 1) ^ 1, 190);     // the epilogue of tile it-2 has drained this buffer
@@ -210,8 +222,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 TC_T(mf1);
                 TC_ACC(m_full, mf0, mf1);
                 full_seen = false;
-                const uint64_t dbh = make_kmajor_sw128_desc(smem_u32(w_hi(s)));
-                const uint64_t dbl = make_kmajor_sw128_desc(smem_u32(w_lo(s)));
+                const uint64_t dbh = F16 ? make_kmajor_sw64_desc(smem_u32(w_hi(s))) : make_kmajor_sw128_desc(smem_u32(w_hi(s)));
+                const uint64_t dbl = F16 ? make_kmajor_sw64_desc(smem_u32(w_lo(s))) : make_kmajor_sw128_desc(smem_u32(w_lo(s)));
                 // the A operand arrives in TMEM in HALF k-blocks (16 k: 16 columns hi + 16 lo per stage)
 #pragma unroll
                 for (int h = 0; h < 2; ++h, ++hb) {
@@ -225,15 +237,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     // pipe: probe the NEXT half's barriers now (the converters run ahead, so they have usually fired).
                     conv_seen = mbar_test(&conv[(hb + 1) % TC_TSTAGES], ((hb + 1) / TC_TSTAGES) & 1);
                     if (h == 1) full_seen = mbar_test(&full[(g + 1) % TC_STAGES], ((g + 1) / TC_STAGES) & 1);
-                    const uint32_t t_hi = tmem + TC_COL_A + 32 * ts, t_lo = t_hi + 16;
+                    const uint32_t t_hi = tmem + TC_COL_A + TS_COLS * ts, t_lo = t_hi + TS_COLS / 2;
                     if (elect_one()) {
+                        if (F16) {
+                            // one kind::f16 MMA covers the half k-block (16 k = 32 bytes of the 64-byte weight row)
+                            const uint64_t adv = (uint64_t)(h * 32 >> 4);
+                            umma_f16_ts(d_corr, t_lo, dbh + adv, idesc, (t | h) != 0);   // (A - Ahi) 2^11 . Whi
+                            umma_f16_ts(d_corr, t_hi, dbl + adv, idesc, 1);              // Ahi . (W - Whi) 2^11
+                            umma_f16_ts(d_main, t_hi, dbh + adv, idesc, (t | h) != 0);
+                        } else {
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const int k = 2 * h + kk;
-                            const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
-                            umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (t | k) != 0);
-                            umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
-                            umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                            for (int kk = 0; kk < 2; ++kk) {
+                                const int k = 2 * h + kk;
+                                const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
+                                umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                                umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
+                                umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                            }
                         }
                         umma_commit(&tfree[ts]);                 // TMEM A stage reusable once these MMAs retire
                         if (h == 1) umma_commit(&w_free[s]);     // W smem stage reusable once these MMAs retire
@@ -278,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 const float4* rowp = reinterpret_cast<const float4*>(a_raw(s) + row_in_tile * 128);
 #pragma unroll
                 for (int h = 0; h < 2; ++h, ++hb) {
-                    uint32_t hl[32];   // this half k-block: [0,16) hi, [16,32) lo  -> one 32-column TMEM stage
+                    uint32_t hl[TS_COLS];   // this half k-block: first half hi, second half lo  -> one TMEM stage
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         // 128B swizzle: logical 16-byte chunk j of row r sits at physical chunk j ^ (r & 7); a quarter
@@ -286,13 +306,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         const int j = 4 * h + jj;
                         const float4 x = rowp[j ^ (row_in_tile & 7)];
                         const float xv[4] = {x.x, x.y, x.z, x.w};
+                        if (F16) {
+                            // hi = fp16(x) (11-bit significand, like TF32), lo = fp16((x - hi) * 2^11): the residual is
+                            // taken from the value the tensor core will actually see, so fp16 subnormals lose nothing;
+                            // |x| >= 65520 becomes inf and the row's result NaN (loud, never silently clipped)
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            // cvt.rna.tf32.f32 by hand (add half a TF32 ulp to the magnitude, clear the low 13 bits):
-                            // 2 ALU ops instead of the 4 (add, inf test, select, mask) ptxas emits; inputs are finite
-                            const uint32_t u = (__float_as_uint(xv[e]) + 0x1000u) & 0xffffe000u;
-                            hl[4 * jj + e] = u;
-                            hl[16 + 4 * jj + e] = __float_as_uint(xv[e] - __uint_as_float(u));
+                            for (int e = 0; e < 4; e += 2) {
+                                const uint32_t hp = pack_f16x2(xv[e], xv[e + 1]);
+                                float h0, h1;
+                                unpack_f16x2(hp, h0, h1);
+                                hl[2 * jj + (e >> 1)] = hp;
+                                hl[TS_COLS / 2 + 2 * jj + (e >> 1)] = pack_f16x2((xv[e] - h0) * 2048.0f, (xv[e + 1] - h1) * 2048.0f);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                // cvt.rna.tf32.f32 by hand (add half a TF32 ulp to the magnitude, clear the low 13 bits):
+                                // 2 ALU ops instead of the 4 (add, inf test, select, mask) ptxas emits; inputs are finite
+                                const uint32_t u = (__float_as_uint(xv[e]) + 0x1000u) & 0xffffe000u;
+                                hl[4 * jj + e] = u;
+                                hl[TS_COLS / 2 + 4 * jj + e] = __float_as_uint(xv[e] - __uint_as_float(u));
+                            }
                         }
                     }
                     if (h == 1) mbar_arrive(&a_free[s]);   // whole row is in registers: the A smem stage may be refilled
@@ -307,7 +341,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     TC_T(ct1);
                     TC_ACC(c_tfree, ct0, ct1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    tmem_st32(tmem + lane_addr + TC_COL_A + 32 * ts, hl);
+                    if constexpr (F16) tmem_st16(tmem + lane_addr + TC_COL_A + TS_COLS * ts, hl);
+                    else tmem_st32(tmem + lane_addr + TC_COL_A + TS_COLS * ts, hl);
                     pending = ts;
                 }
             }
@@ -389,7 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 {
                     tmem_ld16(acc_corr + (uint32_t)c0, r);
     #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = F16 ? fmaf(__uint_as_float(r[j]), 4.8828125e-4f, v[j]) : v[j] + __uint_as_float(r[j]);
                 }
                 const int col = n0 + c0;
                 if (col >= a.N) continue;                     // warp-uniform
@@ -612,39 +647,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
 
 // ----------------------------------------------------------------------------- host: tensor maps
 struct MapKey {
-    const void* base; uint64_t inner, outer, stride; uint32_t box_outer;
+    const void* base; uint64_t inner, outer, stride; uint32_t box_outer; int f16;
     bool operator==(const MapKey& o) const {
-        return base == o.base && inner == o.inner && outer == o.outer && stride == o.stride && box_outer == o.box_outer;
+        return base == o.base && inner == o.inner && outer == o.outer && stride == o.stride && box_outer == o.box_outer && f16 == o.f16;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         size_t h = std::hash<const void*>()(k.base);
         h ^= std::hash<uint64_t>()(k.inner * 1315423911u + k.outer) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
-        h ^= std::hash<uint64_t>()(k.stride * 31 + k.box_outer) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+        h ^= std::hash<uint64_t>()(k.stride * 31 + k.box_outer * 2 + k.f16) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
         return h;
     }
 };
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 std::mutex g_maps_mu;
 
-// fp32 [outer][inner] row-major with row stride `stride_floats`; box = 32 x box_outer, 128B swizzle, OOB -> 0.
+// [outer][inner] row-major with row stride `stride_floats` ELEMENTS; box = 32 x box_outer, OOB -> 0.  fp32 elements with
+// the 128B swizzle (a box row is 128 bytes) or, f16 = 1, fp16 elements with the 64B swizzle (a box row is 64 bytes).
 // Maps only encode address + geometry, so they are cached (the flow re-uses the same workspace every call).
-bool get_map(const float* base, uint64_t inner, uint64_t outer, uint64_t stride_floats, uint32_t box_outer, CUtensorMap* out) {
-    MapKey key{base, inner, outer, stride_floats, box_outer};
+bool get_map(const void* base, uint64_t inner, uint64_t outer, uint64_t stride_floats, uint32_t box_outer, CUtensorMap* out,
+             int f16 = 0) {
+    MapKey key{base, inner, outer, stride_floats, box_outer, f16};
     std::lock_guard<std::mutex> lk(g_maps_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return true; }
     FcEncodeTiledFn enc = fc_get_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {stride_floats * 4};
+    cuuint64_t strides[1] = {stride_floats * (f16 ? 2 : 4)};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         fprintf(stderr, "flowcompare_b200: cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu stride=%llu box=%ux%u\n",
                 (int)r, (const void*)base, (unsigned long long)inner, (unsigned long long)outer,
@@ -669,16 +706,35 @@ bool fc_gemm_tc_supported(const GemmArgs& a) {
 }
 
 namespace {
-template <int EPI, int ACT, bool RES>
-cudaError_t launch_tc(const cudaLaunchConfig_t& cfg, const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mWh,
-                      const CUtensorMap& mWl, const TcParams& p) {
-    static bool configured = false;   // one per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+template <int EPI, int ACT, bool RES, bool F16>
+cudaError_t launch_tc2(cudaLaunchConfig_t cfg, int dev, const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mWh,
+                       const CUtensorMap& mWl, const TcParams& p) {
+    // the dynamic shared-memory opt-in is PER DEVICE (and per instantiation): one bit per device id
+    static std::atomic<uint64_t> configured{0};
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, ACT, RES, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             TcCfg<F16>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.fetch_or(bit, std::memory_order_release);
     }
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, ACT, RES>, mA1, mA2, mWh, mWl, p);
+    cfg.dynamicSmemBytes = TcCfg<F16>::SMEM_BYTES;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, ACT, RES, F16>, mA1, mA2, mWh, mWl, p);
+}
+template <int EPI, int ACT, bool RES>
+cudaError_t launch_tc(const cudaLaunchConfig_t& cfg, int dev, int f16, const CUtensorMap& mA1, const CUtensorMap& mA2,
+                      const CUtensorMap& mWh, const CUtensorMap& mWl, const TcParams& p) {
+    return f16 ? launch_tc2<EPI, ACT, RES, true>(cfg, dev, mA1, mA2, mWh, mWl, p)
+               : launch_tc2<EPI, ACT, RES, false>(cfg, dev, mA1, mA2, mWh, mWl, p);
+}
+int sm_count(int dev) {   // per device, cached
+    static std::atomic<int> cache[64];
+    int v = cache[dev & 63].load(std::memory_order_relaxed);
+    if (!v) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 0;
+        cache[dev & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
 }
 }  // namespace
 
@@ -704,17 +760,19 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     if (!get_map(a.A1, (uint64_t)a.K1, (uint64_t)a.M, (uint64_t)a.lda1, TC_BM, &mA1)) return FC_ERR_CUDA;
     if (a.K2) { if (!get_map(a.A2, (uint64_t)a.K2, (uint64_t)a.M, (uint64_t)a.lda2, TC_BM, &mA2)) return FC_ERR_CUDA; }
     else mA2 = mA1;
-    if (!get_map(a.Whi, (uint64_t)a.ldk, (uint64_t)p.n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWh)) return FC_ERR_CUDA;
-    if (!get_map(a.Wlo, (uint64_t)a.ldk, (uint64_t)p.n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWl)) return FC_ERR_CUDA;
-    static int nsm = 0;
-    if (!nsm) { int dev = 0; FC_CUDA_OK(cudaGetDevice(&dev)); FC_CUDA_OK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev)); }
+    const int f16 = a.tc_fmt ? 1 : 0;
+    if (!get_map(a.Whi, (uint64_t)a.ldk, (uint64_t)p.n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWh, f16)) return FC_ERR_CUDA;
+    if (!get_map(a.Wlo, (uint64_t)a.ldk, (uint64_t)p.n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWl, f16)) return FC_ERR_CUDA;
+    int dev = 0;
+    FC_CUDA_OK(cudaGetDevice(&dev));
+    const int nsm = sm_count(dev);
+    FC_REQUIRE(nsm > 0);
     const int total_tiles = p.n_tiles * p.m_tiles;
     FcProfScope prof(FC_CLS_GEMM_TC, 2.0 * a.M * a.N * (a.K1 + a.K2),
                      4.0 * ((double)a.M * (a.K1 + a.K2) + (double)a.N * (a.K1 + a.K2) + (double)a.M * a.N), stream);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(total_tiles < nsm ? total_tiles : nsm);      // persistent: one CTA per SM
     cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
     cfg.stream = stream;
     // FC_TC_PDL=1 turns programmatic dependent launch on: measured +0.5 % on the step (406.8 vs 405.0 pairs/s, all
     // parity tests green), off by default until it has been through the multi-GPU runs
@@ -728,22 +786,22 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     const bool res = a.res != nullptr;
     cudaError_t le = cudaErrorInvalidValue;
     if (a.epi == FC_EPI_STORE) {
-        if (a.act == FC_ACT_NONE)       le = res ? launch_tc<FC_EPI_STORE, FC_ACT_NONE, true>(cfg, mA1, mA2, mWh, mWl, p)
-                                                 : launch_tc<FC_EPI_STORE, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
-        else if (a.act == FC_ACT_GELU)  le = res ? launch_tc<FC_EPI_STORE, FC_ACT_GELU, true>(cfg, mA1, mA2, mWh, mWl, p)
-                                                 : launch_tc<FC_EPI_STORE, FC_ACT_GELU, false>(cfg, mA1, mA2, mWh, mWl, p);
-        else if (a.act == FC_ACT_LRELU) le = res ? launch_tc<FC_EPI_STORE, FC_ACT_LRELU, true>(cfg, mA1, mA2, mWh, mWl, p)
-                                                 : launch_tc<FC_EPI_STORE, FC_ACT_LRELU, false>(cfg, mA1, mA2, mWh, mWl, p);
-        else if (a.act == FC_ACT_RELU)  le = res ? launch_tc<FC_EPI_STORE, FC_ACT_RELU, true>(cfg, mA1, mA2, mWh, mWl, p)
-                                                 : launch_tc<FC_EPI_STORE, FC_ACT_RELU, false>(cfg, mA1, mA2, mWh, mWl, p);
+        if (a.act == FC_ACT_NONE)       le = res ? launch_tc<FC_EPI_STORE, FC_ACT_NONE, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
+        else if (a.act == FC_ACT_GELU)  le = res ? launch_tc<FC_EPI_STORE, FC_ACT_GELU, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_GELU, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
+        else if (a.act == FC_ACT_LRELU) le = res ? launch_tc<FC_EPI_STORE, FC_ACT_LRELU, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_LRELU, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
+        else if (a.act == FC_ACT_RELU)  le = res ? launch_tc<FC_EPI_STORE, FC_ACT_RELU, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_RELU, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
     } else if (a.epi == FC_EPI_LNQ && a.act == FC_ACT_NONE && !res) {
-        le = launch_tc<FC_EPI_LNQ, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
+        le = launch_tc<FC_EPI_LNQ, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
     } else if (a.epi == FC_EPI_COUPLING) {
-        le = launch_tc<FC_EPI_COUPLING, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
+        le = launch_tc<FC_EPI_COUPLING, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
     } else if (a.epi == FC_EPI_AUGMENT) {
-        le = launch_tc<FC_EPI_AUGMENT, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
+        le = launch_tc<FC_EPI_AUGMENT, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
     } else if (a.epi == FC_EPI_KVSPLIT && a.act == FC_ACT_NONE && !res) {
-        le = launch_tc<FC_EPI_KVSPLIT, FC_ACT_NONE, false>(cfg, mA1, mA2, mWh, mWl, p);
+        le = launch_tc<FC_EPI_KVSPLIT, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
     } else {
         return FC_ERR_UNSUPPORTED;
     }

@@ -8,13 +8,15 @@
 constexpr int FC_MAX_HIDDEN = 8;
 constexpr int32_t FC_FLOW_MAGIC = 0x46435F46;  // 'FC_F'
 constexpr int32_t FC_EMB_MAGIC = 0x46435F45;   // 'FC_E'
-constexpr int32_t FC_ARENA_VERSION = 2;
+constexpr int32_t FC_ARENA_VERSION = 2;        // tensor-core weight copies: TF32 hi/lo (fp32 storage)
+constexpr int32_t FC_ARENA_VERSION_F16 = 3;    // tensor-core weight copies: fp16 hi / scaled lo
 
 struct FcLinear {
     const float* w = nullptr;  // K-major [Kp][ldw]
     const float* b = nullptr;  // [N] or null
     const float* whi = nullptr; const float* wlo = nullptr;  // tcgen05 copies [n_tiles*BN][ldk] or null
     int K1 = 0, K2 = 0, N = 0, ldw = 0, ldk = 0;
+    int tc_fmt = 0;            // format of whi / wlo (GemmArgs::tc_fmt)
 };
 
 struct FcMlp {
@@ -70,6 +72,7 @@ struct fc_embedder {
 // table cursor used by the *_create functions
 struct FcCursor {
     const int64_t* table; int n; int pos; const float* arena; int64_t arena_floats; bool ok;
+    int tc_fmt = 0;
     int64_t next() { if (pos >= n) { ok = false; return -1; } return table[pos++]; }
     const float* ptr(int64_t off, int64_t count) {
         if (off < 0) return nullptr;
@@ -86,8 +89,8 @@ struct FcCursor {
         const int64_t hoff = next(), loff = next();
         if (hoff >= 0 && loff >= 0) {
             l.ldk = fc_tc_kpad(K1) + (K2 ? fc_tc_kpad(K2) : 0);
-            const int64_t cnt = (int64_t)fc_tc_n_tiles(N) * fc_tc_bn(N) * l.ldk;
-            l.whi = ptr(hoff, cnt); l.wlo = ptr(loff, cnt);
+            const int64_t cnt = (int64_t)fc_tc_n_tiles(N) * fc_tc_bn(N) * l.ldk / (tc_fmt ? 2 : 1);   // fp16: two per float slot
+            l.whi = ptr(hoff, cnt); l.wlo = ptr(loff, cnt); l.tc_fmt = tc_fmt;
             if (!l.whi || !l.wlo) ok = false;
         }
         return l;

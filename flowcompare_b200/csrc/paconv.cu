@@ -316,7 +316,7 @@ PaWs carve_pa(const fc_embedder* e, const PaModel* pm, int B, int Nc, void* base
 int gemm_relu(const FcLinear& l, const float* A, int lda, int act, float* C, int ldc, long long M, int precision, cudaStream_t s) {
     GemmArgs g = fc_gemm_args_zero();
     g.A1 = A; g.lda1 = lda; g.K1 = l.K1; g.Wt = l.w; g.ldw = l.ldw; g.bias = l.b; g.act = act; g.Whi = l.whi; g.Wlo = l.wlo;
-    g.ldk = l.ldk; g.C = C; g.ldc = ldc; g.M = (int)M; g.N = l.N; g.precision = precision;
+    g.ldk = l.ldk; g.tc_fmt = l.tc_fmt; g.C = C; g.ldc = ldc; g.M = (int)M; g.N = l.N; g.precision = precision;
     return fc_launch_gemm(g, s);
 }
 

@@ -41,7 +41,9 @@ class FlowCompareB200:
 
     Parameters: `models` -- the reference's `models_dict` ({'flow': Flow, 'input_embedder': Module}) or a
     pair of state_dicts `(flow_sd, embedder_sd)`; `config` -- the reference config dict (YAML values).
-    `precision`: 'fp32' (exact FFMA GEMMs) or 'tf32x3' (tcgen05 tensor cores, 3xTF32 error-compensated).
+    `precision`: 'fp32' (exact FFMA GEMMs), 'tf32x3' (tcgen05 tensor cores, 3xTF32 error-compensated) or 'fp16x3'
+    (tcgen05, 3xFP16 error-compensated: the same 11-bit significands at twice the tensor rate; activations beyond
+    fp16's range, |a| >= 65520, turn the affected rows into NaN instead of a silently wrong value).
     """
 
     def __init__(self, models, config, device="cuda:0", precision="fp32"):
@@ -50,7 +52,8 @@ class FlowCompareB200:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.FlowCompareError("flowcompare_b200 runs on CUDA devices only (no CPU fallback)")
-        self.precision = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3}[precision]
+        self.precision_name = precision
+        self.precision, tc_format = _lib.PRECISIONS[precision]
         if isinstance(models, dict):
             for m in (models["flow"], models["input_embedder"]):
                 if getattr(m, "training", False):
@@ -65,8 +68,9 @@ class FlowCompareB200:
         self.has_extra = bool(self.config["using_extra_context"])
         self.k = self.config["n_neighbors"]
         with torch.cuda.device(self.device):
-            self._flow = self._create(packing.pack_flow(flow_sd, self.config), self.lib.fc_flow_create, "fc_flow_create")
-            self._emb = self._create(packing.pack_embedder(emb_sd, self.config), self.lib.fc_embedder_create,
+            self._flow = self._create(packing.pack_flow(flow_sd, self.config, tc_format), self.lib.fc_flow_create,
+                                      "fc_flow_create")
+            self._emb = self._create(packing.pack_embedder(emb_sd, self.config, tc_format), self.lib.fc_embedder_create,
                                      "fc_embedder_create")
         self._ws = None
         self._seed_counter = 0

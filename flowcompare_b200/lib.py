@@ -15,7 +15,10 @@ ERRORS = {0: "FC_OK", -1: "FC_ERR_INVALID_ARG", -2: "FC_ERR_CUDA", -3: "FC_ERR_L
           -4: "FC_ERR_WORKSPACE", -5: "FC_ERR_UNSUPPORTED", -6: "FC_ERR_MODEL"}
 
 PREC_FP32 = 0
+PREC_TENSOR = 1          # tcgen05 path; 3xTF32 or 3xFP16 according to the format of the packed weights
 PREC_TF32X3 = 1
+# engine precision name -> (precision argument of the C entry points, tensor-core weight format packed into the arena)
+PRECISIONS = {"fp32": (PREC_FP32, "tf32"), "tf32x3": (PREC_TENSOR, "tf32"), "fp16x3": (PREC_TENSOR, "fp16")}
 
 c_int, c_i64, c_f, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 c_u64 = ctypes.c_uint64
@@ -29,6 +32,7 @@ SIGNATURES = {
     "fc_knn_query": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "fc_gemm": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "fc_gemm_tf32x3": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "fc_gemm_f16x3": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "fc_edgeconv_gather_max": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "fc_cross_attention": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_vp]),
     "fc_cross_attention_tf32x3": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_vp]),

@@ -29,7 +29,9 @@ from .configs import derive
 
 FLOW_MAGIC = 0x46435F46
 EMB_MAGIC = 0x46435F45
-ARENA_VERSION = 2
+ARENA_VERSION = 2        # tensor-core weight copies as TF32 hi / lo (fp32 storage)
+ARENA_VERSION_F16 = 3    # tensor-core weight copies as fp16 hi / 2^11-scaled fp16 lo
+TC_FORMATS = {"tf32": ARENA_VERSION, "fp16": ARENA_VERSION_F16}
 
 
 def gemm_ldw(n):
@@ -61,8 +63,18 @@ def tf32_round(x):
     return r.view(torch.float32)
 
 
+def f16_split(w32):
+    """fp32 -> (hi, lo) fp16 tensors with w ~= hi + lo * 2^-11: hi = fp16(w) carries the same 11-bit significand as
+    TF32, lo = fp16((w - hi) * 2^11) the next 11 bits (the scale keeps it clear of fp16's subnormal range)."""
+    hi = w32.to(torch.float16)
+    lo = ((w32 - hi.to(torch.float32)) * 2048.0).to(torch.float16)
+    return hi, lo
+
+
 class Arena:
-    def __init__(self):
+    def __init__(self, tc_format="tf32"):
+        assert tc_format in TC_FORMATS, tc_format
+        self.tc_format = tc_format
         self.chunks = []
         self.size = 0
         self.table = []
@@ -105,6 +117,13 @@ class Arena:
         W32[:N, :K1] = W[:, :K1].to(torch.float32)
         if K2:
             W32[:N, t1:t1 + K2] = W[:, K1:].to(torch.float32)
+        if self.tc_format == "fp16":
+            hi, lo = f16_split(W32)
+            assert torch.isfinite(hi.to(torch.float32)).all(), "weight beyond fp16 range: use tc_format='tf32'"
+            # two fp16 per fp32 slot of the arena (bit patterns are preserved by every copy on the way to the device)
+            self.table.append(self.add(hi.view(torch.float32)))
+            self.table.append(self.add(lo.view(torch.float32)))
+            return
         hi = tf32_round(W32)
         lo = tf32_round(W32 - hi)
         self.table.append(self.add(hi))
@@ -213,7 +232,7 @@ def fold_inverse_actnorm_lu(flow_sd, config):
     return out
 
 
-def pack_flow(flow_sd, config):
+def pack_flow(flow_sd, config, tc_format="tf32"):
     cfg = derive(config)
     from .spec import _check_supported
     _check_supported(cfg)
@@ -223,7 +242,7 @@ def pack_flow(flow_sd, config):
     E = cfg["input_embedding_dim"]
     inner = cfg["cross_heads"] * cfg["cross_dim_head"]
     assert inner == 64, "only inner_dim 64 (all shipped configs) is built"
-    ar = Arena()
+    ar = Arena(tc_format)
     ar.table.append(0)  # placeholder for the fp64 log-det constant
     has_cb = bool(ex) or is_global
     cb_cols, cb_bias = [], []
@@ -302,7 +321,7 @@ def pack_flow(flow_sd, config):
     assert hid == aug_hid, "coupling and augment conditioners must share the hidden width"
     ar.table[0] = struct.unpack("<q", struct.pack("<d", ldj_const))[0]
     arena, table = ar.finish()
-    header = np.asarray([FLOW_MAGIC, ARENA_VERSION, L, D, d_in, half, ex, int(is_global), E, inner,
+    header = np.asarray([FLOW_MAGIC, TC_FORMATS[tc_format], L, D, d_in, half, ex, int(is_global), E, inner,
                          cfg["attn_input_dim"], hid, n_hid, pre_hid or 0, n_pre, aug_hid, n_aug,
                          augpre_hid, n_augpre], dtype=np.int32)
     return header, table, arena
@@ -315,16 +334,16 @@ def _bn_fold(sd, prefix):
     return a, b - a * rm
 
 
-def pack_embedder(emb_sd, config):
+def pack_embedder(emb_sd, config, tc_format="tf32"):
     cfg = derive(config)
     name = cfg["input_embedder"]
     if name == "PAConv":
         from .paconv_packing import pack_paconv
-        return pack_paconv(emb_sd, cfg)
+        return pack_paconv(emb_sd, cfg, tc_format)
     if name not in ("DGCNNembedder", "DGCNNembedderGlobal"):
         raise NotImplementedError(name)
     kind = 1 if name == "DGCNNembedderGlobal" else 0
-    ar = Arena()
+    ar = Arena(tc_format)
     cins = [cfg["input_dim"], 64, 64, 128]
     for i in range(4):
         W = _d(emb_sd, f"conv{i + 1}.0.weight")[:, :, 0, 0]
@@ -340,6 +359,6 @@ def pack_embedder(emb_sd, config):
     ar.linear(a5[:, None] * W5, b5, 512)
     out_hid, n_out = _pack_plain_mlp(ar, emb_sd, "out_mlp", 1024 if kind == 1 else 512)
     arena, table = ar.finish()
-    header = np.asarray([EMB_MAGIC, ARENA_VERSION, kind, cfg["input_dim"], cfg["n_neighbors"],
+    header = np.asarray([EMB_MAGIC, TC_FORMATS[tc_format], kind, cfg["input_dim"], cfg["n_neighbors"],
                          cfg["input_embedding_dim"], out_hid, n_out], dtype=np.int32)
     return header, table, arena

@@ -8,7 +8,7 @@ W[o][(m, c)] = a_o * WB[c, m*Cout + o] with the layer's eval-mode BatchNorm (a, 
 import numpy as np
 import torch
 
-from .packing import ARENA_VERSION, EMB_MAGIC, Arena, _bn_fold, _d, _pack_plain_mlp
+from .packing import EMB_MAGIC, TC_FORMATS, Arena, _bn_fold, _d, _pack_plain_mlp
 from .paconv_spec import M_KERNELS, NSAMPLE, fp_mlps, sa_mlps
 
 
@@ -22,9 +22,9 @@ def latched_npoints(n_context):
     return out
 
 
-def pack_paconv(sd, cfg):
+def pack_paconv(sd, cfg, tc_format="tf32"):
     c = cfg["input_dim"] - 3
-    ar = Arena()
+    ar = Arena(tc_format)
     for i, widths in enumerate(sa_mlps(c)):
         for j in range(len(widths) - 1):
             p = f"SA_modules.{i}.mlps.0.layer{j}"
@@ -49,6 +49,6 @@ def pack_paconv(sd, cfg):
     out_hid, n_out = _pack_plain_mlp(ar, sd, "out_mlp", 128)
     arena, table = ar.finish()
     npts = latched_npoints(cfg["n_samples_context"])
-    header = np.asarray([EMB_MAGIC, ARENA_VERSION, 2, cfg["input_dim"], 0, cfg["input_embedding_dim"], out_hid, n_out]
+    header = np.asarray([EMB_MAGIC, TC_FORMATS[tc_format], 2, cfg["input_dim"], 0, cfg["input_embedding_dim"], out_hid, n_out]
                         + npts + [NSAMPLE, M_KERNELS], dtype=np.int32)
     return header, table, arena

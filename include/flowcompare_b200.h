@@ -81,6 +81,13 @@ FC_API int fc_gemm(const float* A, int lda, const float* Wt, int ldw, const floa
 FC_API int fc_gemm_tf32x3(const float* A, int lda, const float* Whi, const float* Wlo, int ldk,
                    const float* bias, float* C, int ldc, int M, int N, int K, int act, fc_stream_t stream);
 
+/* Same product as 3xFP16: Whi16 = fp16(W), Wlo16 = fp16((W - Whi16) * 2^11), same [rows][ldk] layout with 2-byte
+ * elements.  fp16 carries the same 11-bit significand as TF32, so the three products A_hi W_hi + 2^-11 (A_lo' W_hi +
+ * A_hi W_lo') are as accurate as the TF32 ones at twice the tensor rate and half the operand bytes; the price is fp16's
+ * exponent range: an activation with |a| >= 65520 turns its output row into NaN (loud, never a silently wrong value). */
+FC_API int fc_gemm_f16x3(const float* A, int lda, const void* Whi16, const void* Wlo16, int ldk,
+                  const float* bias, float* C, int ldc, int M, int N, int K, int act, fc_stream_t stream);
+
 /* ------------------------------------------------------------------ EdgeConv --------------
  * One DGCNN EdgeConv block, reference models/pytorch_gcn.py:23-47 + :63-74 + :86-100:
  *   out_i = max_{j in idx_i} LeakyReLU_0.2( BN_eval( W * [x_j - x_i ; x_i] ) )

@@ -36,6 +36,7 @@ FIXTURES = {
     "full_dgcnn_attn_extra": ("dgcnn_attn_extra", {}, 1, 2, 4),
     "full_dgcnn_global": ("dgcnn_global", {}, 1, 3, 5),
     "full_paconv_attn": ("paconv_attn", {}, 1, 4, 6),
+    "full_paconv_attn_extra": ("paconv_attn_extra", {}, 1, 5, 7),
 }
 
 

@@ -73,3 +73,21 @@ def load_yaml_config(name: str) -> dict:
     with open(os.path.join(REFERENCE_ROOT, "config", f"{name}.yaml")) as f:
         raw = yaml.safe_load(f)
     return {k: v["value"] for k, v in raw.items() if isinstance(v, dict) and "value" in v}
+
+
+def load_test_flow():
+    """The reference's evaluation script `test_flow.py` as a module (for `log_prob_to_change` / `clamp_infs`,
+    test_flow.py:241-275).  Its data-set and Dash imports (`dataloaders/__init__.py:3` imports a file that does not
+    exist; `visualize_change_map.py` needs dash) are replaced by empty stubs; nothing of the functions under test
+    touches them."""
+    load()
+    stubs = {"dataloaders": {"ChallengeDataset": object, "AmsVoxelLoader": object, "FullSceneLoader": object},
+             "visualize_change_map": {"visualize_change": None}}
+    for name, attrs in stubs.items():
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+    import test_flow
+    return test_flow

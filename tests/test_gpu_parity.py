@@ -3,10 +3,13 @@
 and the reference's golden outputs (tests/golden/*.pt).  /root/reference is NOT needed.
 
 Tolerances (north_star): kNN indices bit-exact against the canonical-arithmetic oracle; per-point
-log-prob within 1e-3 nats absolute, mean within 1e-4 relative.  Where a full-depth (115-layer) case is
-compared with an fp32 reference whose own rounding noise is measured at ~2e-3 nats (DESIGN.md
-"precision"), the per-point bound is widened to 5e-3 and the test says so.
+log-prob within 1e-3 nats absolute, mean within 1e-4 relative.  At full depth (115 layers) the reference's own
+fp32 output is 0.7e-3 .. 1.6e-3 nats (max over the cloud) away from an exact evaluation of the same model
+(oracle/make_fp64_truth.py prints it per fixture), so the full-depth tests check the CUDA path against that fp64
+truth with north_star's 1e-3 (`test_full_depth_within_1e3_of_fp64_truth`) and against the reference's fp32 golden
+with 1e-3 plus the reference's own distance from the truth at that point.
 """
+import functools
 import math
 
 import numpy as np
@@ -93,7 +96,7 @@ def _pack_wt(W):
 
 @pytest.mark.parametrize("M,N,K,act", [(1024, 512, 512, 1), (1000, 300, 150, 0), (513, 64, 256, 0), (77, 588, 512, 2),
                                        (2500, 128, 6, 0), (4096, 256, 662, 1)])
-@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("precision", [0, 1, 2])
 def test_gemm_matches_fp64(lib, M, N, K, act, precision):
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g)
@@ -111,12 +114,16 @@ def test_gemm_matches_fp64(lib, M, N, K, act, precision):
         rows, ldk = packing.tc_n_tiles(N) * packing.tc_bn(N), packing.tc_kpad(K)
         W32 = torch.zeros(rows, ldk)
         W32[:N, :K] = W
-        hi = packing.tf32_round(W32)
-        lo = packing.tf32_round(W32 - hi)
+        if precision == 1:
+            hi = packing.tf32_round(W32)
+            lo = packing.tf32_round(W32 - hi)
+            fn = lib.fc_gemm_tf32x3
+        else:
+            hi, lo = packing.f16_split(W32)
+            fn = lib.fc_gemm_f16x3
         hi, lo = hi.to(DEV), lo.to(DEV)
-        rc = lib.fc_gemm_tf32x3(Ad.data_ptr(), lda, hi.data_ptr(), lo.data_ptr(), ldk, bd.data_ptr(), C.data_ptr(), N, M, N,
-                                K, act, _stream())
-    if precision == 1 and rc == -5:
+        rc = fn(Ad.data_ptr(), lda, hi.data_ptr(), lo.data_ptr(), ldk, bd.data_ptr(), C.data_ptr(), N, M, N, K, act, _stream())
+    if precision >= 1 and rc == -5:
         pytest.skip("tcgen05 path does not cover this shape")
     assert rc == 0, (rc, fclib.load().fc_last_error())
     ref = A.double() @ W.double().t() + b.double()
@@ -192,7 +199,7 @@ def test_embedder_matches_port_and_golden(name):
 
 
 @pytest.mark.parametrize("name", ["tiny_paconv_attn", "tiny_paconv_attn_extra", "full_paconv_attn"])
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp16x3"])
 def test_paconv_embedder_matches_port_and_golden(name, precision):
     """PAConv embedder (FPS, heap kNN, grouping, ScoreNet + weight-bank GEMM, max, 3-NN interpolation, FP MLPs)
     against the oracle port (whose index kernels are oracle/pointops_ref.c) and the reference's golden output.
@@ -209,8 +216,8 @@ def test_paconv_embedder_matches_port_and_golden(name, precision):
     assert (got[:, ::stride] - ref).abs().max().item() < 1e-4 * max(1.0, scale)
 
 
-@pytest.mark.parametrize("name", ["tiny_paconv_attn", "tiny_paconv_attn_extra", "full_paconv_attn"])
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("name", ["tiny_paconv_attn", "tiny_paconv_attn_extra"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp16x3"])
 def test_inner_loop_paconv_matches_reference_golden(name, precision):
     cfg, fsd, esd, batch, e = _engine(name, precision=precision)
     gold = load_golden(name)
@@ -218,10 +225,7 @@ def test_inner_loop_paconv_matches_reference_golden(name, precision):
     loss, lp, bpd = e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV),
                                   None if extra is None else extra.to(DEV)), eps=batch["eps"].to(DEV))
     d = (lp.cpu() - gold["log_prob"]).abs()
-    print(name, precision, "max", d.max().item(), "median", d.median().item())
-    full = name.startswith("full")
-    assert d.median().item() < 1e-3
-    assert d.max().item() < (5e-3 if full else 1e-3)   # full depth: fp32-noise note in the module docstring
+    assert d.max().item() < 1e-3
     assert abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
 
 
@@ -257,39 +261,92 @@ def test_inner_loop_matches_reference_golden(name):
     assert abs(bpd.item() - gold["bpd"].item()) / abs(gold["bpd"].item()) < 1e-4
 
 
-@pytest.mark.parametrize("name", ["full_dgcnn_attn", "full_dgcnn_attn_extra", "full_dgcnn_global"])
-def test_inner_loop_full_depth_matches_reference_golden(name):
-    """115 layers, B=1, the reference's CPU fp32 output.  The fp32 reference itself sits ~2e-3 nats (max)
-    from an fp64 evaluation of the same model (DESIGN.md "precision"), so the per-point bound here is
-    5e-3; the typical (median) error and the mean-nats bound keep north_star's figures."""
-    cfg, fsd, esd, batch, e = _engine(name)
-    gold = load_golden(name)
+FULL = ["full_dgcnn_attn", "full_dgcnn_attn_extra", "full_dgcnn_global", "full_paconv_attn", "full_paconv_attn_extra"]
+
+
+@functools.lru_cache(maxsize=None)
+def _run_fixture(name, precision):
+    cfg, fsd, esd, batch, e = _engine(name, precision=precision)
     extra = batch["extra_context"]
     loss, lp, bpd = e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV),
                                   None if extra is None else extra.to(DEV)), eps=batch["eps"].to(DEV))
-    d = (lp.cpu() - gold["log_prob"]).abs()
-    print(name, "max", d.max().item(), "median", d.median().item())
-    assert d.median().item() < 1e-3
-    assert d.max().item() < 5e-3
-    assert abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
+    out = (loss.item(), lp.cpu(), bpd.item())
+    e.close()
+    return out
 
 
-@pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_attn_extra", "tiny_dgcnn_global", "mid_dgcnn_attn",
-                                  "full_dgcnn_attn", "full_dgcnn_attn_extra", "full_dgcnn_global"])
-def test_inner_loop_tf32x3_tensor_core_path_matches_reference_golden(name):
-    """Same goldens through the tcgen05 3xTF32 GEMMs (precision='tf32x3')."""
-    cfg, fsd, esd, batch, e = _engine(name, precision="tf32x3")
+@pytest.mark.parametrize("name", FULL)
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp16x3"])
+def test_full_depth_within_1e3_of_fp64_truth(name, precision):
+    """115 layers, B=1.  Truth = the same model evaluated in float64 (tests/golden/<name>_fp64.pt, made by
+    oracle/make_fp64_truth.py with the port that is pinned to the live reference).  north_star's tolerance: every
+    point within 1e-3 nats of it, the mean within 1e-4 relative.  The reference's own fp32 output misses this on
+    three of the five fixtures (max 1.0e-3 .. 1.6e-3), which is why the bound is taken against the truth."""
+    truth = load_golden(name + "_fp64")["log_prob"]
     gold = load_golden(name)
-    extra = batch["extra_context"]
-    n0 = fclib.launch_count()
-    loss, lp, bpd = e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV),
-                                  None if extra is None else extra.to(DEV)), eps=batch["eps"].to(DEV))
-    d = (lp.cpu() - gold["log_prob"]).abs()
-    print(name, "tf32x3 max", d.max().item(), "median", d.median().item())
-    full = name.startswith("full")
+    loss, lp, bpd = _run_fixture(name, precision)
+    d = (lp.double() - truth).abs()
+    dref = (gold["log_prob"].double() - truth).abs()
+    print(f"{name} {precision}: |cuda-fp64| max {d.max().item():.3e} mean {d.mean().item():.3e}   "
+          f"|reference-fp64| max {dref.max().item():.3e} mean {dref.mean().item():.3e}")
+    assert d.max().item() < 1e-3
+    assert abs(-lp.double().mean().item() + truth.mean().item()) / abs(truth.mean().item()) < 1e-4
+
+
+@pytest.mark.parametrize("name", FULL)
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp16x3"])
+def test_full_depth_matches_reference_golden(name, precision):
+    """Same runs against the UNMODIFIED reference's fp32 output (tests/golden/<name>.pt): per point within 1e-3 nats plus the
+    reference's own distance from the fp64 truth at that point (its fp32 noise, up to 1.6e-3); median within 1e-3 outright;
+    loss / bpd within 1e-4 relative."""
+    truth = load_golden(name + "_fp64")["log_prob"]
+    gold = load_golden(name)
+    loss, lp, bpd = _run_fixture(name, precision)
+    d = (lp - gold["log_prob"]).abs().double()
+    dref = (gold["log_prob"].double() - truth).abs()
+    print(f"{name} {precision}: |cuda-reference| max {d.max().item():.3e} median {d.median().item():.3e}")
     assert d.median().item() < 1e-3
-    assert d.max().item() < (5e-3 if full else 1e-3)   # full depth: see the fp32-noise note above
-    assert abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
+    assert (d <= 1e-3 + dref).all()
+    assert abs(loss - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
+    assert abs(bpd - gold["bpd"].item()) / abs(gold["bpd"].item()) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_attn_extra", "tiny_dgcnn_global", "mid_dgcnn_attn"])
+@pytest.mark.parametrize("precision", ["tf32x3", "fp16x3"])
+def test_inner_loop_tensor_core_paths_match_reference_golden(name, precision):
+    """The 3- and 12-layer goldens through the tcgen05 GEMMs (3xTF32 and 3xFP16): north_star's tolerances as they stand."""
+    gold = load_golden(name)
+    loss, lp, bpd = _run_fixture(name, precision)
+    d = (lp - gold["log_prob"]).abs()
+    assert d.max().item() < 1e-3
+    assert abs(loss - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "fp16x3"])
+def test_full_depth_batch8_against_port(precision):
+    """The benchmarked regime (several pairs per launch, 115 layers) against the oracle port run on this box's CPU:
+    B = 8 pairs of the bench workload.  Per point within 1e-3 nats of the port's float64 evaluation (or within the port's
+    own fp32 noise at that point, whichever is larger); mean within 1e-4 relative."""
+    cfg = configs.get_config("dgcnn_attn")
+    dcfg = configs.derive(cfg)
+    fsd, esd = spec.random_state_dicts(cfg, seed=0)
+    B = 8
+    batch = spec.synthetic_batch(cfg, B, seed=100)
+    e = eng.FlowCompareB200((fsd, esd), cfg, device=DEV, precision=precision)
+    _, lp, _ = e.inner_loop((batch["extract_0"].to(DEV), batch["extract_1"].to(DEV), None), eps=batch["eps"].to(DEV))
+    lp = lp.cpu()
+    e.close()
+    ctx32, idxs = port.dgcnn_embed(esd, batch["extract_0"], cfg["n_neighbors"])
+    want32 = port.flow_log_prob(fsd, dcfg, batch["extract_1"], ctx32, None, batch["eps"])
+    f64, e64 = port.to_dtype(fsd, torch.float64), port.to_dtype(esd, torch.float64)
+    ctx64, _ = port.dgcnn_embed(e64, batch["extract_0"].double(), cfg["n_neighbors"], idx_list=idxs)
+    want64 = port.flow_log_prob(f64, dcfg, batch["extract_1"].double(), ctx64, None, batch["eps"].double())
+    d = (lp.double() - want64).abs()
+    dport = (want32.double() - want64).abs()
+    print(f"B=8 {precision}: |cuda-fp64| max {d.max().item():.3e} mean {d.mean().item():.3e}   |port fp32-fp64| max "
+          f"{dport.max().item():.3e} mean {dport.mean().item():.3e}")
+    assert (d <= torch.clamp(dport, min=1e-3)).all()
+    assert abs(lp.double().mean().item() - want64.mean().item()) / abs(want64.mean().item()) < 1e-4
 
 
 def test_inner_loop_host_equals_device_path():
@@ -303,7 +360,7 @@ def test_inner_loop_host_equals_device_path():
     assert dev[0].item() == host[0].item()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp16x3"])
 def test_inner_loop_deterministic_and_batch_invariant(precision):
     cfg, fsd, esd, batch, e = _engine("tiny_dgcnn_attn", precision)
     args = (batch["extract_0"].to(DEV), batch["extract_1"].to(DEV), None)
@@ -372,6 +429,15 @@ def test_change_score_matches_port(lib):
         got = eng.log_prob_to_change(lp10.to(DEV), lp00.to(DEV), 1.5, cut).cpu()
         assert (got - want).abs().max().item() < 1e-5
         assert torch.equal(got == 0, want == 0)
+
+
+def test_change_score_matches_reference_golden(lib):
+    """fc_change_score against the UNMODIFIED reference's log_prob_to_change (tests/golden/change_score.pt)."""
+    gold = load_golden("change_score")
+    for c in gold["cases"]:
+        got = eng.log_prob_to_change(c["lp10"].to(DEV), c["lp00"].to(DEV), c["multiple"], c["hard_cutoff"]).cpu()
+        assert torch.equal(got == 0, c["change"] == 0)
+        assert (got - c["change"]).abs().max().item() < 1e-5
 
 
 def test_fill_normal_statistics(lib):

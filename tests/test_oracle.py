@@ -243,3 +243,33 @@ def test_change_score_port_properties():
     lp10[0, 3] = float("-inf")
     ch = port.log_prob_to_change(lp10, lp00, 1.0)
     assert ch.min() >= 0 and ch.max() <= 1 and torch.isfinite(ch).all()
+
+
+# ----------------------------------------------------------------------------- change score
+def test_port_change_score_matches_reference_golden():
+    """oracle/port.py: log_prob_to_change against the UNMODIFIED reference's outputs (tests/golden/change_score.pt, made by
+    oracle/make_change_golden.py from test_flow.py:241-275), incl. -inf clamping over the whole tensor and both masks."""
+    gold = load_golden("change_score")
+    assert len(gold["cases"]) == 9
+    for c in gold["cases"]:
+        got = port.log_prob_to_change(c["lp10"].clone(), c["lp00"].clone(), c["multiple"], c["hard_cutoff"])
+        assert torch.equal(got == 0, c["change"] == 0)
+        assert (got - c["change"]).abs().max().item() < 1e-6
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_port_change_score_matches_live_reference():
+    tf = refload.load_test_flow()
+    g = torch.Generator().manual_seed(77)
+    lp10 = torch.randn(5, 300, generator=g) * 4 - 20
+    lp00 = torch.randn(5, 300, generator=g) - 11
+    lp10[2, 17] = float("-inf")
+    lp00[0, 3] = float("-inf")
+    for multiple, cut in ((5.4, None), (2.0, -21.0)):
+        want = tf.log_prob_to_change(lp10.clone(), lp00.clone(), multiple, cut)
+        got = port.log_prob_to_change(lp10.clone(), lp00.clone(), multiple, cut)
+        assert torch.equal(got == 0, want == 0) and (got - want).abs().max().item() < 1e-6
+    # the reference clamps its ARGUMENTS in place (clamp_infs mutates); the port (and fc_change_score) do not
+    a = lp10.clone()
+    tf.log_prob_to_change(a, lp00.clone(), 5.4)
+    assert not torch.isinf(a).any() and torch.isinf(lp10).any()
