@@ -1,6 +1,6 @@
 # Builds the C-ABI library (sm_100a only) and the C oracle.
 NVCC ?= nvcc
-NVFLAGS = -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
+NVFLAGS = -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -diag-suppress 177 -Wno-deprecated-gpu-targets
 CSRC = $(wildcard flowcompare_b200/csrc/*.cu)
 OBJS = $(patsubst flowcompare_b200/csrc/%.cu,build/%.o,$(CSRC))
 LIB = flowcompare_b200/libflowcompare_b200.so

@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="dgcnn_attn")
     ap.add_argument("--batch", type=int, default=128, help="cloud pairs per step per GPU")
-    ap.add_argument("--precision", default=os.environ.get("FC_PRECISION", "auto"), choices=["auto", "fp32", "tf32x3"])
+    ap.add_argument("--precision", default=os.environ.get("FC_PRECISION", "auto"), choices=["auto", "fp32", "tf32x3", "fp16x3"])
     ap.add_argument("--cpu-pairs", type=int, default=6, help="pairs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true", help="profiling run: 1 warm-up, timed steps only (not a bench value)")
@@ -329,7 +329,7 @@ def main():
     # live precision evidence: the timed path (3xTF32 on the tensor cores) against the exact-fp32 FFMA path of the same
     # library on 2 pairs of this step's batch (both are parity-tested at full depth against the reference's goldens)
     precision_check = None
-    if rank == 0 and precision == "tf32x3" and not args.ncu:
+    if rank == 0 and precision != "fp32" and not args.ncu:
         fsd, esd = spec.random_state_dicts(cfg, seed=0)
         eng32 = engine.FlowCompareB200((fsd, esd), cfg, device=dev, precision="fp32")
         del fsd, esd
@@ -354,7 +354,7 @@ def main():
     if rank == 0:
         out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "tf32x3(f32-faithful)",
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else precision + "(f32-faithful)",
                "data": "synthetic", "config": workload_config(args, cfg, B, "B200"),
                "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "matches_device_resident_result": same},

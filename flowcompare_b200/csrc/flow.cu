@@ -316,9 +316,9 @@ static int run_attention_block(const fc_flow* f, const FcMlp& pre, const FcAttn&
     return fc_launch_cross_attention(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
 }
 
-extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* context, const float* extra,
-                                const float* eps, float* log_prob_out, int B, int N, int Nc, void* workspace,
-                                int64_t workspace_bytes, int precision, fc_stream_t stream_) {
+static int flow_forward(const fc_flow* f, const float* x, const float* context, const float* extra, const float* eps,
+                        float* log_prob_out, float* z_out, int B, int N, int Nc, void* workspace, int64_t workspace_bytes,
+                        int precision, fc_stream_t stream_) {
     FC_REQUIRE(f && x && context && eps && log_prob_out && B > 0 && N > 0 && Nc > 0);
     FC_REQUIRE((f->extra != 0) == (extra != nullptr));
     FC_REQUIRE((int64_t)B * N < (1ll << 31) && (int64_t)B * Nc < (1ll << 31));
@@ -412,5 +412,112 @@ extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* c
         fc_count_launch();
         FC_LAUNCH_OK();
     }
+    if (z_out) {   // the final latent, [B*N, D] contiguous
+        const long long tot = (long long)M * f->D;
+        copy_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(lat, w.ldx, z_out, f->D, M, f->D);
+        fc_count_launch();
+        FC_LAUNCH_OK();
+    }
+    return FC_OK;
+}
+
+extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* context, const float* extra,
+                                const float* eps, float* log_prob_out, int B, int N, int Nc, void* workspace,
+                                int64_t workspace_bytes, int precision, fc_stream_t stream_) {
+    return flow_forward(f, x, context, extra, eps, log_prob_out, nullptr, B, N, Nc, workspace, workspace_bytes, precision, stream_);
+}
+
+extern "C" int fc_flow_forward(const fc_flow* f, const float* x, const float* context, const float* extra, const float* eps,
+                               float* log_prob_out, float* z_out, int B, int N, int Nc, void* workspace, int64_t workspace_bytes,
+                               int precision, fc_stream_t stream_) {
+    FC_REQUIRE(z_out != nullptr);
+    return flow_forward(f, x, context, extra, eps, log_prob_out, z_out, B, N, Nc, workspace, workspace_bytes, precision, stream_);
+}
+
+// ------------------------------------------------------------------------------------------ inverse / sampling pass
+extern "C" int fc_flow_set_inverse(fc_flow* f, const int32_t* header, int n_header, const int64_t* table, int n_table,
+                                   const float* arena, int64_t arena_floats) {
+    FC_REQUIRE(f && header && table && arena && n_header >= 4);
+    if (header[0] != FC_INV_MAGIC || (header[1] != FC_ARENA_VERSION && header[1] != FC_ARENA_VERSION_F16)) return FC_ERR_MODEL;
+    if (header[2] != f->L || header[3] != f->D || (reinterpret_cast<uintptr_t>(arena) & 15)) return FC_ERR_MODEL;
+    FcCursor c{table, n_table, 0, arena, arena_floats, true};
+    c.tc_fmt = header[1] == FC_ARENA_VERSION_F16 ? 1 : 0;
+    for (int l = 0; l < f->L; ++l) {
+        FcFlowLayer& y = f->layers[l];
+        if (!y.has_lu) continue;
+        y.lu_inv = c.linear(f->D, 0, f->D);
+        y.lu_inv_diag = c.ptr(c.next(), f->D);
+        if (!y.lu_inv_diag) c.ok = false;
+    }
+    if (!c.ok || c.pos != n_table) return FC_ERR_MODEL;
+    f->has_inverse = true;
+    return FC_OK;
+}
+
+// `Flow.sample` after the base draw (reference models/transform.py:79-84): the transform list walked backwards with each
+// `.inverse` -- LinearLU (models/permuters.py:171-177) and ActNorm (models/act_norm.py:45-46) as ONE folded GEMM
+// z = Wp^-1 z' + shift (packing.fold_inverse_actnorm_lu), the affine coupling's inverse x2 = (y2 - t)/s
+// (models/affine_coupling.py:48-62) in the epilogue of its conditioner's last GEMM, the conditioner itself exactly as in the
+// forward pass (it reads the untouched half y1); the augmenter's inverse keeps the first input_dim columns
+// (models/augmenter.py:20-21,65-67).  z: [B, P, D] base draw, x_out: [B, P, d_in].
+extern "C" int fc_flow_sample(const fc_flow* f, const float* z, const float* context, const float* extra, float* x_out, int B,
+                              int P, int Nc, void* workspace, int64_t workspace_bytes, int precision, fc_stream_t stream_) {
+    FC_REQUIRE(f && z && context && x_out && B > 0 && P > 0 && Nc > 0);
+    FC_REQUIRE((f->extra != 0) == (extra != nullptr));
+    FC_REQUIRE((int64_t)B * P < (1ll << 31) && (int64_t)B * Nc < (1ll << 31));
+    if (!f->has_inverse) return FC_ERR_MODEL;
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return FC_ERR_WORKSPACE;
+    FlowWs w = carve_flow_ws(f, B, P, Nc, workspace);
+    if (w.total_bytes > workspace_bytes) return FC_ERR_WORKSPACE;
+    const int M = B * P;
+    int rc;
+    {
+        const long long tot = (long long)M * f->D;
+        copy_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(z, f->D, w.lat0, w.ldx, M, f->D);
+        fc_count_launch();
+        FC_LAUNCH_OK();
+    }
+    if (f->has_cb) {
+        const int tot = B * w.cbA_ld;
+        build_cb_input_kernel<<<(tot + 255) / 256, 256, 0, s>>>(extra, context, f->E, f->extra, f->is_global, B, w.cbA_ld, w.cbA);
+        fc_count_launch();
+        FC_LAUNCH_OK();
+        rc = gemm_plain(f->cb, w.cbA, w.cbA_ld, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, w.cb, w.cb_ld, B, 0, s);
+        if (rc) return rc;
+    }
+    auto cb_ptr = [&](int slot) -> const float* { return f->has_cb ? w.cb + (size_t)slot * f->hid : nullptr; };
+    float* lat = w.lat0; float* lat_next = w.lat1;
+    for (int l = f->L - 1; l >= 0; --l) {
+        const FcFlowLayer& y = f->layers[l];
+        if (y.has_lu) {
+            GemmArgs g = fc_gemm_args_zero();
+            g.A1 = lat; g.lda1 = w.ldx; g.K1 = y.lu_inv.K1; g.Wt = y.lu_inv.w; g.ldw = y.lu_inv.ldw; g.Whi = y.lu_inv.whi; g.Wlo = y.lu_inv.wlo;
+            g.ldk = y.lu_inv.ldk; g.tc_fmt = y.lu_inv.tc_fmt; g.bias = y.lu_inv.b; g.res = lat; g.ldres = w.ldx; g.res_scale = y.lu_inv_diag;
+            g.C = lat_next; g.ldc = w.ldx; g.M = M; g.N = y.lu_inv.N; g.precision = precision;
+            rc = fc_launch_gemm(g, s);
+            if (rc) return rc;
+            float* t = lat; lat = lat_next; lat_next = t;
+        }
+        if (!f->is_global) {
+            rc = run_attention_block(f, y.pre, y.attn, lat, w.ldx, f->half, context, B, P, Nc, w, precision, s);
+            if (rc) return rc;
+        }
+        FcMlpIn in{lat, w.ldx, f->is_global ? nullptr : w.o, 64, cb_ptr(l + 1), w.cb_ld, P};
+        if (!f->has_cb) { in.bias = nullptr; in.bias_ld = 0; in.bias_group = 0; }
+        float* last = nullptr;
+        rc = fc_run_mlp_hidden(y.cpl, in, M, w.hA, w.hB, w.ldh, precision, s, &last);
+        if (rc) return rc;
+        GemmArgs g = fc_gemm_args_zero();
+        g.A1 = last; g.lda1 = w.ldh; g.K1 = f->hid; g.Wt = y.cpl.out.w; g.ldw = y.cpl.out.ldw; g.bias = y.cpl.out.b; g.Whi = y.cpl.out.whi; g.Wlo = y.cpl.out.wlo;
+        g.ldk = y.cpl.out.ldk; g.tc_fmt = y.cpl.out.tc_fmt; g.M = M; g.N = y.cpl.out.N; g.epi = FC_EPI_COUPLING_INV; g.x = lat; g.ldx = w.ldx; g.col0 = f->half;
+        g.precision = precision;
+        rc = fc_launch_gemm(g, s);
+        if (rc) return rc;
+    }
+    const long long tot = (long long)M * f->d_in;
+    copy_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(lat, w.ldx, x_out, f->d_in, M, f->d_in);
+    fc_count_launch();
+    FC_LAUNCH_OK();
     return FC_OK;
 }

@@ -191,6 +191,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_ffma_kernel(const GemmArgs a
                         ldj += logf(s);
                     }
                 }
+            } else if (epi == FC_EPI_COUPLING_INV) {
+                // reference models/affine_coupling.py:48-62: x2 = (y2 - t) / s with the same sigmoid scale
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    if (col + 2 * p + 1 < a.N) {
+                        const int j = (col >> 1) + p;
+                        const float sraw = v[2 * p], tt = v[2 * p + 1];
+                        const float sig = 1.0f / (1.0f + expf(-sraw));
+                        const float s = (2.0f * sig - 1.0f) + 1.0f;
+                        float* xp = a.x + (size_t)row * a.ldx + a.col0 + j;
+                        *xp = (*xp - tt) / s;
+                    }
+                }
             } else if (epi == FC_EPI_AUGMENT) {
                 // reference models/distributions.py:128-153 + models/augmenter.py:49-63
 #pragma unroll
@@ -244,6 +257,7 @@ int fc_launch_gemm_ffma(const GemmArgs& a, cudaStream_t stream) {
     if (a.epi == FC_EPI_STORE || a.epi == FC_EPI_LNQ) FC_REQUIRE(a.C != nullptr);
     if (a.epi == FC_EPI_LNQ) FC_REQUIRE(a.row_mu && a.row_rstd && a.csum && a.bias && a.bias_group == 0);
     if (a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) FC_REQUIRE(a.x && a.part && (a.N % 4) == 0);
+    if (a.epi == FC_EPI_COUPLING_INV) FC_REQUIRE(a.x && (a.N % 4) == 0);
     if (a.epi == FC_EPI_AUGMENT) FC_REQUIRE(a.eps != nullptr);
     if (a.N <= 64) return launch<64>(a, stream);
     return launch<128>(a, stream);

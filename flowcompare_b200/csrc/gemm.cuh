@@ -15,6 +15,7 @@ enum {
     FC_EPI_AUGMENT = 3,   // augment: columns interleaved (mean_j, log_std_j); z2 written; ldj partial
     FC_EPI_KVSPLIT = 4,   // to_kv for the tcgen05 attention (N = 128): k -> TF32 hi/lo [M][64]; v -> hi/lo TRANSPOSED
                           // per cloud [B][64][kv_ncp]  (tcgen05 path only)
+    FC_EPI_COUPLING_INV = 5,  // inverse affine coupling (sampling pass): x2 = (y2 - t) / s in place, no log-det
 };
 
 struct GemmArgs {

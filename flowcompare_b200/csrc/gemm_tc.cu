@@ -59,7 +59,33 @@ constexpr int TC_STAGES = 5;                   // shared-memory stages: a load i
 #ifndef TC_STAGES_F16
 #define TC_STAGES_F16 7                        // 3xFP16 mode: a stage is 16 KB of A + 2 x 6 KB of W, tensor time per k-block is halved
 #endif
-constexpr int TC_THREADS = 448;                // TMA, MMA, 4 converter warps, 8 epilogue warps
+// Knock-out switches for bottleneck hunting (scripts/build_variant.sh ... "-DTC_KO_MMA=1"): the pipeline keeps its shape and
+// barrier traffic, one stage of work is skipped; the RESULTS ARE GARBAGE, only the timing is meaningful.
+#ifndef TC_KO_MMA
+#define TC_KO_MMA 0     // no tcgen05.mma (commits stay)
+#endif
+#ifndef TC_KO_CONV
+#define TC_KO_CONV 0    // converters neither read shared memory nor write tensor memory
+#endif
+#ifndef TC_KO_WTMA
+#define TC_KO_WTMA 0    // no weight loads
+#endif
+#ifndef TC_KO_ATMA
+#define TC_KO_ATMA 0    // no activation loads
+#endif
+#ifndef TC_KO_EPI
+#define TC_KO_EPI 0     // epilogue reads the accumulators but touches no global memory
+#endif
+#ifndef TC_ISSUE_KBLOCK
+#define TC_ISSUE_KBLOCK 1                      // MMA issuer: one synchronisation point per k-block (0: per half k-block)
+#endif
+#ifndef TC_CONV_WARPS
+#define TC_CONV_WARPS 8                        // 4: one converter thread per tile row; 8: two (one per half k-block; measured +10 % in 3xFP16 mode)
+#endif
+constexpr int TC_CONV_WARPS_N = TC_CONV_WARPS;
+static_assert(TC_CONV_WARPS_N == 4 || TC_CONV_WARPS_N == 8, "converter warps: 4 or 8");
+constexpr int TC_EPI_WARP0 = 2 + TC_CONV_WARPS_N;             // first epilogue warp (a multiple of 2 past a multiple of 4: TMEM quadrants line up)
+constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + 8);           // TMA, MMA, converter warps, 8 epilogue warps
 // Per operand format: F16 = false 3xTF32 (weights as fp32 TF32 hi/lo), true 3xFP16 (weights as fp16 hi / 2^11-scaled lo)
 template <bool F16> struct TcCfg {
     static constexpr int STAGES = F16 ? TC_STAGES_F16 : TC_STAGES;
@@ -152,8 +178,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     auto tile_bn_of = [&](int nt) { return 16 * (n_base + (nt < n_rem ? 1 : 0)); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], 128); mbar_init(&w_free[s], 1); }
-        for (int s = 0; s < TC_TSTAGES; ++s) { mbar_init(&conv[s], 128); mbar_init(&tfree[s], 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], 32 * TC_CONV_WARPS_N); mbar_init(&w_free[s], 1); }
+        for (int s = 0; s < TC_TSTAGES / 2; ++s) { mbar_init(&conv[s], 256); mbar_init(&tfree[s], 1); }   // one pair per K-BLOCK of A in tensor memory
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -185,11 +211,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     const uint32_t ph = (g / TC_STAGES) & 1;
                     mbar_wait(&a_free[s], ph ^ 1, 100 + t);
                     mbar_wait(&w_free[s], ph ^ 1, 150 + t);
-                    mbar_expect_tx(&full[s], (uint32_t)(TC_A_BYTES + 2 * w_bytes));
-                    if (t < p.T1) tma_load_2d(&mapA1, a_raw(s), &full[s], t * TC_BK, m0);
-                    else          tma_load_2d(&mapA2, a_raw(s), &full[s], (t - p.T1) * TC_BK, m0);
-                    tma_load_2d(&mapWhi, w_hi(s), &full[s], t * TC_BK, tile_n0);
-                    tma_load_2d(&mapWlo, w_lo(s), &full[s], t * TC_BK, tile_n0);
+                    mbar_expect_tx(&full[s], (uint32_t)((TC_KO_ATMA ? 0 : TC_A_BYTES) + (TC_KO_WTMA ? 0 : 2 * w_bytes)));
+                    if (!TC_KO_ATMA) {
+                        if (t < p.T1) tma_load_2d(&mapA1, a_raw(s), &full[s], t * TC_BK, m0);
+                        else          tma_load_2d(&mapA2, a_raw(s), &full[s], (t - p.T1) * TC_BK, m0);
+                    }
+                    if (!TC_KO_WTMA) {
+                        tma_load_2d(&mapWhi, w_hi(s), &full[s], t * TC_BK, tile_n0);
+                        tma_load_2d(&mapWlo, w_lo(s), &full[s], t * TC_BK, tile_n0);
+                    }
                 }
             }
         }
@@ -197,10 +227,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         // ===================================================== MMA issuer
         // The whole warp runs the loop and ONE ELECTED lane issues: inside a divergent `if (lane == 0)` the compiler
         // cannot keep the descriptors in uniform registers and wraps every UTCHMMA in an ELECT/vote loop with R2UR moves.
-        uint32_t g = 0, hb = 0;   // k-blocks / half k-blocks consumed so far
+        //
+        // This warp is a serial program and MMA issue blocks (the tensor queue is a couple of MMAs deep), so everything it
+        // does besides issuing is dead time for the tensor pipe.  Measured with the knock-out builds (TC_KO_*): with NO
+        // MMAs, NO loads and NO conversion the loop still took ~780 cycles per k-block -- every mbarrier check costs
+        // ~40 cycles, a commit ~30 -- against 288 tensor cycles for a 3xFP16 k-block.  Hence: ONE barrier per k-block
+        // towards the converters (conv[]; it implies full[]: the converters only publish after they have seen the stage's
+        // TMA bytes land, and the weights arrive on the same transaction barrier), one probe of the next one, two commits
+        // (tfree[], w_free[]), ring positions kept as counters (no division), and optionally TC_ISSUE_KBLOCK k-blocks per
+        // synchronisation point.
+        constexpr int KBI = (TC_TSTAGES / 2 >= 4) ? TC_ISSUE_KBLOCK : 1;   // 3xTF32 has only 2 k-blocks of A stages in tensor memory
         int it = 0;
-        long long m_full = 0, m_conv = 0, m_acc = 0;
-        bool full_seen = false, conv_seen = false;   // the next stage's barriers were seen complete by the probe
+        long long m_conv = 0, m_acc = 0, m_probe = 0, m_issue = 0;
+        bool conv_seen = false;   // the next k-block's barrier was seen complete by the probe
+        int s = 0;                // shared-memory stage of the next k-block
+        int ks = 0; uint32_t kph = 0;   // tensor-memory A stage (one per k-block) of the next k-block and its barrier phase
         TC_T(m_t0);
         for (int L = blockIdx.x; L < total_tiles; L += gridDim.x, ++it) {
             const int n_tile = L % n_tiles;
@@ -214,52 +255,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             mbar_wait(&acc_free[buf], ((it >> 1) & 1) ^ 1, 190);     // the epilogue of tile it-2 has drained this buffer
             TC_T(ma1);
             TC_ACC(m_acc, ma0, ma1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int t = 0; t < T; ++t, ++g) {
-                const int s = g % TC_STAGES;
-                TC_T(mf0);
-                if (!full_seen) mbar_wait(&full[s], (g / TC_STAGES) & 1, 200 + t);
-                TC_T(mf1);
-                TC_ACC(m_full, mf0, mf1);
-                full_seen = false;
-                const uint64_t dbh = F16 ? make_kmajor_sw64_desc(smem_u32(w_hi(s))) : make_kmajor_sw128_desc(smem_u32(w_hi(s)));
-                const uint64_t dbl = F16 ? make_kmajor_sw64_desc(smem_u32(w_lo(s))) : make_kmajor_sw128_desc(smem_u32(w_lo(s)));
-                // the A operand arrives in TMEM in HALF k-blocks (16 k: 16 columns hi + 16 lo per stage)
+            for (int t = 0; t < T;) {
+                const int nb = min(KBI, T - t);
+                TC_T(mc0);
+                if (!conv_seen) mbar_wait(&conv[ks], kph, 300 + t);
+                if (nb > 1) { const int k2 = ks + 1 == TC_TSTAGES / 2 ? 0 : ks + 1; mbar_wait(&conv[k2], k2 ? kph : kph ^ 1, 350 + t); }
+                TC_T(mc1);
+                TC_ACC(m_conv, mc0, mc1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                {   // probe the NEXT group's first k-block now: a wait after the issue is dead time for the tensor pipe
+                    int kn = ks + nb; uint32_t pn = kph;
+                    if (kn >= TC_TSTAGES / 2) { kn -= TC_TSTAGES / 2; pn ^= 1; }
+                    conv_seen = mbar_test(&conv[kn], pn);
+                }
+                TC_T(mp1);
+                TC_ACC(m_probe, mc1, mp1);
+                if (elect_one()) {
+                    int sj = s, kj = ks;
+                    for (int j = 0; j < nb; ++j) {
+                        const uint64_t dbh = F16 ? make_kmajor_sw64_desc(smem_u32(w_hi(sj))) : make_kmajor_sw128_desc(smem_u32(w_hi(sj)));
+                        const uint64_t dbl = F16 ? make_kmajor_sw64_desc(smem_u32(w_lo(sj))) : make_kmajor_sw128_desc(smem_u32(w_lo(sj)));
+                        const int tt = t + j;
 #pragma unroll
-                for (int h = 0; h < 2; ++h, ++hb) {
-                    const int ts = hb % TC_TSTAGES;
-                    TC_T(mc0);
-                    if (!conv_seen) mbar_wait(&conv[ts], (hb / TC_TSTAGES) & 1, 300 + t);
-                    TC_T(mc1);
-                    TC_ACC(m_conv, mc0, mc1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    // Issuing blocks while the tensor queue is full, and a wait after it is dead time for the tensor
-                    // pipe: probe the NEXT half's barriers now (the converters run ahead, so they have usually fired).
-                    conv_seen = mbar_test(&conv[(hb + 1) % TC_TSTAGES], ((hb + 1) / TC_TSTAGES) & 1);
-                    if (h == 1) full_seen = mbar_test(&full[(g + 1) % TC_STAGES], ((g + 1) / TC_STAGES) & 1);
-                    const uint32_t t_hi = tmem + TC_COL_A + TS_COLS * ts, t_lo = t_hi + TS_COLS / 2;
-                    if (elect_one()) {
-                        if (F16) {
-                            // one kind::f16 MMA covers the half k-block (16 k = 32 bytes of the 64-byte weight row)
-                            const uint64_t adv = (uint64_t)(h * 32 >> 4);
-                            umma_f16_ts(d_corr, t_lo, dbh + adv, idesc, (t | h) != 0);   // (A - Ahi) 2^11 . Whi
-                            umma_f16_ts(d_corr, t_hi, dbl + adv, idesc, 1);              // Ahi . (W - Whi) 2^11
-                            umma_f16_ts(d_main, t_hi, dbh + adv, idesc, (t | h) != 0);
-                        } else {
+                        for (int h = 0; h < 2; ++h) {
+                            // the k-block's A operand: two half k-blocks of TS_COLS columns each (first half hi, second half lo)
+                            const uint32_t t_hi = tmem + TC_COL_A + TS_COLS * (2 * kj + h), t_lo = t_hi + TS_COLS / 2;
+                            if (F16) {
+                                // one kind::f16 MMA covers the half k-block (16 k = 32 bytes of the 64-byte weight row)
+                                const uint64_t adv = (uint64_t)(h * 32 >> 4);
+                                umma_f16_ts(d_corr, t_lo, dbh + adv, idesc, (tt | h) != 0);   // (A - Ahi) 2^11 . Whi
+                                umma_f16_ts(d_corr, t_hi, dbl + adv, idesc, 1);               // Ahi . (W - Whi) 2^11
+                                umma_f16_ts(d_main, t_hi, dbh + adv, idesc, (tt | h) != 0);
+                            } else {
 #pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) {
-                                const int k = 2 * h + kk;
-                                const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
-                                umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (t | k) != 0);
-                                umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
-                                umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                                for (int kk = 0; kk < 2; ++kk) {
+                                    const int k = 2 * h + kk;
+                                    const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
+                                    umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (tt | k) != 0);
+                                    umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
+                                    umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (tt | k) != 0);
+                                }
                             }
                         }
-                        umma_commit(&tfree[ts]);                 // TMEM A stage reusable once these MMAs retire
-                        if (h == 1) umma_commit(&w_free[s]);     // W smem stage reusable once these MMAs retire
+                        umma_commit(&tfree[kj]);                     // TMEM A stage reusable once these MMAs retire
+                        umma_commit(&w_free[sj]);                    // W smem stage reusable once these MMAs retire
+                        sj = sj + 1 == TC_STAGES ? 0 : sj + 1;
+                        kj = kj + 1 == TC_TSTAGES / 2 ? 0 : kj + 1;
                     }
-                    __syncwarp();
                 }
+                TC_T(mi1);
+                TC_ACC(m_issue, mp1, mi1);
+                __syncwarp();
+                t += nb;
+                s += nb; if (s >= TC_STAGES) s -= TC_STAGES;
+                ks += nb; if (ks >= TC_TSTAGES / 2) { ks -= TC_TSTAGES / 2; kph ^= 1; }
             }
             if (elect_one()) umma_commit(&acc_full[buf]);        // accumulators of this tile complete
             __syncwarp();
@@ -267,24 +316,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
 #if TC_PHASE_TIMERS
         if (lane == 0) {
             atomicAdd(&fc_tc_dbg[0], 1ull); atomicAdd(&fc_tc_dbg[1], (unsigned long long)(clock64() - m_t0));
-            atomicAdd(&fc_tc_dbg[2], (unsigned long long)m_full); atomicAdd(&fc_tc_dbg[3], (unsigned long long)m_conv);
-            atomicAdd(&fc_tc_dbg[4], (unsigned long long)m_acc);
+            atomicAdd(&fc_tc_dbg[3], (unsigned long long)m_conv); atomicAdd(&fc_tc_dbg[4], (unsigned long long)m_acc);
+            atomicAdd(&fc_tc_dbg[10], (unsigned long long)m_probe); atomicAdd(&fc_tc_dbg[11], (unsigned long long)m_issue);
         }
 #endif
-    } else if (warp < 6) {
+    } else if (warp < TC_EPI_WARP0) {
         // ===================================================== converters: fp32 smem row -> (hi, lo) in TMEM
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
         const int row_in_tile = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        // Software pipelined by one half k-block: the tcgen05.st of half h is in flight while half h+1 is loaded and
-        // split; only then is it awaited and published (conv[]), so the store latency is off the critical path.
-        uint32_t g = 0, hb = 0;
-        int pending = -1;        // TMEM stage whose store has been issued but not yet published
+        const int my_half = (warp - 2) >> 2;         // 8 converter warps: warps 2-5 take the first half of every k-block, 6-9 the second
+        // Software pipelined by one half k-block: the tcgen05.st of a half is in flight while the next one is loaded and
+        // split; only then is it awaited and published (one arrival per thread and half on the k-block's conv[] barrier,
+        // 256 arrivals per k-block with 4 or 8 converter warps), so the store latency is off the critical path.
+        int s = 0; uint32_t sph = 0;   // shared-memory stage / phase of the current k-block
+        int ks = 0; uint32_t kph = 0;  // tensor-memory A stage (one per k-block) / phase
+        int pending = -1;              // k-block stage whose store has been issued but not yet published
         long long c_full = 0, c_tfree = 0;
         TC_T(c_t0);
         for (int L = blockIdx.x; L < total_tiles; L += gridDim.x) {
-            for (int t = 0; t < T; ++t, ++g) {
-                const int s = g % TC_STAGES;
+            for (int t = 0; t < T; ++t) {
                 if (pending >= 0) {      // never hold a finished stage back while waiting for the next k-block's data
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -292,15 +343,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     pending = -1;
                 }
                 TC_T(cf0);
-                mbar_wait(&full[s], (g / TC_STAGES) & 1, 400 + t);
+                mbar_wait(&full[s], sph, 400 + t);
                 TC_T(cf1);
                 TC_ACC(c_full, cf0, cf1);
                 const float4* rowp = reinterpret_cast<const float4*>(a_raw(s) + row_in_tile * 128);
 #pragma unroll
-                for (int h = 0; h < 2; ++h, ++hb) {
-                    uint32_t hl[TS_COLS];   // this half k-block: first half hi, second half lo  -> one TMEM stage
+                for (int h = 0; h < 2; ++h) {
+                    if (TC_CONV_WARPS_N == 8 && h != my_half) continue;   // two threads per row: each converts its own half k-block
+                    uint32_t hl[TS_COLS];   // this half k-block: first half hi, second half lo
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
+                    for (int jj = 0; jj < (TC_KO_CONV ? 0 : 4); ++jj) {
                         // 128B swizzle: logical 16-byte chunk j of row r sits at physical chunk j ^ (r & 7); a quarter
                         // warp (8 consecutive rows) therefore hits all 32 banks exactly once
                         const int j = 4 * h + jj;
@@ -329,22 +381,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                             }
                         }
                     }
-                    if (h == 1) mbar_arrive(&a_free[s]);   // whole row is in registers: the A smem stage may be refilled
+                    if (h == 1 || TC_CONV_WARPS_N == 8) mbar_arrive(&a_free[s]);   // this thread's part of the row is in registers: the A smem stage may be refilled
                     if (pending >= 0) {
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         mbar_arrive(&conv[pending]);
                     }
-                    const int ts = hb % TC_TSTAGES;
-                    TC_T(ct0);
-                    mbar_wait(&tfree[ts], ((hb / TC_TSTAGES) & 1) ^ 1, 450 + t);
-                    TC_T(ct1);
-                    TC_ACC(c_tfree, ct0, ct1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if constexpr (F16) tmem_st16(tmem + lane_addr + TC_COL_A + TS_COLS * ts, hl);
-                    else tmem_st32(tmem + lane_addr + TC_COL_A + TS_COLS * ts, hl);
-                    pending = ts;
+                    if (h == 0 || TC_CONV_WARPS_N == 8) {   // once per k-block: the MMAs that read this TMEM stage have retired
+                        TC_T(ct0);
+                        mbar_wait(&tfree[ks], kph ^ 1, 450 + t);
+                        TC_T(ct1);
+                        TC_ACC(c_tfree, ct0, ct1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    const uint32_t dst = tmem + lane_addr + TC_COL_A + TS_COLS * (2 * ks + h);
+                    if constexpr (TC_KO_CONV) { (void)hl; (void)dst; }
+                    else if constexpr (F16) tmem_st16(dst, hl);
+                    else tmem_st32(dst, hl);
+                    pending = ks;
                 }
+                s = s + 1 == TC_STAGES ? 0 : s + 1; if (s == 0) sph ^= 1;
+                ks = ks + 1 == TC_TSTAGES / 2 ? 0 : ks + 1; if (ks == 0) kph ^= 1;
             }
         }
         if (pending >= 0) {
@@ -364,9 +421,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         const int quad = warp & 3;
         const int row_in_tile = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const int ew = warp - 6;                     // 0..7
+        const int ew = warp - TC_EPI_WARP0;          // 0..7
         const int half = ew >> 2;
-        const int etid = threadIdx.x - 192;          // 0..255
+        const int etid = threadIdx.x - 32 * TC_EPI_WARP0;   // 0..255
         const GemmArgs& a = p.g;
         // per-warp staging tile [32 rows][16 + 4 pad] (rows 16-byte aligned; a thread's own-row float4 accesses are
         // conflict free, the transposed ones 2-way at worst)
@@ -428,6 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 }
                 const int col = n0 + c0;
                 if (col >= a.N) continue;                     // warp-uniform
+                if (TC_KO_EPI) { if (v[0] == 123.456f) a.C[0] = v[1]; continue; }
                 if (EPI == FC_EPI_LNQ) {
     #pragma unroll
                     for (int j = 0; j < 16; ++j)
@@ -605,6 +663,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                             }
                         }
                     }
+                } else if (EPI == FC_EPI_COUPLING_INV) {
+                    // reference models/affine_coupling.py:48-62 (sampling pass): x2 = (y2 - t) / s
+    #pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (col + 2 * q + 1 < a.N) {
+                            const float sig = 1.0f / (1.0f + expf(-v[2 * q]));
+                            const float sc = (2.0f * sig - 1.0f) + 1.0f;
+                            float* xp = a.x + (size_t)row * a.ldx + a.col0 + (col >> 1) + q;
+                            *xp = (*xp - v[2 * q + 1]) / sc;
+                        }
+                    }
                 } else if (EPI == FC_EPI_AUGMENT) {
                     // reference models/distributions.py:128-153 + models/augmenter.py:49-63
     #pragma unroll
@@ -633,7 +702,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             mbar_arrive(&acc_free[buf]);
         }
 #if TC_PHASE_TIMERS
-        if (threadIdx.x == 192) {
+        if (threadIdx.x == 32 * TC_EPI_WARP0) {
             atomicAdd(&fc_tc_dbg[8], (unsigned long long)(clock64() - e_t0)); atomicAdd(&fc_tc_dbg[9], (unsigned long long)e_wait);
         }
 #endif
@@ -743,6 +812,7 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     if (a.epi == FC_EPI_STORE || a.epi == FC_EPI_LNQ) FC_REQUIRE(a.C != nullptr);
     if (a.epi == FC_EPI_LNQ) FC_REQUIRE(a.row_mu && a.row_rstd && a.csum && a.bias && a.bias_group == 0);
     if (a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) FC_REQUIRE(a.x && a.part && (a.N % 4) == 0);
+    if (a.epi == FC_EPI_COUPLING_INV) FC_REQUIRE(a.x && (a.N % 4) == 0);
     if (a.epi == FC_EPI_KVSPLIT)
         FC_REQUIRE(a.N == 128 && fc_tc_bn(a.N) == 64 && a.C && a.kv_klo && a.kv_vthi && a.kv_vtlo && a.kv_nc > 0 &&
                    a.kv_ncp >= a.kv_nc && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 &&
@@ -800,6 +870,8 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
         le = launch_tc<FC_EPI_COUPLING, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
     } else if (a.epi == FC_EPI_AUGMENT) {
         le = launch_tc<FC_EPI_AUGMENT, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
+    } else if (a.epi == FC_EPI_COUPLING_INV) {
+        le = launch_tc<FC_EPI_COUPLING_INV, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
     } else if (a.epi == FC_EPI_KVSPLIT && a.act == FC_ACT_NONE && !res) {
         le = launch_tc<FC_EPI_KVSPLIT, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
     } else {

@@ -8,6 +8,7 @@
 constexpr int FC_MAX_HIDDEN = 8;
 constexpr int32_t FC_FLOW_MAGIC = 0x46435F46;  // 'FC_F'
 constexpr int32_t FC_EMB_MAGIC = 0x46435F45;   // 'FC_E'
+constexpr int32_t FC_INV_MAGIC = 0x46435F49;   // 'FC_I': inverse ActNorm+LinearLU matrices of the sampling pass
 constexpr int32_t FC_ARENA_VERSION = 2;        // tensor-core weight copies: TF32 hi/lo (fp32 storage)
 constexpr int32_t FC_ARENA_VERSION_F16 = 3;    // tensor-core weight copies: fp16 hi / scaled lo
 
@@ -40,6 +41,9 @@ struct FcFlowLayer {
     FcLinear lu;    // folded ActNorm + LinearLU minus its diagonal (absent on the last layer)
     const float* lu_diag = nullptr;  // [D] the diagonal, applied to the latent in the GEMM epilogue
     bool has_lu = false;
+    // sampling pass (fc_flow_set_inverse): (ActNorm + LinearLU)^-1 = Wp^-1 z' + shift, same diagonal / off-diagonal split
+    FcLinear lu_inv;
+    const float* lu_inv_diag = nullptr;
 };
 
 struct fc_flow {
@@ -54,6 +58,7 @@ struct fc_flow {
     FcFlowLayer* layers = nullptr;
     const float* arena = nullptr;
     int64_t arena_floats = 0;
+    bool has_inverse = false;    // fc_flow_set_inverse was called (needed by fc_flow_sample)
 };
 
 struct FcEdgeConv { FcLinear pq; int Cin, Cout; };

@@ -49,88 +49,140 @@ __global__ void split_points_kernel(const float* __restrict__ pts, int d_in, lon
     for (int c = 3; c < d_in; ++c) feat[i * ldf + c - 3] = p[c];
 }
 
-// K2: one CTA per cloud, block = 2^floor(log2 n) threads (<= 1024) like the reference launcher.  Running minimum
-// distance in `temp`, block arg-max: within a thread the first maximum of its strided scan, across threads the
-// lower thread id (strict > in the tree), start index 0.
-__global__ void fps_kernel(const float* __restrict__ xyz, int n, int m, float* __restrict__ temp, int32_t* __restrict__ idx,
-                           float* __restrict__ new_xyz) {
+// K2, furthest point sampling.  The algorithm is sequential in the number of samples (each pick depends on the last), so
+// the kernel is latency bound: what matters is the length of ONE iteration.  One CTA per cloud; every thread keeps its
+// points AND their running minimum distances in registers (PT points per thread), the cloud's coordinates sit in shared
+// memory for the broadcast read of the last pick, and the block arg-max is two warp-shuffle reductions around ONE barrier
+// (double-buffered partials) -- the reference design (lib/pointops/src/sampling/sampling_cuda_kernel.cu:58-168) re-reads
+// xyz and `temp` from global memory every iteration and walks a 10-level shared-memory tree with a barrier per level.
+// Tie rule (needed for bit-exact indices on clouds with duplicate points; checked against the reference's compiled
+// kernel, tests/test_pointops_gpu.py): the reference scans point k in thread k % block of ITS launch (block = 2^floor(log2 n)
+// <= 1024 threads; first maximum within a thread) and then walks a halving tree in which slot s meets slot s + h and the
+// LOWER slot keeps ties.  Two equal candidates therefore meet at the lowest bit in which their thread ids differ and the
+// one with a 0 there wins: the order is the BIT-REVERSED thread id, then the index within the thread.  That key is carried
+// through the reduction, so the result does not depend on this kernel's own block size.  log2bs < 0: lowest index wins.
+template <int PT>
+__global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ xyz, int n, int m, int log2bs,
+                                                   int32_t* __restrict__ idx, float* __restrict__ new_xyz, int xyz_in_smem) {
     extern __shared__ float fps_sm[];
-    float* dv = fps_sm;
-    int* di = reinterpret_cast<int*>(fps_sm + blockDim.x);
-    const int b = blockIdx.x, tid = threadIdx.x, bs = blockDim.x;
+    __shared__ unsigned long long part[2][32];
+    const int b = blockIdx.x, tid = threadIdx.x, bs = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = bs >> 5;
     const float* x = xyz + (size_t)b * n * 3;
-    float* t = temp + (size_t)b * n;
-    for (int k = tid; k < n; k += bs) t[k] = 1e10f;
-    int old = 0;
+    float px[PT], py[PT], pz[PT], dist[PT];
+    unsigned prio[PT];
+    const unsigned bs_ref = log2bs >= 0 ? 1u << log2bs : 0u;
+    const unsigned R = log2bs >= 0 ? ((unsigned)n + bs_ref - 1) >> log2bs : 1u;   // points per reference thread
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+        const int k = tid + i * bs;
+        px[i] = py[i] = pz[i] = 0.f; dist[i] = 1e10f; prio[i] = 0xffffffffu;
+        if (k < n) {
+            px[i] = x[k * 3 + 0]; py[i] = x[k * 3 + 1]; pz[i] = x[k * 3 + 2];
+            prio[i] = log2bs > 0 ? (__brev((unsigned)k & (bs_ref - 1)) >> (32 - log2bs)) * R + ((unsigned)k >> log2bs) : (unsigned)k;
+            if (xyz_in_smem) { fps_sm[k * 3 + 0] = px[i]; fps_sm[k * 3 + 1] = py[i]; fps_sm[k * 3 + 2] = pz[i]; }
+        }
+    }
+    const float* xs = xyz_in_smem ? fps_sm : x;
     if (tid == 0) {
         idx[(size_t)b * m] = 0;
-        new_xyz[(size_t)b * m * 3 + 0] = x[0]; new_xyz[(size_t)b * m * 3 + 1] = x[1]; new_xyz[(size_t)b * m * 3 + 2] = x[2];
+        if (new_xyz) { float* o = new_xyz + (size_t)b * m * 3; o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; }
     }
     __syncthreads();
+    int old = 0;
     for (int j = 1; j < m; ++j) {
-        const float ox = x[old * 3 + 0], oy = x[old * 3 + 1], oz = x[old * 3 + 2];
-        float best = -1.0f; int besti = 0;
-        for (int k = tid; k < n; k += bs) {
-            const float d = sqdist3(x[k * 3 + 0], x[k * 3 + 1], x[k * 3 + 2], ox, oy, oz);
-            const float d2 = fminf(d, t[k]);
-            t[k] = d2;
-            if (d2 > best) { best = d2; besti = k; }
+        const float ox = xs[old * 3 + 0], oy = xs[old * 3 + 1], oz = xs[old * 3 + 2];
+        // key = (distance bits, ~priority): distances are >= 0, so their bit patterns order like the values
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+            const float d2 = fminf(sqdist3(px[i], py[i], pz[i], ox, oy, oz), dist[i]);
+            dist[i] = d2;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(~prio[i]);
+            if (prio[i] != 0xffffffffu && key > best) best = key;
         }
-        dv[tid] = best; di[tid] = besti;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o); best = v > best ? v : best; }
+        if (lane == 0) part[j & 1][warp] = best;
         __syncthreads();
-        for (int half = bs >> 1; half >= 1; half >>= 1) {
-            if (tid < half) {
-                const float v1 = dv[tid], v2 = dv[tid + half];
-                if (v2 > v1) { dv[tid] = v2; di[tid] = di[tid + half]; }
-            }
-            __syncthreads();
-        }
-        old = di[0];
+        best = lane < nwarps ? part[j & 1][lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o); best = v > best ? v : best; }
+        const unsigned pr = ~(unsigned)best;
+        old = log2bs > 0 ? (int)(((pr % R) << log2bs) + (__brev(pr / R) >> (32 - log2bs))) : (int)pr;
         if (tid == 0) {
             idx[(size_t)b * m + j] = old;
-            float* o = new_xyz + ((size_t)b * m + j) * 3;
-            o[0] = x[old * 3 + 0]; o[1] = x[old * 3 + 1]; o[2] = x[old * 3 + 2];
+            if (new_xyz) { float* o = new_xyz + ((size_t)b * m + j) * 3; o[0] = xs[old * 3 + 0]; o[1] = xs[old * 3 + 1]; o[2] = xs[old * 3 + 2]; }
         }
-        __syncthreads();
     }
 }
 
-// K1: one thread per query.  Max-heap of the k best candidates (strict < replaces the root), heap-sorted
-// ascending at the end; slots never filled (k > n) keep index 0 -- the reference's algorithm and tie behaviour.
-__device__ __forceinline__ void heap_sift(float* d, int* ix, int size) {
+// K1, k-nearest-neighbour query: one thread per query, the reference's max-heap algorithm step for step (strict < replaces
+// the root, heap-sort at the end; slots never filled when k > n keep index 0) because the ORDER of equal-distance
+// neighbours in its output is an artefact of that heap and neighbour 0 is PAConv's centre (paconv.py:123).  What changes is
+// where things live: the reference keeps the heap in per-thread LOCAL memory (dynamically indexed best_dist[100] /
+// best_idx[100], lib/pointops/src/knnquery_heap/knnquery_heap_cuda_kernel.cu:67-68) and every thread streams the whole
+// cloud from global memory; here the heaps of a CTA's queries live in shared memory ([slot][query], padded: conflict free
+// for the sift and for the coalesced write-out) and the candidates are staged once per CTA in shared-memory tiles.
+constexpr int KH_Q = 128;      // queries per CTA
+constexpr int KH_T = 512;      // candidates per tile
+__device__ __forceinline__ void heap_sift(float* d, int* ix, int size) {   // d / ix: this query's column, stride KH_Q + 1
+    constexpr int S = KH_Q + 1;
     int root = 0;
     for (;;) {
         int child = 2 * root + 1;
         if (child >= size) return;
-        if (child + 1 < size && d[child + 1] > d[child]) ++child;
-        if (d[root] > d[child]) return;
-        const float td = d[root]; d[root] = d[child]; d[child] = td;
-        const int ti = ix[root]; ix[root] = ix[child]; ix[child] = ti;
+        if (child + 1 < size && d[(child + 1) * S] > d[child * S]) ++child;
+        const float dr = d[root * S], dc = d[child * S];
+        if (dr > dc) return;
+        d[root * S] = dc; d[child * S] = dr;
+        const int ti = ix[root * S]; ix[root * S] = ix[child * S]; ix[child * S] = ti;
         root = child;
     }
 }
-__global__ void knn_heap_kernel(const float* __restrict__ xyz, const float* __restrict__ queries, int n, int m,
-                                int32_t* __restrict__ idx) {
-    const int b = blockIdx.y;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= m) return;
+__global__ void __launch_bounds__(KH_Q) knn_heap_kernel(const float* __restrict__ xyz, const float* __restrict__ queries, int n, int m,
+                                                         int k, int32_t* __restrict__ idx, float* __restrict__ dist2) {
+    extern __shared__ float kh_sm[];
+    constexpr int S = KH_Q + 1;
+    float* hd = kh_sm;                                      // [k][S]
+    int* hi = reinterpret_cast<int*>(kh_sm + (size_t)k * S);   // [k][S]
+    float* tile = kh_sm + (size_t)2 * k * S;                // [KH_T][3]
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int q = blockIdx.x * KH_Q + tid;
     const float* x = xyz + (size_t)b * n * 3;
-    const float* c = queries + ((size_t)b * m + q) * 3;
-    const float cx = c[0], cy = c[1], cz = c[2];
-    float d[PA_K]; int ix[PA_K];
-#pragma unroll
-    for (int i = 0; i < PA_K; ++i) { d[i] = 1e10f; ix[i] = 0; }
-    for (int i = 0; i < n; ++i) {
-        const float d2 = sqdist3(cx, cy, cz, x[i * 3 + 0], x[i * 3 + 1], x[i * 3 + 2]);
-        if (d2 < d[0]) { d[0] = d2; ix[0] = i; heap_sift(d, ix, PA_K); }
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (q < m) { const float* c = queries + ((size_t)b * m + q) * 3; cx = c[0]; cy = c[1]; cz = c[2]; }
+    float* d = hd + tid; int* ix = hi + tid;
+    for (int i = 0; i < k; ++i) { d[i * S] = 1e10f; ix[i * S] = 0; }
+    for (int t0 = 0; t0 < n; t0 += KH_T) {
+        const int cnt = min(KH_T, n - t0);
+        __syncthreads();
+        for (int e = tid; e < cnt * 3; e += KH_Q) tile[e] = x[(size_t)t0 * 3 + e];
+        __syncthreads();
+        if (q < m) {
+            float root = d[0];
+            for (int i = 0; i < cnt; ++i) {
+                const float d2 = sqdist3(cx, cy, cz, tile[i * 3 + 0], tile[i * 3 + 1], tile[i * 3 + 2]);
+                if (d2 < root) { d[0] = d2; ix[0] = t0 + i; heap_sift(d, ix, k); root = d[0]; }
+            }
+        }
     }
-    for (int i = PA_K - 1; i > 0; --i) {
-        const float td = d[0]; d[0] = d[i]; d[i] = td;
-        const int ti = ix[0]; ix[0] = ix[i]; ix[i] = ti;
-        heap_sift(d, ix, i);
+    if (q < m)
+        for (int i = k - 1; i > 0; --i) {
+            const float td = d[0]; d[0] = d[i * S]; d[i * S] = td;
+            const int ti = ix[0]; ix[0] = ix[i * S]; ix[i * S] = ti;
+            heap_sift(d, ix, i);
+        }
+    __syncthreads();
+    // coalesced write-out: consecutive threads write consecutive slots of one query
+    const int q0 = blockIdx.x * KH_Q;
+    for (int e = tid; e < KH_Q * k; e += KH_Q) {
+        const int ql = e / k, sl = e % k;
+        if (q0 + ql < m) {
+            const size_t o = ((size_t)b * m + q0 + ql) * k + sl;
+            idx[o] = hi[sl * S + ql];
+            if (dist2) dist2[o] = hd[sl * S + ql];
+        }
     }
-    int32_t* o = idx + ((size_t)b * m + q) * PA_K;
-    for (int i = 0; i < PA_K; ++i) o[i] = ix[i];
 }
 
 // QueryAndGroup: edge e = (b, centre j, k).  f0[e] = [xyz[idx] - new_xyz[j] | feat[idx]]  (width 3 + C),
@@ -211,29 +263,42 @@ __global__ void max_over_k_kernel(const float* __restrict__ f, int ldf, int C, l
     out[(size_t)g * ldo + c] = m;
 }
 
-// K5 + FP weights: one thread per unknown point; strict < insertion (lower index wins ties); w = (1/(sqrt(d2)+1e-8)) / sum
-// then out[p] = [ sum_3 w * known_feat[idx] | unknown_feat[p] ]   (K6 + torch.cat, pointnet2_paconv_modules.py:225-235)
-__global__ void three_nn_kernel(const float* __restrict__ unknown, const float* __restrict__ known, int n, int m,
-                                int32_t* __restrict__ idx, float* __restrict__ w) {
+// K5 + FP weights: one thread per unknown point; strict < insertion (lower index wins ties); the known points are staged once
+// per CTA in shared memory (the reference re-reads them from global memory in every thread,
+// lib/pointops/src/interpolation/interpolation_cuda_kernel.cu:134-176).  Outputs: idx, and either the reference's squared
+// distances (op-level entry point) or the FP module's weights w = (1/(sqrt(d2)+1e-8)) / sum (pointnet2_paconv_modules.py:225-228).
+constexpr int NN_T = 1024;
+__global__ void __launch_bounds__(128) three_nn_kernel(const float* __restrict__ unknown, const float* __restrict__ known, int n, int m,
+                                                       int32_t* __restrict__ idx, float* __restrict__ w, float* __restrict__ dist2) {
+    __shared__ float tile[NN_T * 3];
     const int b = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    const float* u = unknown + ((size_t)b * n + p) * 3;
     const float* kx = known + (size_t)b * m * 3;
-    const float ux = u[0], uy = u[1], uz = u[2];
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (p < n) { const float* u = unknown + ((size_t)b * n + p) * 3; ux = u[0]; uy = u[1]; uz = u[2]; }
     double b1 = 1e40, b2 = 1e40, b3 = 1e40;
     int i1 = 0, i2 = 0, i3 = 0;
-    for (int k = 0; k < m; ++k) {
-        const float d = sqdist3(ux, uy, uz, kx[k * 3 + 0], kx[k * 3 + 1], kx[k * 3 + 2]);
-        if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
-        else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
-        else if (d < b3) { b3 = d; i3 = k; }
+    for (int t0 = 0; t0 < m; t0 += NN_T) {
+        const int cnt = min(NN_T, m - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * 3; e += blockDim.x) tile[e] = kx[(size_t)t0 * 3 + e];
+        __syncthreads();
+        for (int k = 0; k < cnt; ++k) {
+            const float d = sqdist3(ux, uy, uz, tile[k * 3 + 0], tile[k * 3 + 1], tile[k * 3 + 2]);
+            if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = t0 + k; }
+            else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = t0 + k; }
+            else if (d < b3) { b3 = d; i3 = t0 + k; }
+        }
     }
-    const float r1 = 1.0f / (sqrtf((float)b1) + 1e-8f), r2 = 1.0f / (sqrtf((float)b2) + 1e-8f), r3 = 1.0f / (sqrtf((float)b3) + 1e-8f);
-    const float norm = (r1 + r2) + r3;
+    if (p >= n) return;
     const size_t o = ((size_t)b * n + p) * 3;
     idx[o + 0] = i1; idx[o + 1] = i2; idx[o + 2] = i3;
-    w[o + 0] = r1 / norm; w[o + 1] = r2 / norm; w[o + 2] = r3 / norm;
+    if (dist2) { dist2[o + 0] = (float)b1; dist2[o + 1] = (float)b2; dist2[o + 2] = (float)b3; }
+    if (w) {
+        const float r1 = 1.0f / (sqrtf((float)b1) + 1e-8f), r2 = 1.0f / (sqrtf((float)b2) + 1e-8f), r3 = 1.0f / (sqrtf((float)b3) + 1e-8f);
+        const float norm = (r1 + r2) + r3;
+        w[o + 0] = r1 / norm; w[o + 1] = r2 / norm; w[o + 2] = r3 / norm;
+    }
 }
 __global__ void interp_concat_kernel(const float* __restrict__ known_feat, int ldk, int C2, const float* __restrict__ unk_feat,
                                      int ldu, int C1, const int32_t* __restrict__ idx, const float* __restrict__ w, int n, int m,
@@ -254,7 +319,7 @@ __global__ void interp_concat_kernel(const float* __restrict__ known_feat, int l
     out[(size_t)p * ldo + c] = v;
 }
 
-int fps_threads(int n) {
+int fps_threads(int n) {   // block size of the REFERENCE launcher (opt_n_threads, cuda_utils.h:15-18): fixes its tie order
     const int p = (int)(log((double)n) / log(2.0));
     int t = 1 << p;
     if (t > 1024) t = 1024;
@@ -262,12 +327,57 @@ int fps_threads(int n) {
     return t;
 }
 
+// tie_block: 0 = the reference launcher's rule (2^floor(log2 n) <= 1024), > 0 explicit, < 0 lowest index wins
+int launch_fps(const float* xyz, int B, int n, int m, int tie_block, int32_t* idx, float* new_xyz, cudaStream_t s) {
+    FC_REQUIRE(xyz && idx && B > 0 && n > 0 && m > 0 && m <= n && n <= 32768 && B <= 65535);
+    const int bs_ref = tie_block == 0 ? fps_threads(n) : tie_block;
+    FC_REQUIRE(tie_block < 0 || (bs_ref & (bs_ref - 1)) == 0);     // the reference's blocks are powers of two
+    int log2bs = -1;
+    if (tie_block >= 0) { log2bs = 0; while ((1 << log2bs) < bs_ref) ++log2bs; }
+    int threads = fc_round_up(n, 32);
+    if (threads > 1024) threads = 1024;
+    const int pt = (n + threads - 1) / threads;
+    const int in_smem = (size_t)n * 12 <= 40 * 1024;
+    const size_t smem = in_smem ? (size_t)n * 12 : 0;
+#define FC_FPS_CASE(P) fps_kernel<P><<<B, threads, smem, s>>>(xyz, n, m, log2bs, idx, new_xyz, in_smem)
+    if (pt <= 1) FC_FPS_CASE(1); else if (pt <= 2) FC_FPS_CASE(2); else if (pt <= 4) FC_FPS_CASE(4);
+    else if (pt <= 8) FC_FPS_CASE(8); else if (pt <= 16) FC_FPS_CASE(16); else FC_FPS_CASE(32);
+#undef FC_FPS_CASE
+    fc_count_launch(); FC_LAUNCH_OK();
+    return FC_OK;
+}
+
+int launch_knn_heap(const float* xyz, const float* queries, int B, int n, int m, int k, int32_t* idx, float* dist2, cudaStream_t s) {
+    FC_REQUIRE(xyz && queries && idx && B > 0 && n > 0 && m > 0 && k >= 1 && k <= 40 && B <= 65535);
+    const size_t smem = ((size_t)2 * k * (KH_Q + 1) + KH_T * 3) * 4;   // <= 47.4 KB at k = 40
+    knn_heap_kernel<<<dim3((m + KH_Q - 1) / KH_Q, B), KH_Q, smem, s>>>(xyz, queries, n, m, k, idx, dist2);
+    fc_count_launch(); FC_LAUNCH_OK();
+    return FC_OK;
+}
+
+int launch_three_nn(const float* unknown, const float* known, int B, int n, int m, int32_t* idx, float* w, float* dist2, cudaStream_t s) {
+    FC_REQUIRE(unknown && known && idx && B > 0 && n > 0 && m > 0 && B <= 65535);
+    three_nn_kernel<<<dim3((n + 127) / 128, B), 128, 0, s>>>(unknown, known, n, m, idx, w, dist2);
+    fc_count_launch(); FC_LAUNCH_OK();
+    return FC_OK;
+}
+
+// K4 (grouping) in point-major layout: out[b, j, kk, :] = feat[b, idx[b, j, kk], :]
+__global__ void gather_rows_kernel(const float* __restrict__ feat, int ldf, int C, const int32_t* __restrict__ idx, int n, long long rows_per_cloud,
+                                   long long total, float* __restrict__ out, int ldo) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total * C) return;
+    const long long r = i / C; const int c = (int)(i % C);
+    const long long b = r / rows_per_cloud;
+    out[(size_t)r * ldo + c] = feat[((size_t)b * n + idx[r]) * ldf + c];
+}
+
 const int SA_W[4][4] = {{0, 32, 32, 64}, {64, 64, 64, 128}, {128, 128, 128, 256}, {256, 256, 256, 512}};   // [i][0] + 3 (+c for i=0)
 const int FP_N[4] = {3, 2, 2, 2};
 const int FP_W[4][4] = {{128, 128, 128, 128}, {320, 256, 128, 0}, {384, 256, 256, 0}, {768, 256, 256, 0}};  // [0][0] + c
 
 struct PaWs {
-    float *xyz[5], *feat[5], *temp, *dxyz, *fA, *fB, *X, *fpcat, *fph, *w3, *hA, *hB;
+    float *xyz[5], *feat[5], *dxyz, *fA, *fB, *X, *fpcat, *fph, *w3, *hA, *hB;
     int32_t *fidx, *kidx, *idx3;
     int n[5], ldfeat[5];
     int64_t total;
@@ -295,7 +405,6 @@ PaWs carve_pa(const fc_embedder* e, const PaModel* pm, int B, int Nc, void* base
             max_f = fin > max_f ? fin : max_f; max_f = fout > max_f ? fout : max_f; max_x = xx > max_x ? xx : max_x;
         }
     }
-    w.temp = (float*)take((int64_t)B * Nc * 4);
     w.fidx = (int32_t*)take((int64_t)B * w.n[1] * 4);
     w.kidx = (int32_t*)take(max_edges * 4);
     w.dxyz = (float*)take(max_edges * 3 * 4);
@@ -378,11 +487,10 @@ int fc_paconv_embed(const fc_embedder* e, const float* pts, float* out, int B, i
     for (int i = 0; i < 4; ++i) {
         const int n = w.n[i], m = w.n[i + 1];
         FC_REQUIRE(m <= n);
-        const int th = fps_threads(n);
-        fps_kernel<<<B, th, th * 8, s>>>(w.xyz[i], n, m, w.temp, w.fidx, w.xyz[i + 1]);
-        fc_count_launch(); FC_LAUNCH_OK();
-        knn_heap_kernel<<<dim3((m + 63) / 64, B), 64, 0, s>>>(w.xyz[i], w.xyz[i + 1], n, m, w.kidx);
-        fc_count_launch(); FC_LAUNCH_OK();
+        rc = launch_fps(w.xyz[i], B, n, m, 0, w.fidx, w.xyz[i + 1], s);
+        if (rc) return rc;
+        rc = launch_knn_heap(w.xyz[i], w.xyz[i + 1], B, n, m, PA_K, w.kidx, nullptr, s);
+        if (rc) return rc;
         const long long edges = (long long)B * m * PA_K;
         const int C0 = cfeat[i];
         int ldf = fc_round_up(3 + C0, 4);
@@ -410,8 +518,8 @@ int fc_paconv_embed(const fc_embedder* e, const float* pts, float* out, int B, i
     float* fp_out[2] = {w.hA, w.hB};
     for (int lev = 3; lev >= 0; --lev) {
         const int n = w.n[lev], m = w.n[lev + 1];
-        three_nn_kernel<<<dim3((n + 127) / 128, B), 128, 0, s>>>(w.xyz[lev], w.xyz[lev + 1], n, m, w.idx3, w.w3);
-        fc_count_launch(); FC_LAUNCH_OK();
+        rc = launch_three_nn(w.xyz[lev], w.xyz[lev + 1], B, n, m, w.idx3, w.w3, nullptr, s);
+        if (rc) return rc;
         const int C1 = cfeat[lev], Ct = Ck + C1, ldcat = fc_round_up(Ct, 4);
         const long long pts_tot = (long long)B * n;
         interp_concat_kernel<<<(unsigned)((pts_tot * Ct + 255) / 256), 256, 0, s>>>(known_feat, ldk, Ck, w.feat[lev], w.ldfeat[lev], C1,
@@ -437,4 +545,35 @@ int fc_paconv_embed(const fc_embedder* e, const float* pts, float* out, int B, i
     rc = fc_run_mlp_hidden(e->out_mlp, in, B * Nc, bufA, w.X, 512, precision, s, &last);
     if (rc) return rc;
     return gemm_relu(e->out_mlp.out, last, 512, FC_ACT_NONE, out, e->E, (long long)B * Nc, precision, s);
+}
+
+// ------------------------------------------------------------------------------------------ op-level C ABI (pointops)
+extern "C" int fc_fps(const float* xyz, int B, int n, int m, int tie_block, int32_t* idx_out, float* new_xyz_out, fc_stream_t stream) {
+    return launch_fps(xyz, B, n, m, tie_block, idx_out, new_xyz_out, (cudaStream_t)stream);
+}
+extern "C" int fc_knn_heap(const float* xyz, const float* new_xyz, int B, int n, int m, int k, int32_t* idx_out, float* dist2_out,
+                           fc_stream_t stream) {
+    return launch_knn_heap(xyz, new_xyz, B, n, m, k, idx_out, dist2_out, (cudaStream_t)stream);
+}
+extern "C" int fc_three_nn(const float* unknown, const float* known, int B, int n, int m, float* dist2_out, int32_t* idx_out,
+                           fc_stream_t stream) {
+    FC_REQUIRE(dist2_out != nullptr);
+    return launch_three_nn(unknown, known, B, n, m, idx_out, nullptr, dist2_out, (cudaStream_t)stream);
+}
+extern "C" int fc_three_interpolate(const float* known_feat, int ldk, int C, const int32_t* idx, const float* weight, int B, int n, int m,
+                                    float* out, int ldo, fc_stream_t stream) {
+    FC_REQUIRE(known_feat && idx && weight && out && B > 0 && n > 0 && m > 0 && C > 0 && ldk >= C && ldo >= C);
+    const long long pts = (long long)B * n;
+    interp_concat_kernel<<<(unsigned)((pts * C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(known_feat, ldk, C, nullptr, 0, 0, idx, weight,
+                                                                                           n, m, pts, out, ldo);
+    fc_count_launch(); FC_LAUNCH_OK();
+    return FC_OK;
+}
+extern "C" int fc_group_points(const float* feat, int ldf, int C, const int32_t* idx, int B, int n, int m, int k, float* out, int ldo,
+                               fc_stream_t stream) {
+    FC_REQUIRE(feat && idx && out && B > 0 && n > 0 && m > 0 && k > 0 && C > 0 && ldf >= C && ldo >= C);
+    const long long rows = (long long)B * m * k;
+    gather_rows_kernel<<<(unsigned)((rows * C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, C, idx, n, (long long)m * k, rows, out, ldo);
+    fc_count_launch(); FC_LAUNCH_OK();
+    return FC_OK;
 }

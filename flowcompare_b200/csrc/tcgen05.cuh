@@ -82,21 +82,25 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // D[tmem] (+)= A[tmem] * B[smem descriptor]   (A: 128 lanes x 8 columns of TF32, B: K-major tile)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    #if !(defined(TC_KO_MMA) && TC_KO_MMA)
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+#endif
 }
 // D[tmem] (+)= A[tmem] * B[smem descriptor]   (kind::f16: A = 128 lanes x 8 columns, each column two fp16 (k even in the low half); B: K-major fp16 tile, K = 16)
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    #if !(defined(TC_KO_MMA) && TC_KO_MMA)
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+#endif
 }
 // K-major operand tile, 64-byte rows (32 fp16), SWIZZLE_64B: 8-row groups are 512 B apart (SBO)
 __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {

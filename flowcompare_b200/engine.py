@@ -74,6 +74,12 @@ class FlowCompareB200:
                                      "fc_embedder_create")
         self._ws = None
         self._seed_counter = 0
+        self._tc_format = tc_format
+        self._flow_sd_for_inverse = flow_sd      # the inverse ActNorm+LinearLU matrices are packed on the first make_sample
+        self._inv = None
+        # reference Flow(sample_dist=Normal(loc, scale)) (model_initialization.py:154-161): buffers of the flow's state_dict
+        self._sample_loc = float(flow_sd["sample_dist.loc"].reshape(-1)[0]) if "sample_dist.loc" in flow_sd else 0.0
+        self._sample_scale = float(flow_sd["sample_dist.scale"].reshape(-1)[0]) if "sample_dist.scale" in flow_sd else 1.0
 
     # ------------------------------------------------------------------ lifecycle
     def _create(self, packed, create_fn, what):
@@ -147,19 +153,7 @@ class FlowCompareB200:
         with torch.cuda.device(self.device):
             x = _f32c(x[..., :self.d_in], self.device)
             B, N = x.shape[0], x.shape[1]
-            context = context.to(self.device)
-            if self.is_global and context.dim() == 3:
-                context = context[:, 0, :]
-            context = _f32c(context, self.device)
-            Nc = 1 if self.is_global else context.shape[1]
-            extra = None
-            if self.has_extra:
-                if extra_context is None:
-                    raise _lib.FlowCompareError("this config uses extra context (extra_z_value_context) but none was given")
-                extra = extra_context.to(self.device)
-                if extra.dim() == 3:
-                    extra = extra[:, 0, :]
-                extra = _f32c(extra.reshape(B), self.device)
+            context, Nc, extra = self._prep_context(context, extra_context, B)
             eps = self.draw_eps(B, N) if eps is None else _f32c(eps, self.device)
             assert eps.shape == (B, N, self.D - self.d_in), eps.shape
             out = torch.empty((B, N), dtype=torch.float32, device=self.device)
@@ -169,6 +163,81 @@ class FlowCompareB200:
                                            eps.data_ptr(), out.data_ptr(), B, N, Nc, ws, nbytes, self.precision, _stream())
             _lib.check(rc, "fc_flow_log_prob")
         return out
+
+    def _prep_context(self, context, extra_context, B):
+        context = context.to(self.device)
+        if self.is_global and context.dim() == 3:
+            context = context[:, 0, :]
+        context = _f32c(context, self.device)
+        Nc = 1 if self.is_global else context.shape[1]
+        extra = None
+        if self.has_extra:
+            if extra_context is None:
+                raise _lib.FlowCompareError("this config uses extra context (extra_z_value_context) but none was given")
+            extra = extra_context.to(self.device)
+            if extra.dim() == 3:
+                extra = extra[:, 0, :]
+            extra = _f32c(extra.reshape(B), self.device)
+        return context, Nc, extra
+
+    def forward(self, x, context, extra_context=None, eps=None):
+        """The forward pass with its latent: returns (log_prob [B,N], z [B,N,latent]) -- `Flow.log_prob` plus the point at
+        which the base density was evaluated (what `Flow.sample` inverts)."""
+        with torch.cuda.device(self.device):
+            x = _f32c(x[..., :self.d_in], self.device)
+            B, N = x.shape[0], x.shape[1]
+            context, Nc, extra = self._prep_context(context, extra_context, B)
+            eps = self.draw_eps(B, N) if eps is None else _f32c(eps, self.device)
+            out = torch.empty((B, N), dtype=torch.float32, device=self.device)
+            z = torch.empty((B, N, self.D), dtype=torch.float32, device=self.device)
+            nbytes = self.lib.fc_flow_workspace_bytes(self._flow["handle"], B, N, Nc)
+            ws = self._workspace(nbytes)
+            rc = self.lib.fc_flow_forward(self._flow["handle"], x.data_ptr(), context.data_ptr(), _ptr(extra), eps.data_ptr(),
+                                          out.data_ptr(), z.data_ptr(), B, N, Nc, ws, nbytes, self.precision, _stream())
+            _lib.check(rc, "fc_flow_forward")
+        return out, z
+
+    # ------------------------------------------------------------------ inverse / sampling pass
+    def _ensure_inverse(self):
+        if self._inv is None:
+            header, table, arena = packing.pack_flow_inverse(self._flow_sd_for_inverse, self.config, self._tc_format)
+            with torch.cuda.device(self.device):
+                arena_dev = arena.to(self.device)
+                rc = self.lib.fc_flow_set_inverse(self._flow["handle"], header.ctypes.data, len(header), table.ctypes.data, len(table),
+                                                  arena_dev.data_ptr(), arena_dev.numel())
+            _lib.check(rc, "fc_flow_set_inverse")
+            self._inv = {"arena": arena_dev, "header": header, "table": table}
+
+    def sample(self, n_points, context, extra_context=None, z=None, seed=None):
+        """`Flow.sample(num_samples=1, n_points=, context=, extra_context=)` (reference models/transform.py:79-84):
+        z ~ sample_dist = N(loc, scale) [B, n_points, latent] (or the injected `z`), then every transform's inverse.
+        Returns x [B, n_points, input_dim]."""
+        self._ensure_inverse()
+        with torch.cuda.device(self.device):
+            B = context.shape[0]
+            context, Nc, extra = self._prep_context(context, extra_context, B)
+            if z is None:
+                z = torch.empty((B, n_points, self.D), dtype=torch.float32, device=self.device)
+                if seed is None:
+                    self._seed_counter += 1
+                    seed = 0x5A3B0000 + self._seed_counter
+                _lib.check(self.lib.fc_fill_normal(z.data_ptr(), z.numel(), seed, 0, _stream()), "fc_fill_normal")
+                z = z * self._sample_scale + self._sample_loc
+            z = _f32c(z, self.device).reshape(B, n_points, self.D)
+            out = torch.empty((B, n_points, self.d_in), dtype=torch.float32, device=self.device)
+            nbytes = self.lib.fc_flow_workspace_bytes(self._flow["handle"], B, n_points, Nc)
+            ws = self._workspace(nbytes)
+            rc = self.lib.fc_flow_sample(self._flow["handle"], z.data_ptr(), context.data_ptr(), _ptr(extra), out.data_ptr(), B,
+                                         n_points, Nc, ws, nbytes, self.precision, _stream())
+            _lib.check(rc, "fc_flow_sample")
+        return out
+
+    def make_sample(self, n_points, extract_0, extra_context=None, z=None, seed=None):
+        """`make_sample(n_points, extract_0, models_dict, config, sample_distrib=None, extra_context=None)` (reference
+        model_initialization.py:231-245): embed the context cloud, then the generative pass.  Returns what the reference
+        returns: x [B, n_points, input_dim] with singleton dimensions squeezed."""
+        emb = self.embed(extract_0)
+        return self.sample(n_points, emb, extra_context=extra_context, z=z, seed=seed).squeeze()
 
     # ------------------------------------------------------------------ whole path
     def inner_loop(self, batch, eps=None):
@@ -302,9 +371,21 @@ class _FlowAdapter:
     def __init__(self, engine):
         self.engine = engine
         self.eps = None  # set to a tensor to inject the augmentation noise (parity tests)
+        self.z = None    # set to a tensor to inject the base draw of `sample` (parity tests)
 
     def log_prob(self, x, context=None, extra_context=None):
         return self.engine.log_prob(x, context, extra_context, eps=self.eps)
+
+    def sample(self, num_samples, n_points, context=None, sample_distrib=None, extra_context=None):
+        """`Flow.sample` (models/transform.py:79-84); `sample_distrib` may be any object with the reference's
+        `.sample(num_samples, n_points=)` (it is asked for the base draw exactly as the reference asks it)."""
+        z = None
+        if sample_distrib is not None:
+            z = sample_distrib.sample(num_samples, n_points=n_points)
+        elif self.z is not None:
+            z = self.z
+        assert num_samples == 1, "the reference only ever draws num_samples=1 (model_initialization.py:243)"
+        return self.engine.sample(n_points, context, extra_context=extra_context, z=z)
 
     def eval(self):
         return self
@@ -332,3 +413,10 @@ def accelerate(models_dict, config, device="cuda:0", precision="fp32"):
 def inner_loop(batch, models_dict, config, eps=None):
     """Same signature as the reference's `inner_loop`; `models_dict` must come from `accelerate`."""
     return models_dict["engine"].inner_loop(batch, eps=eps)
+
+
+def make_sample(n_points, extract_0, models_dict, config, sample_distrib=None, extra_context=None):
+    """Same signature as the reference's `make_sample` (model_initialization.py:231-245); `models_dict` from `accelerate`."""
+    eng = models_dict["engine"]
+    z = None if sample_distrib is None else sample_distrib.sample(1, n_points=n_points)
+    return eng.make_sample(n_points, extract_0, extra_context=extra_context, z=z)

@@ -30,6 +30,11 @@ SIGNATURES = {
     "fc_launch_count": (c_i64, []),
     "fc_knn_self": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "fc_knn_query": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "fc_fps": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "fc_knn_heap": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "fc_three_nn": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "fc_three_interpolate": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "fc_group_points": (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "fc_gemm": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "fc_gemm_tf32x3": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "fc_gemm_f16x3": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
@@ -42,6 +47,9 @@ SIGNATURES = {
     "fc_flow_destroy": (None, [c_vp]),
     "fc_flow_workspace_bytes": (c_i64, [c_vp, c_int, c_int, c_int]),
     "fc_flow_log_prob": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
+    "fc_flow_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
+    "fc_flow_set_inverse": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_i64]),
+    "fc_flow_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
     "fc_embedder_create": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_i64, ctypes.POINTER(c_vp)]),
     "fc_embedder_destroy": (None, [c_vp]),
     "fc_embedder_workspace_bytes": (c_i64, [c_vp, c_int, c_int]),

@@ -202,8 +202,8 @@ def fold_inverse_actnorm_lu(flow_sd, config):
     models/act_norm.py:45-46, i.e. the inverse of one ActNorm + LinearLU pair): with the forward fold
     z' = Wp z - Wp shift, Wp = L U diag(exp(-log_scale)), the inverse is z = Wp^-1 z' + shift.  Returned per pair, in
     forward layer order, as (off-diagonal part of Wp^-1, its diagonal, bias) in fp64 -- the same split the forward GEMM
-    uses so that the latent's own column is applied in fp32 in the epilogue.  (Host side of SURVEY 8f rank 1; the
-    kernels of the inverse pass are not built yet.)"""
+    uses so that the latent's own column is applied in fp32 in the epilogue (consumed by
+    pack_flow_inverse -> csrc/flow.cu: fc_flow_sample)."""
     cfg = derive(config)
     D, L = cfg["latent_dim"], cfg["n_flow_layers"]
     out = []
@@ -230,6 +230,23 @@ def fold_inverse_actnorm_lu(flow_sd, config):
             out.append((Winv - torch.diag(wdiag), wdiag, shift.clone()))
             t += 1
     return out
+
+
+INV_MAGIC = 0x46435F49
+
+
+def pack_flow_inverse(flow_sd, config, tc_format="tf32"):
+    """Arena of the sampling pass (csrc/flow.cu: fc_flow_set_inverse): per ActNorm+LinearLU pair, in forward layer order,
+    the off-diagonal part of Wp^-1 with bias = shift as a Linear, then its diagonal (fold_inverse_actnorm_lu)."""
+    cfg = derive(config)
+    ar = Arena(tc_format)
+    D = cfg["latent_dim"]
+    for w_off, wdiag, shift in fold_inverse_actnorm_lu(flow_sd, config):
+        ar.linear(w_off, shift, D)
+        ar.vector(wdiag)
+    arena, table = ar.finish()
+    header = np.asarray([INV_MAGIC, TC_FORMATS[tc_format], cfg["n_flow_layers"], D], dtype=np.int32)
+    return header, table, arena
 
 
 def pack_flow(flow_sd, config, tc_format="tf32"):

@@ -67,6 +67,47 @@ FC_API int fc_knn_self(const float* x, int ldx, int B, int N, int C, int k,
 FC_API int fc_knn_query(const float* q, const float* t, int Nq, int Nt, int D, int k,
                  int64_t* idx64, fc_stream_t stream);
 
+/* ------------------------------------------------------------------ pointops (PAConv embedder, data side) ----
+ * Op-level entry points for the reference's `pointops` kernels (models/scene_seg_PAConv/lib/pointops; python wrappers
+ * lib/pointops/functions/pointops.py), point-major layouts, int32 indices, bit-exact INDICES against the reference's
+ * compiled kernels (oracle/_ref/libpointops_ref.so, tests/test_pointops_gpu.py).
+ *
+ * fc_fps replaces `furthestsampling(xyz, m)` (pointops.py:47-62 -> src/sampling/sampling_cuda_kernel.cu:58-209):
+ * xyz [B,n,3] -> idx_out [B,m] (first pick = point 0, then repeatedly the point farthest from the picked set);
+ * new_xyz_out [B,m,3] optional (the gathered coordinates, `gathering` :68-90).  tie_block selects how equal
+ * distances are resolved: 0 = exactly as the reference's launch does (its block of 2^floor(log2 n) <= 1024 threads
+ * prefers the lowest thread, point k living in thread k % block), > 0 = that rule for an explicit block size,
+ * < 0 = lowest index.  n <= 32768.  Also serves the data-side sub-sampling of the clouds
+ * (dataloaders/ams_voxel_loader.py:298-307 uses torch_cluster.fps; same greedy rule).              */
+FC_API int fc_fps(const float* xyz, int B, int n, int m, int tie_block, int32_t* idx_out, float* new_xyz_out,
+           fc_stream_t stream);
+
+/* fc_knn_heap replaces `knnquery_heap(nsample, xyz, new_xyz)` (pointops.py:475-497 ->
+ * src/knnquery_heap/knnquery_heap_cuda_kernel.cu:53-110): for each of the m queries the k nearest of the n points,
+ * ascending squared distance; idx_out [B,m,k]; dist2_out [B,m,k] optional.  The reference's heap algorithm is followed
+ * step for step (the order of exactly equal distances is an artefact of it; k > n leaves index 0 / 1e10 in the unfilled
+ * slots).  1 <= k <= 40.                                                                                             */
+FC_API int fc_knn_heap(const float* xyz, const float* new_xyz, int B, int n, int m, int k, int32_t* idx_out,
+                float* dist2_out, fc_stream_t stream);
+
+/* fc_three_nn replaces `nearestneighbor(unknown, known)` (pointops.py:96-115 ->
+ * src/interpolation/interpolation_cuda_kernel.cu:134-213): unknown [B,n,3], known [B,m,3] -> the three nearest known
+ * points of every unknown point: dist2_out [B,n,3] SQUARED distances (the python wrapper takes the sqrt), idx_out [B,n,3];
+ * ties by lower index; m < 3 leaves index 0 / +inf in the unfilled slots.                                           */
+FC_API int fc_three_nn(const float* unknown, const float* known, int B, int n, int m, float* dist2_out,
+                int32_t* idx_out, fc_stream_t stream);
+
+/* fc_three_interpolate replaces `interpolation(features, idx, weight)` (pointops.py:121-140 -> interpolation_cuda_kernel.cu:
+ * 181-229) in point-major layout: known_feat [B,m,ldk] (C columns used), idx / weight [B,n,3] -> out [B,n,ldo]:
+ * out = fma(w2, f[idx2], fma(w1, f[idx1], w0 * f[idx0])) (the contraction nvcc applies to the reference expression).  */
+FC_API int fc_three_interpolate(const float* known_feat, int ldk, int C, const int32_t* idx, const float* weight,
+                         int B, int n, int m, float* out, int ldo, fc_stream_t stream);
+
+/* fc_group_points replaces `grouping(features, idx)` (pointops.py:158-175 -> src/grouping/grouping_cuda_kernel.cu:60-95) in
+ * point-major layout: feat [B,n,ldf] (C columns), idx [B,m,k] -> out [B,m,k,ldo].                                      */
+FC_API int fc_group_points(const float* feat, int ldf, int C, const int32_t* idx, int B, int n, int m, int k,
+                    float* out, int ldo, fc_stream_t stream);
+
 /* ------------------------------------------------------------------ GEMM (test hook) ------
  * C[M,N] = act(A[M,K] * Wt[K,N] + bias) with the library's fp32 GEMM; `Wt` is K-major
  * ([Kp, ldw], Kp = K rounded up to 16, rows >= K zero, ldw >= N rounded up to 128 (64 if N<=64)).
@@ -132,10 +173,31 @@ FC_API int64_t fc_flow_workspace_bytes(const fc_flow* h, int B, int N, int Nc);
  *   x [B,N,input_dim]; context [B,Nc,E] (attention configs) or [B,E] (global embedder);
  *   extra [B] or NULL; eps [B,N,latent-input_dim] = the N(0,1) draw of
  *   models/distributions.py:148-153 made explicit; log_prob_out [B,N].
- *   precision: 0 = fp32 FFMA GEMMs, 1 = 3xTF32 tcgen05 GEMMs.                                 */
+ *   precision: 0 = fp32 FFMA GEMMs, 1 = tcgen05 GEMMs (3xTF32 or 3xFP16, whichever weight
+ *   copies the model was packed with).                                                        */
 FC_API int fc_flow_log_prob(const fc_flow* h, const float* x, const float* context, const float* extra,
                      const float* eps, float* log_prob_out, int B, int N, int Nc,
                      void* workspace, int64_t workspace_bytes, int precision, fc_stream_t stream);
+
+/* Same pass, additionally returning the final latent z_out [B,N,latent] (the point of the base density; the input of
+ * the sampling pass run backwards).                                                                              */
+FC_API int fc_flow_forward(const fc_flow* h, const float* x, const float* context, const float* extra,
+                    const float* eps, float* log_prob_out, float* z_out, int B, int N, int Nc,
+                    void* workspace, int64_t workspace_bytes, int precision, fc_stream_t stream);
+
+/* Inverse / sampling pass: fc_flow_sample replaces `Flow.sample` after its base draw (reference models/transform.py:79-84,
+ * called by `make_sample`, model_initialization.py:231-245): the transforms walked backwards with each `.inverse`
+ * (models/affine_coupling.py:48-62, models/permuters.py:171-177, models/act_norm.py:45-46, models/augmenter.py:20-21,65-67).
+ *   z [B,P,latent] the base draw (reference: sample_dist.sample = N(loc, scale), P = n_points); context / extra as in
+ *   fc_flow_log_prob; x_out [B,P,input_dim].  fc_flow_workspace_bytes(h, B, P, Nc) sizes the workspace.
+ * The inverse ActNorm+LinearLU matrices are not part of the forward model: fc_flow_set_inverse attaches them first
+ * (header/table/arena from packing.pack_flow_inverse; the arena must outlive the handle); without it fc_flow_sample
+ * returns FC_ERR_MODEL.                                                                                          */
+FC_API int fc_flow_set_inverse(fc_flow* h, const int32_t* header_host, int n_header, const int64_t* table_host,
+                        int n_table, const float* arena, int64_t arena_floats);
+FC_API int fc_flow_sample(const fc_flow* h, const float* z, const float* context, const float* extra, float* x_out,
+                   int B, int P, int Nc, void* workspace, int64_t workspace_bytes, int precision,
+                   fc_stream_t stream);
 
 FC_API int fc_embedder_create(const int32_t* header_host, int n_header, const int64_t* table_host, int n_table,
                        const float* arena, int64_t arena_floats, fc_embedder** out);

@@ -15,14 +15,17 @@ for K, N, act in shapes:
     rows, ldk = packing.tc_n_tiles(N) * packing.tc_bn(N), packing.tc_kpad(K)
     W32 = torch.zeros(rows, ldk); W32[:N, :K] = W
     hi = packing.tf32_round(W32); lo = packing.tf32_round(W32 - hi)
-    Wt, hi, lo = Wt.cuda(), hi.cuda(), lo.cuda()
+    h16, l16 = packing.f16_split(W32)
+    Wt, hi, lo, h16, l16 = Wt.cuda(), hi.cuda(), lo.cuda(), h16.cuda(), l16.cuda()
     b = torch.randn(N, device="cuda")
     C = torch.empty(M, N, device="cuda")
     res = {}
-    for name in ("ffma", "tc"):
+    for name in ("ffma", "tc", "f16"):
         def run():
             if name == "ffma":
                 return lib.fc_gemm(A.data_ptr(), A.shape[1], Wt.data_ptr(), Wt.shape[1], b.data_ptr(), C.data_ptr(), N, M, N, K, act, 0, st)
+            if name == "f16":
+                return lib.fc_gemm_f16x3(A.data_ptr(), A.shape[1], h16.data_ptr(), l16.data_ptr(), ldk, b.data_ptr(), C.data_ptr(), N, M, N, K, act, st)
             return lib.fc_gemm_tf32x3(A.data_ptr(), A.shape[1], hi.data_ptr(), lo.data_ptr(), ldk, b.data_ptr(), C.data_ptr(), N, M, N, K, act, st)
         for _ in range(3): assert run() == 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,13 +34,6 @@ for K, N, act in shapes:
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
         res[name] = (ms, 2.0 * M * N * K / ms / 1e9)
-    if os.environ.get("FC_TC_DEBUG") == "1":
-        import ctypes
-        buf = (ctypes.c_ulonglong * 16)()
-        lib.fc_debug_tc_phases.argtypes = [ctypes.c_void_p]; lib.fc_debug_tc_phases.restype = ctypes.c_int
-        lib.fc_debug_tc_phases(buf)
-        n = max(1, buf[0])
-        print(f"   phases per CTA (cycles): setup {buf[3]/n:8.0f}  mainloop(setup->accum) {buf[1]/n:8.0f}  epilogue {buf[2]/n:8.0f} (tmem ld {buf[4]/n:.0f}, math {buf[5]/n:.0f}, stage+store {buf[6]/n:.0f})  ctas {buf[0]}")
-    if os.environ.get("FC_TC_DEBUG") == "1":
-        print(f"      converter/CTA: wait_full {buf[8]/n:.0f} convert {buf[9]/n:.0f} wait_tfree {buf[10]/n:.0f} tmem_st {buf[11]/n:.0f} | MMA/CTA: wait_full {buf[12]/n:.0f} wait_conv {buf[13]/n:.0f} issue {buf[14]/n:.0f}")
-    print(f"M={M} K={K:4d} N={N:4d} act={act}  ffma {res['ffma'][0]*1e3:8.1f} us {res['ffma'][1]:6.1f} TF/s | tc {res['tc'][0]*1e3:8.1f} us {res['tc'][1]:6.1f} TF/s", flush=True)
+        if name != "ffma":
+            res[name + "_err"] = (C.double() - (A[:, :K].double() @ W.double().cuda().t() + b.double())).abs().max().item() if act == 0 else float("nan")
+    print(f"M={M} K={K:4d} N={N:4d} act={act}  ffma {res['ffma'][0]*1e3:8.1f} us {res['ffma'][1]:6.1f} TF/s | tf32x3 {res['tc'][0]*1e3:8.1f} us {res['tc'][1]:6.1f} TF/s err {res['tc_err']:.2e} | f16x3 {res['f16'][0]*1e3:8.1f} us {res['f16'][1]:6.1f} TF/s err {res['f16_err']:.2e}", flush=True)

@@ -10,10 +10,12 @@ A = torch.randn(M, (K + 3) // 4 * 4, device="cuda")
 W = torch.randn(N, K) / math.sqrt(K)
 rows, ldk = packing.tc_n_tiles(N) * packing.tc_bn(N), packing.tc_kpad(K)
 W32 = torch.zeros(rows, ldk); W32[:N, :K] = W
-hi = packing.tf32_round(W32); lo = packing.tf32_round(W32 - hi)
+F16 = os.environ.get("FC_FMT", "fp16") == "fp16"
+hi, lo = packing.f16_split(W32) if F16 else (packing.tf32_round(W32), packing.tf32_round(W32 - packing.tf32_round(W32)))
 hi, lo = hi.cuda(), lo.cuda()
+fn = lib.fc_gemm_f16x3 if F16 else lib.fc_gemm_tf32x3
 b = torch.randn(N, device="cuda"); C = torch.empty(M, N, device="cuda")
 for _ in range(4):
-    assert lib.fc_gemm_tf32x3(A.data_ptr(), A.shape[1], hi.data_ptr(), lo.data_ptr(), ldk, b.data_ptr(), C.data_ptr(), N, M, N, K, act, st) == 0
+    assert fn(A.data_ptr(), A.shape[1], hi.data_ptr(), lo.data_ptr(), ldk, b.data_ptr(), C.data_ptr(), N, M, N, K, act, st) == 0
 torch.cuda.synchronize()
 print("ok")

@@ -15,12 +15,16 @@ for (M, N, K, act) in shapes:
     A = torch.randn(M, (K + 3) // 4 * 4, generator=g).cuda()
     rows, ldk = packing.tc_n_tiles(N) * packing.tc_bn(N), packing.tc_kpad(K)
     W32 = torch.zeros(rows, ldk); W32[:N, :K] = torch.randn(N, K, generator=g) / math.sqrt(K)
-    hi = packing.tf32_round(W32); lo = packing.tf32_round(W32 - hi)
+    F16 = os.environ.get("FC_FMT", "fp16") == "fp16"
+    if F16:
+        hi, lo = packing.f16_split(W32)
+    else:
+        hi = packing.tf32_round(W32); lo = packing.tf32_round(W32 - hi)
     hi, lo, b = hi.cuda(), lo.cuda(), torch.randn(N, generator=g).cuda()
     C = torch.empty(M, N, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     def run():
-        rc = lib.fc_gemm_tf32x3(A.data_ptr(), A.shape[1], hi.data_ptr(), lo.data_ptr(), ldk, b.data_ptr(), C.data_ptr(), N, M, N, K, act, st)
+        rc = (lib.fc_gemm_f16x3 if F16 else lib.fc_gemm_tf32x3)(A.data_ptr(), A.shape[1], hi.data_ptr(), lo.data_ptr(), ldk, b.data_ptr(), C.data_ptr(), N, M, N, K, act, st)
         assert rc == 0
     for _ in range(3): run()
     torch.cuda.synchronize()
@@ -32,6 +36,6 @@ for (M, N, K, act) in shapes:
     n = max(1, out[0])
     tiles = ((M + 127) // 128) * packing.tc_n_tiles(N)
     kb = tiles * ((K + 31) // 32) / n
-    print(f"M={M} N={N} K={K} act={act} ctas={out[0]} rc={rc} us={e0.elapsed_time(e1)*1e3:.1f} k-blocks/CTA={kb:.0f} | MMA warp: total {out[1]/n:.0f} "
+    print(f"{'f16x3' if F16 else 'tf32x3'} M={M} N={N} K={K} act={act} ctas={out[0]} rc={rc} us={e0.elapsed_time(e1)*1e3:.1f} k-blocks/CTA={kb:.0f} | MMA warp: total {out[1]/n:.0f} "
           f"(/kb {out[1]/n/kb:.0f}) wait full {out[2]/n:.0f} conv {out[3]/n:.0f} acc_free {out[4]/n:.0f} | converter: total {out[5]/n:.0f} wait full {out[6]/n:.0f} "
-          f"tfree {out[7]/n:.0f} | epilogue: total {out[8]/n:.0f} wait acc_full {out[9]/n:.0f}", flush=True)
+          f"tfree {out[7]/n:.0f} | MMA probe {out[10]/n:.0f} issue {out[11]/n:.0f} | epilogue: total {out[8]/n:.0f} wait acc_full {out[9]/n:.0f}", flush=True)

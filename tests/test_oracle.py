@@ -273,3 +273,24 @@ def test_port_change_score_matches_live_reference():
     a = lp10.clone()
     tf.log_prob_to_change(a, lp00.clone(), 5.4)
     assert not torch.isinf(a).any() and torch.isinf(lp10).any()
+
+
+# ----------------------------------------------------------------------------- sampling pass goldens
+@pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_attn_extra", "tiny_dgcnn_global"])
+def test_port_sampling_pass_matches_reference_golden(name):
+    """oracle/port.py: flow_sample against the UNMODIFIED reference's make_sample outputs (tests/golden/sample_*.pt)."""
+    from oracle.make_sample_golden import base_draw
+    cfg, fsd, esd, batch = fixture_inputs(name)
+    dcfg = configs.derive(cfg)
+    gold = load_golden("sample_" + name)
+    P = gold["n_points"]
+    z = base_draw(name, cfg, batch["extract_0"].shape[0])
+    if dcfg["global"]:
+        emb, _ = port.dgcnn_embed_global(esd, batch["extract_0"], cfg["n_neighbors"])
+        ctx = emb.unsqueeze(1).expand(-1, P, -1)
+    else:
+        ctx, _ = port.dgcnn_embed(esd, batch["extract_0"], cfg["n_neighbors"])
+    extra = batch["extra_context"]
+    ex = None if extra is None else extra.unsqueeze(1).expand(-1, P, -1)
+    got = port.flow_sample(fsd, dcfg, z, ctx, ex)
+    assert (got - gold["x"]).abs().max().item() < 1e-4
