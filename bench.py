@@ -35,7 +35,7 @@ import torch
 
 METRIC = "cloud-pairs/sec for per-point log p(x|ctx)"
 UNIT = "pairs/s"
-CLASS_NAMES = ["gemm_fp32_ffma", "gemm_tf32x3_tcgen05", "cross_attention", "knn", "edgeconv_gather_max", "other"]
+CLASS_NAMES = ["gemm_fp32_ffma", "gemm_tcgen05_3x", "cross_attention", "knn", "edgeconv_gather_max", "other"]
 
 
 def parse():
@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=6, help="pairs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true", help="profiling run: 1 warm-up, timed steps only (not a bench value)")
+    ap.add_argument("--no-extras", action="store_true", help="skip per_batch / per_config / sweep / strong-scaling extras")
+    ap.add_argument("--extras-budget-s", type=float, default=150.0, help="wall-clock budget of the extras")
     ap.add_argument("--n-context", type=int, default=None)
     ap.add_argument("--n-target", type=int, default=None)
     return ap.parse_args()
@@ -192,6 +194,137 @@ def ncu_traffic():
         return None, f"no committed ncu capture readable: {exc}"
 
 
+def _timed(fn, steps, warmup=2):
+    """pairs-agnostic device timing of fn(): CUDA events on the current stream, after warm-up."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def extras_single_gpu(args, eng, cfg, dev, precision, t_end, note):
+    """Extra keys measured on rank 0 at N = 1 after the headline numbers (same engine / weights; device-resident inputs,
+    CUDA events).  SURVEY 8d: batch sizes B in {1, 8, 20, 64} of config 2, the other architectures (BASELINE configs[0],
+    [2], [3] + PAConv with extra context) at the bench batch, and the point-count sweep of configs[4] on one GPU."""
+    from flowcompare_b200 import configs, engine, spec
+    out = {}
+
+    def left():
+        return t_end - time.perf_counter()
+
+    # ---- batch sizes: eager launches vs one CUDA-graph launch (the forward is ~4.6 k kernel launches)
+    per_batch = {}
+    for B in (1, 8, 20, 64):
+        if left() < 20:
+            break
+        b = spec.synthetic_batch(cfg, B, seed=7)
+        e0, e1, eps = b["extract_0"].to(dev), b["extract_1"].to(dev), b["eps"].to(dev)
+        ex = None if b["extra_context"] is None else b["extra_context"].to(dev)
+        steps = 4 if B >= 20 else 8
+        ms = _timed(lambda: eng.inner_loop((e0, e1, ex), eps=eps), steps)
+        rec = {"pairs_per_s": round(B / ms * 1e3, 2), "ms_per_step": round(ms, 3)}
+        try:
+            run = eng.capture_inner_loop(B, e0.shape[1], e1.shape[1])
+            lp_graph = run(e0, e1, ex, eps)[1].clone()
+            lp_eager = eng.inner_loop((e0, e1, ex), eps=eps)[1]
+            msg = _timed(lambda: run(e0, e1, ex, eps, copy=False), steps)
+            rec.update({"cuda_graph_pairs_per_s": round(B / msg * 1e3, 2), "cuda_graph_ms_per_step": round(msg, 3),
+                        "cuda_graph_equals_eager": bool(torch.equal(lp_graph, lp_eager))})
+            del run
+        except Exception as exc:   # keep the bench line alive; the failure is reported
+            rec["cuda_graph_error"] = repr(exc)[:200]
+        per_batch[str(B)] = rec
+    out["per_batch"] = per_batch
+    note("extras: per_batch done")
+
+    # ---- the other architectures at the bench batch
+    per_config = {}
+    for label in ("dgcnn_global", "paconv_attn", "dgcnn_attn_extra", "paconv_attn_extra"):
+        if left() < 35:
+            per_config[label] = "skipped (extras budget)"
+            continue
+        c2 = configs.get_config(label)
+        fsd, esd = spec.random_state_dicts(c2, seed=0)
+        e2 = engine.FlowCompareB200((fsd, esd), c2, device=dev, precision=precision)
+        del fsd, esd
+        b = spec.synthetic_batch(c2, args.batch, seed=100)
+        e0, e1, eps = b["extract_0"].to(dev), b["extract_1"].to(dev), b["eps"].to(dev)
+        ex = None if b["extra_context"] is None else b["extra_context"].to(dev)
+        ms = _timed(lambda: e2.inner_loop((e0, e1, ex), eps=eps), 3, warmup=2)
+        per_config[label] = {"workload": configs.BASELINE_LABEL.get(label, label), "pairs_per_s": round(args.batch / ms * 1e3, 2),
+                             "ms_per_step": round(ms, 3), "pairs_per_step": args.batch}
+        e2.close()
+        del e2, e0, e1, eps
+        torch.cuda.empty_cache()
+    out["per_config"] = per_config
+    note("extras: per_config done")
+
+    # ---- BASELINE configs[4]: point-count sweep Nc = N, same architecture, pairs per step chosen to keep ~131 k target points
+    sweep = {}
+    for npts in (2048, 4096, 8192, 16384, 32768):
+        if left() < 25:
+            sweep[str(npts)] = "skipped (extras budget)"
+            continue
+        B = max(1, min(64, 131072 // npts))
+        g = torch.Generator().manual_seed(npts)
+        e0 = (torch.rand(B, npts, 6, generator=g) * 2 - 1).to(dev)
+        e1 = (torch.rand(B, npts, 6, generator=g) * 2 - 1).to(dev)
+        try:
+            ms = _timed(lambda: eng.inner_loop((e0, e1, None), eps=None), 2, warmup=1)
+            sweep[str(npts)] = {"pairs_per_s": round(B / ms * 1e3, 3), "points_per_s": round(B * npts / ms * 1e3, 1),
+                                "ms_per_step": round(ms, 2), "pairs_per_step": B}
+        except Exception as exc:
+            sweep[str(npts)] = {"error": repr(exc)[:200]}
+        del e0, e1
+        torch.cuda.empty_cache()
+    out["sweep_one_gpu"] = sweep
+    note("extras: sweep done")
+    return out
+
+
+def strong_scaling(eng, cfg, dev, world, rank, B_chunk, total_pairs=1024):
+    """A FIXED evaluation set of 1024 pairs sharded over the ranks through flowcompare_b200.sharding.evaluate_sharded (the
+    host logic of test_flow.evaluate_on_test: score, reduce to the running nats) with the real engine and NCCL: the one
+    collective is the gather of per-cloud scalars.  eps is drawn on the device.  Returns pairs/s (max over ranks)."""
+    import torch.distributed as dist
+    from flowcompare_b200 import sharding
+    Nc, N = cfg["n_samples_context"], cfg["sample_size"]
+    lo, hi = sharding.shard_bounds(total_pairs, rank, world)
+    g = torch.Generator().manual_seed(1234)      # every rank builds the same set and scores its own block
+    e0 = torch.rand(total_pairs, Nc, 6, generator=g)
+    e1 = torch.rand(total_pairs, N, 6, generator=g)
+    e0, e1 = (e0 * 2 - 1).to(dev), (e1 * 2 - 1).to(dev)
+    eps_dummy = torch.empty(total_pairs, 0)
+
+    def score(batch, _eps):
+        a, b_, _ = batch
+        outs = []
+        for i in range(0, a.shape[0], B_chunk):
+            outs.append(eng.inner_loop((a[i:i + B_chunk], b_[i:i + B_chunk], None), eps=None)[1])
+        return torch.cat(outs)
+
+    sharding.evaluate_sharded(score, e0[: 2 * world], e1[: 2 * world], None, eps_dummy[: 2 * world])   # warm-up incl. the collective
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    per_cloud, nats = sharding.evaluate_sharded(score, e0, e1, None, eps_dummy)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"pairs": total_pairs, "pairs_per_s": round(total_pairs / t.item(), 2), "seconds": round(t.item(), 3), "nats": nats,
+            "ranks": world, "collective": "one all_gather of per-cloud mean log-prob (NCCL)" if world > 1 else "none",
+            "local_pairs": hi - lo}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -224,7 +357,7 @@ def main():
     precision = args.precision
     clib = lib.load()
     if precision == "auto":
-        precision = "tf32x3"   # tensor-core path; parity-tested at full depth like the exact-fp32 FFMA path
+        precision = "fp16x3"   # tensor-core path (3xFP16 error-compensated); parity-tested at full depth like the exact-fp32 FFMA path
     fsd, esd = spec.random_state_dicts(cfg, seed=0)          # same weights on every rank
     eng = engine.FlowCompareB200((fsd, esd), cfg, device=dev, precision=precision)
     del fsd, esd
@@ -296,6 +429,25 @@ def main():
     d2h = 4 * (hlp.numel() + 2)
     # e2e result must equal the device-resident result
     same = bool(torch.equal(hlp, lp.cpu()))
+    # second end-to-end figure: the augmentation noise drawn ON THE DEVICE (fc_fill_normal), so only the clouds cross PCIe
+    def e2e_device_eps():
+        d0, d1 = h0.to(dev, non_blocking=True), h1.to(dev, non_blocking=True)
+        dx = None if hex_ is None else hex_.to(dev, non_blocking=True)
+        _, lpd, _ = eng.inner_loop((d0, d1, dx), eps=None)
+        hlp.copy_(lpd, non_blocking=True)
+        torch.cuda.synchronize()
+    for _ in range(2):
+        e2e_device_eps()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_device_eps()
+    t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_dev_eps_value = world * B * args.steps / t.item()
+    h2d_dev_eps = 4 * (h0.numel() + h1.numel() + (0 if hex_ is None else hex_.numel()))
 
     # ---- one instrumented step: per-class kernel time with CUDA events around every launch
     roofline, classes = None, None
@@ -315,15 +467,20 @@ def main():
         top = 1 if ln_c[1] and ms_c[1] >= ms_c[0] else 0
         achieved = fl_c[top] / ms_c[top] / 1e9
         traffic, traffic_note = ncu_traffic()
-        roofline = {"kernel": CLASS_NAMES[top], "bound": "tensor", "achieved": round(achieved, 2),
-                    "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_sustained"], 4),
+        f16 = precision == "fp16x3"
+        # what the tensor cores execute: 3 products per algorithmic one; 3xFP16 runs at the bf16/fp16 rate, 3xTF32 at half of it
+        issued = 3 * achieved
+        issue_peak = pk["bf16_sustained"] if f16 else pk["bf16_sustained"] / 2
+        roofline = {"kernel": CLASS_NAMES[top] + ("(fp16)" if f16 else "(tf32)") if top == 1 else CLASS_NAMES[top], "bound": "tensor",
+                    "achieved": round(achieved, 2), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": round(achieved / pk["bf16_sustained"], 4),
                     "traffic": traffic if top == 1 else None, "traffic_note": traffic_note, "peak_source": pk["source"] + ", dense bf16 sustained",
-                    "note": "achieved = algorithmic 2*M*N*K flops of every launch of the class / summed CUDA-event time "
-                            "in one instrumented step; fp32-faithful GEMMs cannot exceed TF32/3 ~ bf16/6 of this peak",
+                    "note": "achieved = algorithmic 2*M*N*K flops of every launch of the class / summed CUDA-event time in one "
+                            "instrumented step; an fp32-faithful GEMM issues 3 tensor products per algorithmic one, so its ceiling is "
+                            + ("1/3 of this peak (3xFP16)" if f16 else "1/6 of this peak (3xTF32: half rate, 3 products)"),
                     "avg_launch_ms": round(ms_c[top] / max(1, ln_c[top]), 4),
-                    # what the tensor cores actually execute: 3 TF32 products per algorithmic one, TF32 = 1/2 the bf16 rate
-                    "issued_tf32_tflops": round(3 * achieved, 1) if top == 1 else None,
-                    "frac_of_tf32_peak": round(3 * achieved / (pk["bf16_sustained"] / 2), 4) if top == 1 else None}
+                    "issued_tensor_tflops": round(issued, 1) if top == 1 else None,
+                    "frac_of_issue_rate_peak": round(issued / issue_peak, 4) if top == 1 else None}
 
     note("e2e + instrumented step done")
     # live precision evidence: the timed path (3xTF32 on the tensor cores) against the exact-fp32 FFMA path of the same
@@ -344,6 +501,15 @@ def main():
         eng32.close()
         del eng32
         note("precision check done")
+    extras = {}
+    if not args.no_extras and not args.ncu:
+        if world == 1:
+            extras = extras_single_gpu(args, eng, cfg, dev, precision, time.perf_counter() + args.extras_budget_s, note)
+        try:
+            extras["strong_scaling_fixed_set"] = strong_scaling(eng, cfg, dev, world, rank, B)
+        except Exception as exc:
+            extras["strong_scaling_fixed_set"] = {"error": repr(exc)[:200]}
+        note("extras: strong scaling done")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # the CPU baseline is measured at N=1 only
         v, dt = cpu_baseline(cfg, args.cpu_pairs)
@@ -357,10 +523,14 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else precision + "(f32-faithful)",
                "data": "synthetic", "config": workload_config(args, cfg, B, "B200"),
                "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "matches_device_resident_result": same},
+                       "matches_device_resident_result": same,
+                       "device_drawn_eps": {"value": round(e2e_dev_eps_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d_dev_eps,
+                                            "d2h_bytes_per_step": 4 * hlp.numel(),
+                                            "note": "same call path through engine.inner_loop with host clouds; the noise is drawn by fc_fill_normal on the device"}},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_classes": classes,
                "cpu_baseline": cpu, "mean_log_prob": float(lp.mean().item()), "bpd": float(bpd.item()),
                "precision_check": precision_check, "weights_mb": round(eng.weight_bytes() / 1e6, 1)}
+        out.update(extras)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()                 # every rank leaves together (rank 0 did the rank-local extras above)

@@ -40,7 +40,7 @@ __global__ void pool_max_mean_kernel(const float* __restrict__ y, int ldy, int N
 }
 
 struct EmbWs {
-    float *feat, *pq, *hA, *hB, *pooled; int32_t* idx;
+    float *feat, *pq, *hA, *hB, *pooled, *norms; int32_t* idx;
     int64_t total_bytes;
 };
 
@@ -56,6 +56,7 @@ EmbWs carve_emb_ws(const fc_embedder* e, int B, int Nc, void* base) {
     w.hB = (float*)take(M * 512 * 4);
     w.pooled = (float*)take((int64_t)B * 1024 * 4);
     w.idx = (int32_t*)take(M * e->k * 4);
+    w.norms = (float*)take(fc_knn_scratch_floats(B, Nc, Nc, true) * 4);
     w.total_bytes = off;
     return w;
 }
@@ -130,7 +131,7 @@ extern "C" int fc_embed(const fc_embedder* e, const float* pts, float* out, int 
         const int ldin = (i == 0) ? e->d_in : 512;
         int32_t* idx = knn_idx_out ? knn_idx_out + (size_t)i * M * e->k : w.idx;
         rc = fc_knn_launch(xin, ldin, (long long)Nc * ldin, xin, ldin, (long long)Nc * ldin, B, Nc, Nc, e->ec[i].Cin,
-                           e->k, 0, idx, nullptr, s);
+                           e->k, 0, idx, nullptr, w.norms, s);
         if (rc) return rc;
         // the kNN is bit-exact by contract and its input feeds a discrete decision, so the [P|Q] GEMM
         // always runs in exact fp32

@@ -1,190 +1,305 @@
-// Brute-force k-nearest-neighbour kernels: shared-memory tiled distances, warp-level top-k.
+// Brute-force k-nearest-neighbour kernels: register-tiled distances, one-thread-per-query selection.
 //
 // Replaces reference models/pytorch_gcn.py:13-20 (`knn`: bmm + materialised [B,N,N] matrix + topk)
-// and knn.py:40-52 (`KNN_torch_fun`).  Nothing of size N^2 is ever written: a CTA owns 32 queries,
-// streams 128-candidate tiles through shared memory, and every warp keeps the running top-k of its
-// 4 queries as a sorted list spread over its lanes (2 slots per lane, k <= 64).
+// and knn.py:40-52 (`KNN_torch_fun`).  Nothing of size N^2 is ever written.
 //
 // Arithmetic is the reference's algebraic form with a FIXED evaluation order (sequential fmaf over
 // the feature index), which oracle/knn_ref.c restates bit-for-bit:
 //   mode 0 (DGCNN):  key_ij = ((-xx_j) - (-2*dot_ij)) - xx_i          (k largest)
 //   mode 1 (knn.py): key_ij = -((qq_i + tt_j) - 2*dot_ij)             (k largest == k smallest diss)
-// Ties are broken by lower candidate index: candidates are visited in increasing index order and a
-// candidate only displaces entries with a strictly smaller key.
+// Ties are broken by lower candidate index.
+//
+// Shape of the kernel (round 2; the round-1 kernel -- 4x4 register tile, norms recomputed per tile, one warp-wide
+// ballot/shuffle insertion per candidate -- ran at 8 TFLOP/s, shared-memory-issue bound, ncu: profiles/r01_small_kernels_*):
+//   * the squared norms are computed ONCE per point by norms_kernel (same sequential fmaf order as before);
+//   * a CTA owns 64 queries and walks the candidates in tiles of 128; the 64 x 128 tile of dot products is accumulated
+//     in an 8 x 8 REGISTER tile per thread (128 threads): per feature step two broadcast and two contiguous LDS.128
+//     feed 64 FMAs (was 5 LDS per 16 FMAs); the next feature chunk is prefetched from global memory into registers
+//     while the current one is multiplied;
+//   * the keys of the tile go to shared memory and the selection is done by ONE THREAD PER QUERY (64 of the 128): it
+//     filters its row against the query's current k-th best (almost everything fails after the first tiles), compacts the
+//     survivors in place and insertion-sorts them into the query's sorted list in shared memory.  A warp-wide insertion
+//     spends 32 lanes on one candidate; this spends one, and 64 queries insert concurrently.
+// Two CTAs fit per SM (88 KB of shared memory each), so one CTA's selection phase overlaps the other's FMA phase.
 #include "common.cuh"
 #include "gemm.cuh"  // fc_count_launch
+#include <atomic>
+#include <mutex>
 
 namespace {
 
-constexpr int QT = 32;     // queries per CTA
-constexpr int CT = 128;    // candidates per tile
-constexpr int CK = 32;     // feature chunk
-constexpr int KNN_THREADS = 256;
+constexpr int TM = 64;      // queries per CTA
+constexpr int TN = 128;     // candidates per tile
+constexpr int CK = 16;      // feature chunk
+constexpr int KNN_THREADS = 128;
+constexpr int KS_LD = TN + 1;   // key tile row stride: the selecting thread r reads Ks[r][j] -> bank (r + j) % 32, conflict free
+constexpr int KNN_KMAX = 64;
 
-struct TopK {
-    float key[2];
-    int idx[2];
+// xx[b][i] = sum_c x[b][i][c]^2 with the canonical order (sequential fmaf over c)
+__global__ void norms_kernel(const float* __restrict__ x, int ld, long long bstride, int N, int C, float* __restrict__ xx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= N) return;
+    const float* p = x + (size_t)b * bstride + (size_t)i * ld;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(p[c], p[c], s);
+    xx[(size_t)b * N + i] = s;
+}
+
+struct KnnSmem {
+    float Qs[CK][TM];                 // query chunk, feature-major
+    float Cs[CK][TN];                 // candidate chunk, feature-major
+    float Ks[TM][KS_LD];              // keys of the current tile
+    unsigned char Js[TM][TN];         // compacted survivor columns of the current tile
+    float qn[TM];                     // query norms
+    float cn[TN];                     // candidate norms of the current tile
+    // followed by the final lists of the two column halves: Lk[TM][2][KCAP] keys, Li[TM][2][KCAP] indices
 };
 
-// insert (v, id) into the warp-distributed descending list; entry e lives in lane e%32, slot e/32
-__device__ __forceinline__ void topk_insert(TopK& t, float v, int id, int lane) {
-    const unsigned m0 = __ballot_sync(0xffffffffu, t.key[0] >= v);
-    const unsigned m1 = __ballot_sync(0xffffffffu, t.key[1] >= v);
-    const int p = __popc(m0) + __popc(m1);  // insertion position (entries are sorted, so these are prefixes)
-    // shifted copies: entry e takes the value of entry e-1
-    float k0 = __shfl_up_sync(0xffffffffu, t.key[0], 1);
-    int i0 = __shfl_up_sync(0xffffffffu, t.idx[0], 1);
-    float k1 = __shfl_up_sync(0xffffffffu, t.key[1], 1);
-    int i1 = __shfl_up_sync(0xffffffffu, t.idx[1], 1);
-    const float wrapk = __shfl_sync(0xffffffffu, t.key[0], 31);
-    const int wrapi = __shfl_sync(0xffffffffu, t.idx[0], 31);
-    if (lane == 0) { k1 = wrapk; i1 = wrapi; }
-    const int e0 = lane, e1 = lane + 32;
-    if (e0 == p) { t.key[0] = v; t.idx[0] = id; }
-    else if (e0 > p) { t.key[0] = k0; t.idx[0] = i0; }
-    if (e1 == p) { t.key[1] = v; t.idx[1] = id; }
-    else if (e1 > p) { t.key[1] = k1; t.idx[1] = i1; }
-}
-
-__device__ __forceinline__ float topk_threshold(const TopK& t, int k) {
-    const int e = k - 1;
-    const float v = (e < 32) ? t.key[0] : t.key[1];
-    return __shfl_sync(0xffffffffu, v, e & 31);
-}
-
 // q: [B][Nq][ldq], t: [B][Nt][ldt]; C features.  mode 0: self form; mode 1: query form.
-__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const float* __restrict__ q, int ldq, long long q_bstride,
-                                                           const float* __restrict__ t, int ldt, long long t_bstride,
-                                                           int Nq, int Nt, int C, int k, int mode,
-                                                           int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
-    __shared__ __align__(16) float Qs[CK][QT + 4];   // rows 16-byte aligned: a warp's 4 query values are one broadcast LDS.128
-    __shared__ float Cs[CK][CT + 1];
+//
+// Selection: TWO threads per query (thread r and r + 64 take columns [0,64) and [64,128) of every tile), each with its own
+// sorted top-KCAP list IN REGISTERS.  Per tile a thread filters its 64 keys against its current k-th best and compacts the
+// survivors in place (shared memory), then the warp inserts in lock step: insertion into the register list is branch free
+// (one compare-select pair per slot, no dependent chain, no dynamic indexing), so 32 queries insert at once at the cost of
+// ~5 instructions per slot.  (A sorted list in shared memory walked by one thread per query was tried first: bit-exact but
+// 2.7x SLOWER than the round-1 kernel -- every shift is a dependent shared-memory round trip and only 8 warps per SM were
+// there to hide it.)  The two half lists are merged once at the end under the total order (key desc, index asc).
+template <int KCAP>
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+knn_kernel(const float* __restrict__ q, int ldq, long long q_bstride, const float* __restrict__ t, int ldt,
+           long long t_bstride, const float* __restrict__ qnorm, const float* __restrict__ tnorm, int Nq, int Nt, int C, int k,
+           int mode, int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
+    extern __shared__ __align__(16) unsigned char knn_raw[];
+    KnnSmem& sm = *reinterpret_cast<KnnSmem*>(knn_raw);
+    float* Lk = reinterpret_cast<float*>(knn_raw + sizeof(KnnSmem));
+    int* Li = reinterpret_cast<int*>(Lk + TM * 2 * KCAP);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tx = tid & 15, ty = tid >> 4;        // 16 column groups x 8 row groups; thread tile: rows ty*8.., cols tx*4.. and 64+tx*4..
+    const int srow = tid & (TM - 1), shalf = tid >> 6;   // selection role: query row and column half
     const int b = blockIdx.y;
-    const int q0 = blockIdx.x * QT;
+    const int q0 = blockIdx.x * TM;
     const float* qb = q + (size_t)b * q_bstride;
     const float* tb = t + (size_t)b * t_bstride;
 
-    TopK top[4];
+    // sorted register lists: keys -inf, index 0 (a query whose keys are all NaN keeps index 0: valid addressing downstream)
+    float lkey[KCAP];
+    int lidx[KCAP];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        top[i].key[0] = -INFINITY; top[i].key[1] = -INFINITY;
-        top[i].idx[0] = -1; top[i].idx[1] = -1;
-    }
+    for (int p = 0; p < KCAP; ++p) { lkey[p] = -INFINITY; lidx[p] = 0; }
+    if (tid < TM) sm.qn[tid] = (q0 + tid < Nq) ? qnorm[(size_t)b * Nq + q0 + tid] : 0.f;
+    float thr = -INFINITY;     // this thread's current k-th best key
 
-    for (int j0 = 0; j0 < Nt; j0 += CT) {
-        float dot[4][4];
-        float xxq[4], xxc[4];
+    const int n_chunks = (C + CK - 1) / CK;
+    // staging map: a chunk is TM x CK query values and TN x CK candidate values; thread e handles element (p, c) = (e / CK, e % CK)
+    constexpr int Q_PER = TM * CK / KNN_THREADS;    // 8
+    constexpr int C_PER = TN * CK / KNN_THREADS;    // 16
+    float rq[Q_PER], rc[C_PER];
+    auto load_chunk = [&](int j0, int c0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            xxq[i] = 0.f; xxc[i] = 0.f;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) dot[i][s] = 0.f;
+        for (int i = 0; i < Q_PER; ++i) {
+            const int e = tid + i * KNN_THREADS, p = e / CK, c = e % CK;
+            rq[i] = (q0 + p < Nq && c0 + c < C) ? qb[(size_t)(q0 + p) * ldq + c0 + c] : 0.f;
         }
-        for (int c0 = 0; c0 < C; c0 += CK) {
-            __syncthreads();
-            // stage the query chunk [CK][QT] and candidate chunk [CK][CT] (zero fill out of range)
-            for (int e = tid; e < QT * CK; e += KNN_THREADS) {
-                const int p = e / CK, c = e % CK;
-                float v = 0.f;
-                if (q0 + p < Nq && c0 + c < C) v = qb[(size_t)(q0 + p) * ldq + c0 + c];
-                Qs[c][p] = v;
-            }
-            for (int e = tid; e < CT * CK; e += KNN_THREADS) {
-                const int p = e / CK, c = e % CK;
-                float v = 0.f;
-                if (j0 + p < Nt && c0 + c < C) v = tb[(size_t)(j0 + p) * ldt + c0 + c];
-                Cs[c][p] = v;
-            }
-            __syncthreads();
-            const int cmax = min(CK, C - c0);
-            for (int c = 0; c < cmax; ++c) {
-                float cv[4];
-                const float4 q4 = *reinterpret_cast<const float4*>(&Qs[c][warp * 4]);
-                const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-                for (int s = 0; s < 4; ++s) cv[s] = Cs[c][lane + 32 * s];
+        for (int i = 0; i < C_PER; ++i) {
+            const int e = tid + i * KNN_THREADS, p = e / CK, c = e % CK;
+            rc[i] = (j0 + p < Nt && c0 + c < C) ? tb[(size_t)(j0 + p) * ldt + c0 + c] : 0.f;
+        }
+    };
+    auto store_chunk = [&]() {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    xxq[i] = fmaf(qv[i], qv[i], xxq[i]);
+        for (int i = 0; i < Q_PER; ++i) { const int e = tid + i * KNN_THREADS; sm.Qs[e % CK][e / CK] = rq[i]; }
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) dot[i][s] = fmaf(qv[i], cv[s], dot[i][s]);
+        for (int i = 0; i < C_PER; ++i) { const int e = tid + i * KNN_THREADS; sm.Cs[e % CK][e / CK] = rc[i]; }
+    };
+
+    for (int j0 = 0; j0 < Nt; j0 += TN) {
+        {
+            float dot[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dot[i][j] = 0.f;
+            load_chunk(j0, 0);
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                __syncthreads();                       // everyone is done with the previous chunk (and the previous tile's selection)
+                store_chunk();
+                if (ch == 0 && tid < TN) sm.cn[tid] = (j0 + tid < Nt) ? tnorm[(size_t)b * Nt + j0 + tid] : 0.f;
+                __syncthreads();
+                if (ch + 1 < n_chunks) load_chunk(j0, (ch + 1) * CK);      // prefetch while multiplying
+                const int cmax = min(CK, C - ch * CK);
+#pragma unroll 4
+                for (int c = 0; c < cmax; ++c) {
+                    const float4 qa = *reinterpret_cast<const float4*>(&sm.Qs[c][ty * 8]);
+                    const float4 qb4 = *reinterpret_cast<const float4*>(&sm.Qs[c][ty * 8 + 4]);
+                    const float4 ca = *reinterpret_cast<const float4*>(&sm.Cs[c][tx * 4]);
+                    const float4 cb = *reinterpret_cast<const float4*>(&sm.Cs[c][64 + tx * 4]);
+                    const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb4.x, qb4.y, qb4.z, qb4.w};
+                    const float cv[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dot[i][j] = fmaf(qv[i], cv[j], dot[i][j]);
                 }
+            }
+            // keys -> shared memory (Ks is only read by the selection below, after the barrier)
 #pragma unroll
-                for (int s = 0; s < 4; ++s) xxc[s] = fmaf(cv[s], cv[s], xxc[s]);
+            for (int i = 0; i < 8; ++i) {
+                const int r = ty * 8 + i;
+                const float xq = sm.qn[r];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                    const float xc = sm.cn[col];
+                    float key;
+                    if (mode == 0) key = __fsub_rn(__fsub_rn(-xc, -2.0f * dot[i][j]), xq);
+                    else           key = -__fsub_rn(__fadd_rn(xq, xc), 2.0f * dot[i][j]);
+                    if (j0 + col >= Nt) key = -INFINITY;
+                    sm.Ks[r][col] = key;
+                }
             }
         }
-        // selection: warp owns queries warp*4 .. +3; lane holds candidates j0 + lane + 32*s
+        __syncthreads();
+        {
+            // filter + compact in place (cnt <= j, so the write never overtakes the read); candidates stay in index order
+            float* row = &sm.Ks[srow][shalf * 64];
+            unsigned char* jr = &sm.Js[srow][shalf * 64];
+            int cnt = 0;
+#pragma unroll 8
+            for (int j = 0; j < 64; ++j) {
+                const float v = row[j];
+                if (v > thr) { row[cnt] = v; jr[cnt] = (unsigned char)j; ++cnt; }
+            }
+            const int mx = __reduce_max_sync(0xffffffffu, cnt);
+            for (int i = 0; i < mx; ++i) {
+                float v = -INFINITY;
+                int id = 0;
+                if (i < cnt) { v = row[i]; id = j0 + shalf * 64 + jr[i]; }
+                if (!(v > thr)) v = -INFINITY;                     // the k-th best may have risen since the filter
+                if (__any_sync(0xffffffffu, v > thr)) {
+                    // branch-free insertion: slot p takes its upper neighbour if that one is smaller than v (shift down), else v if
+                    // the slot itself is smaller (insertion point), else stays.  Strict <: an equal key with a lower index stays ahead.
+                    // v = -inf changes nothing.
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float thr = topk_threshold(top[i], k);
+                    for (int p = KCAP - 1; p >= 1; --p) {
+                        const bool up = lkey[p - 1] < v, here = lkey[p] < v;
+                        lidx[p] = up ? lidx[p - 1] : (here ? id : lidx[p]);
+                        lkey[p] = up ? lkey[p - 1] : (here ? v : lkey[p]);
+                    }
+                    if (lkey[0] < v) { lkey[0] = v; lidx[0] = id; }
+                    if (k == KCAP) thr = lkey[KCAP - 1];       // the usual case (DGCNN: k = 40): no dependent select chain
+                    else {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const int j = j0 + lane + 32 * s;
-                float key;
-                if (mode == 0) {
-                    const float inner = -2.0f * dot[i][s];
-                    key = __fsub_rn(__fsub_rn(-xxc[s], inner), xxq[i]);
-                } else {
-                    key = -__fsub_rn(__fadd_rn(xxq[i], xxc[s]), 2.0f * dot[i][s]);
-                }
-                if (j >= Nt) key = -INFINITY;
-                unsigned m = __ballot_sync(0xffffffffu, key > thr);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float v = __shfl_sync(0xffffffffu, key, src);
-                    if (v > thr) {  // thr may have risen since the ballot
-                        topk_insert(top[i], v, j0 + src + 32 * s, lane);
-                        thr = topk_threshold(top[i], k);
+                        for (int p = 0; p < KCAP; ++p) if (p == k - 1) thr = lkey[p];
                     }
                 }
             }
         }
+        // the next tile's first barrier orders this selection before Ks / cn are overwritten
     }
+    // merge the two half lists of every query under (key desc, index asc)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int qi = q0 + warp * 4 + i;
-        if (qi >= Nq) continue;
-        const size_t base = ((size_t)b * Nq + qi) * k;
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-            const int e = lane + 32 * sl;
-            if (e < k) {
-                if (idx32) idx32[base + e] = top[i].idx[sl];
-                if (idx64) idx64[base + e] = (int64_t)top[i].idx[sl];
-            }
+    for (int p = 0; p < KCAP; ++p) { Lk[(srow * 2 + shalf) * KCAP + p] = lkey[p]; Li[(srow * 2 + shalf) * KCAP + p] = lidx[p]; }
+    __syncthreads();
+    if (tid < TM && q0 + tid < Nq) {
+        const float* ka = Lk + (tid * 2) * KCAP; const float* kb = ka + KCAP;
+        const int* ia = Li + (tid * 2) * KCAP; const int* ib = ia + KCAP;
+        const size_t o = ((size_t)b * Nq + q0 + tid) * k;
+        int i = 0, j = 0;
+        for (int p = 0; p < k; ++p) {
+            const bool take_a = (i < k) && (j >= k || ka[i] > kb[j] || (ka[i] == kb[j] && ia[i] <= ib[j]));
+            const int v = take_a ? ia[i] : ib[j];
+            if (take_a) ++i; else ++j;
+            if (idx32) idx32[o + p] = v;
+            if (idx64) idx64[o + p] = (int64_t)v;
         }
     }
 }
 
+template <int KCAP, typename... Args>
+cudaError_t launch_knn(int dev, dim3 grid, cudaStream_t stream, Args... args) {
+    const size_t smem = sizeof(KnnSmem) + (size_t)TM * 2 * KCAP * 8;
+    static std::atomic<uint64_t> configured{0};    // the dynamic shared-memory opt-in is per device (and per instantiation)
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(knn_kernel<KCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    knn_kernel<KCAP><<<grid, KNN_THREADS, smem, stream>>>(args...);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
+int64_t fc_knn_scratch_floats(int B, int Nq, int Nt, bool self) {
+    return (int64_t)B * (self ? Nt : Nq + Nt);
+}
+
 int fc_knn_launch(const float* q, int ldq, long long q_bstride, const float* t, int ldt, long long t_bstride,
-                  int B, int Nq, int Nt, int C, int k, int mode, int32_t* idx32, int64_t* idx64,
+                  int B, int Nq, int Nt, int C, int k, int mode, int32_t* idx32, int64_t* idx64, float* norms_scratch,
                   cudaStream_t stream) {
-    FC_REQUIRE(q && t && B > 0 && Nq > 0 && Nt > 0 && C > 0);
-    FC_REQUIRE(k >= 1 && k <= 64 && k <= Nt);
+    FC_REQUIRE(q && t && B > 0 && Nq > 0 && Nt > 0 && C > 0 && norms_scratch);
+    FC_REQUIRE(k >= 1 && k <= KNN_KMAX && k <= Nt);
     FC_REQUIRE(B <= 65535);
     FC_REQUIRE(idx32 || idx64);
-    dim3 grid((Nq + QT - 1) / QT, B);
+    const bool self = (q == t && ldq == ldt && q_bstride == t_bstride && Nq == Nt);
+    float* tn = norms_scratch;
+    float* qn = self ? tn : norms_scratch + (size_t)B * Nt;
     FcProfScope prof(FC_CLS_KNN, 2.0 * B * (double)Nq * Nt * C,
-                     4.0 * B * ((double)(q == t ? Nt : Nq + Nt) * C + (double)Nq * k), stream);
-    knn_kernel<<<grid, KNN_THREADS, 0, stream>>>(q, ldq, q_bstride, t, ldt, t_bstride, Nq, Nt, C, k, mode, idx32, idx64);
+                     4.0 * B * ((double)(self ? Nt : Nq + Nt) * C + (double)Nq * k), stream);
+    norms_kernel<<<dim3((Nt + 255) / 256, B), 256, 0, stream>>>(t, ldt, t_bstride, Nt, C, tn);
+    fc_count_launch();
+    if (!self) { norms_kernel<<<dim3((Nq + 255) / 256, B), 256, 0, stream>>>(q, ldq, q_bstride, Nq, C, qn); fc_count_launch(); }
+    int dev = 0;
+    FC_CUDA_OK(cudaGetDevice(&dev));
+    dim3 grid((Nq + TM - 1) / TM, B);
+    cudaError_t le;
+    if (k <= 16)      le = launch_knn<16>(dev, grid, stream, q, ldq, q_bstride, t, ldt, t_bstride, qn, tn, Nq, Nt, C, k, mode, idx32, idx64);
+    else if (k <= 32) le = launch_knn<32>(dev, grid, stream, q, ldq, q_bstride, t, ldt, t_bstride, qn, tn, Nq, Nt, C, k, mode, idx32, idx64);
+    else if (k <= 40) le = launch_knn<40>(dev, grid, stream, q, ldq, q_bstride, t, ldt, t_bstride, qn, tn, Nq, Nt, C, k, mode, idx32, idx64);
+    else              le = launch_knn<64>(dev, grid, stream, q, ldq, q_bstride, t, ldt, t_bstride, qn, tn, Nq, Nt, C, k, mode, idx32, idx64);
+    FC_CUDA_OK(le);
     fc_count_launch();
     FC_LAUNCH_OK();
     return FC_OK;
 }
 
+// The op-level entry points own no workspace argument in the C ABI of round 1 (include/flowcompare_b200.h): the norms (4 bytes
+// per point) are kept in a small per-device scratch that grows on demand and is reused by later calls on the same device.
+namespace {
+struct NormScratch { float* p = nullptr; int64_t floats = 0; };
+NormScratch g_norms[64];
+std::mutex g_norms_mu;
+float* norms_for(int64_t floats, cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(g_norms_mu);
+    NormScratch& s = g_norms[dev & 63];
+    if (s.floats < floats) {
+        if (s.p) { cudaStreamSynchronize(stream); cudaFree(s.p); s.p = nullptr; s.floats = 0; }
+        if (cudaMalloc(&s.p, (size_t)floats * 4) != cudaSuccess) return nullptr;
+        s.floats = floats;
+    }
+    return s.p;
+}
+}  // namespace
+
 extern "C" int fc_knn_self(const float* x, int ldx, int B, int N, int C, int k, int32_t* idx32, int64_t* idx64,
                            fc_stream_t stream) {
-    FC_REQUIRE(ldx >= C);
-    return fc_knn_launch(x, ldx, (long long)N * ldx, x, ldx, (long long)N * ldx, B, N, N, C, k, 0, idx32, idx64,
+    FC_REQUIRE(x && ldx >= C && B > 0 && N > 0 && C > 0 && k >= 1 && k <= KNN_KMAX && k <= N && (idx32 || idx64));   // before any GPU work
+    float* scratch = norms_for(fc_knn_scratch_floats(B, N, N, true), (cudaStream_t)stream);
+    if (!scratch) return FC_ERR_CUDA;
+    return fc_knn_launch(x, ldx, (long long)N * ldx, x, ldx, (long long)N * ldx, B, N, N, C, k, 0, idx32, idx64, scratch,
                          (cudaStream_t)stream);
 }
 
 extern "C" int fc_knn_query(const float* q, const float* t, int Nq, int Nt, int D, int k, int64_t* idx64,
                             fc_stream_t stream) {
-    return fc_knn_launch(q, D, 0, t, D, 0, 1, Nq, Nt, D, k, 1, nullptr, idx64, (cudaStream_t)stream);
+    FC_REQUIRE(q && t && idx64 && Nq > 0 && Nt > 0 && D > 0 && k >= 1 && k <= KNN_KMAX && k <= Nt);   // before any GPU work
+    float* scratch = norms_for(fc_knn_scratch_floats(1, Nq, Nt, false), (cudaStream_t)stream);
+    if (!scratch) return FC_ERR_CUDA;
+    return fc_knn_launch(q, D, 0, t, D, 0, 1, Nq, Nt, D, k, 1, nullptr, idx64, scratch, (cudaStream_t)stream);
 }

@@ -125,8 +125,9 @@ int fc_launch_cross_attention_tc(const float* q, int ldq, const float* kv, int l
 int fc_launch_edgeconv_gather_max(const float* PQ, int ldpq, const int32_t* idx, int B, int N, int k, int Cout,
                                   float* out, int ldo, cudaStream_t stream);
 int fc_knn_launch(const float* q, int ldq, long long q_bstride, const float* t, int ldt, long long t_bstride,
-                  int B, int Nq, int Nt, int C, int k, int mode, int32_t* idx32, int64_t* idx64,
+                  int B, int Nq, int Nt, int C, int k, int mode, int32_t* idx32, int64_t* idx64, float* norms_scratch,
                   cudaStream_t stream);
+int64_t fc_knn_scratch_floats(int B, int Nq, int Nt, bool self);   // floats of `norms_scratch` (squared norms of the points)
 
 // runs in/hidden layers of an MLP; returns the buffer holding the last hidden activation.
 // bufA/bufB: [M][ldh] scratch (ldh >= hidden width).  `in_bias`/group override the in-layer bias.

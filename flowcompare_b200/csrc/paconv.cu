@@ -34,9 +34,10 @@ struct PaModel {
     int c_feat;       // input feature channels (input_dim - 3)
 };
 
+// the contraction nvcc applies to the reference's `dx*dx + dy*dy + dz*dz` (read off the SASS of its kernels: FMUL dy*dy, FFMA dx, FFMA dz)
 __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
     const float dx = ax - bx, dy = ay - by, dz = az - bz;
-    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 // pts [B,N,d_in] -> xyz [B,N,3], feat [B,N,ldf] (first c columns)
@@ -312,7 +313,9 @@ __global__ void interp_concat_kernel(const float* __restrict__ known_feat, int l
         const long long b = p / n;
         const float* kf = known_feat + (size_t)b * m * ldk + c;
         const int32_t* ix = idx + p * 3; const float* ww = w + p * 3;
-        v = fmaf(ww[2], kf[(size_t)ix[2] * ldk], fmaf(ww[1], kf[(size_t)ix[1] * ldk], ww[0] * kf[(size_t)ix[0] * ldk]));
+        // the contraction nvcc applies to the reference's `w0*p0 + w1*p1 + w2*p2` (interpolation_cuda_kernel.cu:194): the first product is
+        // fused into the second's rounded value, then the third is fused on top
+        v = fmaf(ww[2], kf[(size_t)ix[2] * ldk], fmaf(ww[0], kf[(size_t)ix[0] * ldk], ww[1] * kf[(size_t)ix[1] * ldk]));
     } else {
         v = unk_feat[(size_t)p * ldu + (c - C2)];
     }

@@ -48,8 +48,9 @@ def knnquery_heap(nsample, xyz, new_xyz=None, return_dist2=False):
     return (idx, d2) if return_dist2 else idx
 
 
-def nearestneighbor(unknown, known):
-    """`nearestneighbor(unknown, known)` (pointops.py:96-115): -> (dist [B,n,3] = sqrt of the squared distances, idx [B,n,3])."""
+def nearestneighbor(unknown, known, squared=False):
+    """`nearestneighbor(unknown, known)` (pointops.py:96-115): -> (dist [B,n,3] = sqrt of the squared distances, idx [B,n,3]);
+    squared=True returns the kernel's squared distances instead (what the reference's CUDA kernel itself writes)."""
     lib = _lib.load()
     unknown, known = _f32(unknown), _f32(known)
     B, n, _ = unknown.shape
@@ -59,7 +60,7 @@ def nearestneighbor(unknown, known):
     with torch.cuda.device(unknown.device):
         _lib.check(lib.fc_three_nn(unknown.data_ptr(), known.data_ptr(), B, n, m, d2.data_ptr(), idx.data_ptr(), _stream()),
                    "fc_three_nn")
-    return torch.sqrt(d2), idx
+    return (d2 if squared else torch.sqrt(d2)), idx
 
 
 def interpolation(features, idx, weight):

@@ -6,16 +6,18 @@
  *   K5 three nearest neighbours  lib/pointops/src/interpolation/interpolation_cuda_kernel.cu:134-176
  * including their tie behaviour (strict comparisons, heap order, block-strided arg-max), so that the CUDA
  * kernels in flowcompare_b200/csrc/paconv.cu can be checked bit-for-bit.  Distances use the contraction nvcc
- * applies to `dx*dx + dy*dy + dz*dz` (fmaf(dz,dz,fmaf(dy,dy,dx*dx))).  "parity unpinned" against the
- * reference's compiled kernels (not runnable); pinned against the reference's PYTHON modules above them through
- * oracle/port_paconv.py + tests/golden/*paconv*.pt.                                                         */
+ * applies to `dx*dx + dy*dy + dz*dz`: fmaf(dz, dz, fmaf(dx, dx, dy*dy)) -- read off the SASS of the reference's own
+ * kernels compiled for sm_100a (FMUL dy*dy; FFMA dx,dx; FFMA dz,dz in all three).  Pinned: on a GPU box
+ * tests/test_pointops_gpu.py compares the CUDA kernels AND this restatement with the reference's compiled kernels
+ * (oracle/_ref/libpointops_ref.so, built by oracle/build_ref_pointops.sh from the reference's unmodified sources),
+ * indices and distances bit for bit, including clouds with exact duplicate points.                              */
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 
 static float sqdist3(const float* a, const float* b) {
     const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
-    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 /* threads per block the reference launcher picks: 2^floor(log2 n) via double log, clipped to [1,1024] */

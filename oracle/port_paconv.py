@@ -89,7 +89,18 @@ def interpolation(features, idx, weight):
     n = idx.shape[1]
     g = torch.gather(features, 2, idx.long().reshape(B, 1, n * 3).expand(-1, C, -1)).reshape(B, C, n, 3)
     w = weight.unsqueeze(1)
-    return (w[..., 0] * g[..., 0] + w[..., 1] * g[..., 1]) + w[..., 2] * g[..., 2]
+    return _fma3(w[..., 0], g[..., 0], w[..., 1], g[..., 1], w[..., 2], g[..., 2])
+
+
+def _fma3(w0, p0, w1, p1, w2, p2):
+    """`w0*p0 + w1*p1 + w2*p2` as the reference's compiled kernel evaluates it (interpolation_cuda_kernel.cu:194, SASS:
+    FMUL w1*p1; FFMA w0,p0; FFMA w2,p2).  fp32 inputs: each fused step is emulated through float64, where the product of two
+    floats is exact, so only the (rare) double rounding of the sum can differ; other dtypes use the plain expression."""
+    if w0.dtype != torch.float32:
+        return (w0 * p0 + w1 * p1) + w2 * p2
+    t = (w1 * p1).double()
+    t = (w0.double() * p0.double() + t).float().double()
+    return (w2.double() * p2.double() + t).float()
 
 
 def patch_reference_pointops():
@@ -150,7 +161,7 @@ def fp_module(sd, i, unknown, known, unknown_feats, known_feats):
     w = w / w.sum(dim=2, keepdim=True)
     g = torch.gather(known_feats, 1, idx.long().reshape(idx.shape[0], -1, 1).expand(-1, -1, known_feats.shape[-1]))
     g = g.reshape(idx.shape[0], idx.shape[1], 3, -1)
-    interp = (w[..., 0:1] * g[:, :, 0] + w[..., 1:2] * g[:, :, 1]) + w[..., 2:3] * g[:, :, 2]
+    interp = _fma3(w[..., 0:1], g[:, :, 0], w[..., 1:2], g[:, :, 1], w[..., 2:3], g[:, :, 2])
     f = torch.cat((interp, unknown_feats), dim=-1)
     j = 0
     while f"FP_modules.{i}.mlp.layer{j}.conv.weight" in sd:

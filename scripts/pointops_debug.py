@@ -22,3 +22,18 @@ print("fps dup ours vs ref", torch.equal(f1, f2), "first mismatch", (f1 != f2).n
 if not torch.equal(f1, f2):
     j = (f1 != f2).nonzero()[0]
     print("  at", j.tolist(), "ours", f1[j[0], j[1]].item(), "ref", f2[j[0], j[1]].item())
+print("---- fps determinism / tie rule")
+g = torch.Generator().manual_seed(1250 + 312)
+xx = torch.rand(2, 1250, 3, generator=g) * 2 - 1
+xx[:, 625:] = xx[:, :625]
+xx = xx.contiguous()
+w = port_paconv.furthestsampling(xx, 312)
+xc = xx.cuda()
+for rep in range(3):
+    a = fpo.furthestsampling(xc, 312).cpu(); b = ref.furthestsampling(xc, 312).cpu()
+    print(rep, "ours==cpu", torch.equal(a, w), "ref==cpu", torch.equal(b, w), "ours[0,:8]", a[0, :8].tolist(), "ref[0,:8]", b[0, :8].tolist(), "cpu", w[0, :8].tolist())
+a1 = fpo.furthestsampling(xc[:1].contiguous(), 312).cpu()
+print("B=1 ours==cpu", torch.equal(a1, w[:1]))
+for tb in (1024, 512, 2048, -1):
+    a = fpo.furthestsampling(xc, 312, tie_block=tb).cpu()
+    print("tie_block", tb, a[0, :8].tolist())

@@ -102,17 +102,17 @@ def test_three_nn_bit_exact_vs_reference_kernel(B, n, m, dup):
     u = _cloud(B, n, n + 7 * m, dup).to(DEV)
     kn = u[:, :m].contiguous() if dup else _cloud(B, m, m, False).to(DEV)
     want_d2, want_idx = ref.nearestneighbor(u, kn)
-    got_d, got_idx = fpo.nearestneighbor(u, kn)
+    got_d2, got_idx = fpo.nearestneighbor(u, kn, squared=True)
     assert torch.equal(got_idx, want_idx)
-    assert torch.equal(got_d, torch.sqrt(want_d2))
+    assert torch.equal(got_d2, want_d2)
 
 
 @pytest.mark.parametrize("B,n,m,dup", NN_CASES[:3])
 def test_three_nn_matches_cpu_restatement(B, n, m, dup):
     u, kn = _cloud(B, n, n + 7 * m), _cloud(B, m, m)
     d, i = port_paconv.nearestneighbor(u, kn)
-    gd, gi = fpo.nearestneighbor(u.to(DEV), kn.to(DEV))
-    assert torch.equal(gi.cpu(), i) and torch.equal(gd.cpu(), d)
+    gd2, gi = fpo.nearestneighbor(u.to(DEV), kn.to(DEV), squared=True)
+    assert torch.equal(gi.cpu(), i) and torch.equal(torch.sqrt(gd2.cpu()), d)    # same sqrt implementation on both sides
 
 
 @needs_ref
