@@ -82,6 +82,9 @@ constexpr int TC_STAGES = 5;                   // shared-memory stages: a load i
 #ifndef TC_CONV_WARPS
 #define TC_CONV_WARPS 8                        // 4: one converter thread per tile row; 8: two (one per half k-block; measured +10 % in 3xFP16 mode)
 #endif
+#ifndef TC_WARP_ARRIVE
+#define TC_WARP_ARRIVE 1                       // converter / epilogue warps arrive on their mbarriers ONCE PER WARP (lane 0 after a
+#endif                                         // __syncwarp) instead of once per thread: 8 arrivals per barrier phase instead of 256
 constexpr int TC_CONV_WARPS_N = TC_CONV_WARPS;
 static_assert(TC_CONV_WARPS_N == 4 || TC_CONV_WARPS_N == 8, "converter warps: 4 or 8");
 constexpr int TC_EPI_WARP0 = 2 + TC_CONV_WARPS_N;             // first epilogue warp (a multiple of 2 past a multiple of 4: TMEM quadrants line up)
@@ -169,6 +172,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     uint64_t* acc_free = acc_full + 2;                            // [2] epilogue has drained them (256 arrivals)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // One arrival per warp: every lane has finished (and fenced) its part, __syncwarp orders the lanes, lane 0 arrives with
+    // release semantics for all of them.  256 per-thread arrivals on one mbarrier serialise in the shared-memory atomic unit.
+    auto warp_arrive = [&](uint64_t* bar) {
+        if (TC_WARP_ARRIVE) { __syncwarp(); if (lane == 0) mbar_arrive(bar); }
+        else mbar_arrive(bar);
+    };
     const int T = p.T1 + p.T2;
     const int n_tiles = p.n_tiles, total_tiles = p.n_tiles * p.m_tiles;
     // N is cut into n_tiles tiles whose widths are multiples of 16 and differ by at most 16 (512 -> 96,96,80,80,80,80):
@@ -178,9 +187,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     auto tile_bn_of = [&](int nt) { return 16 * (n_base + (nt < n_rem ? 1 : 0)); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], 32 * TC_CONV_WARPS_N); mbar_init(&w_free[s], 1); }
-        for (int s = 0; s < TC_TSTAGES / 2; ++s) { mbar_init(&conv[s], 256); mbar_init(&tfree[s], 1); }   // one pair per K-BLOCK of A in tensor memory
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 256); }
+        constexpr int PER_WARP = TC_WARP_ARRIVE ? 1 : 32;   // arrivals a warp contributes per event
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], PER_WARP * TC_CONV_WARPS_N); mbar_init(&w_free[s], 1); }
+        for (int s = 0; s < TC_TSTAGES / 2; ++s) { mbar_init(&conv[s], PER_WARP * 8); mbar_init(&tfree[s], 1); }   // one pair per K-BLOCK of A in tensor memory
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], PER_WARP * 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -339,7 +349,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 if (pending >= 0) {      // never hold a finished stage back while waiting for the next k-block's data
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&conv[pending]);
+                    warp_arrive(&conv[pending]);
                     pending = -1;
                 }
                 TC_T(cf0);
@@ -381,11 +391,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                             }
                         }
                     }
-                    if (h == 1 || TC_CONV_WARPS_N == 8) mbar_arrive(&a_free[s]);   // this thread's part of the row is in registers: the A smem stage may be refilled
+                    if (h == 1 || TC_CONV_WARPS_N == 8) warp_arrive(&a_free[s]);   // this thread's part of the row is in registers: the A smem stage may be refilled
                     if (pending >= 0) {
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        mbar_arrive(&conv[pending]);
+                        warp_arrive(&conv[pending]);
                     }
                     if (h == 0 || TC_CONV_WARPS_N == 8) {   // once per k-block: the MMAs that read this TMEM stage have retired
                         TC_T(ct0);
@@ -407,7 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         if (pending >= 0) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&conv[pending]);
+            warp_arrive(&conv[pending]);
         }
 #if TC_PHASE_TIMERS
         if (threadIdx.x == 64) {
@@ -699,7 +709,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             }
             // this thread's TMEM reads of the tile are complete (every tcgen05.ld above is followed by its wait)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acc_free[buf]);
+            warp_arrive(&acc_free[buf]);
         }
 #if TC_PHASE_TIMERS
         if (threadIdx.x == 32 * TC_EPI_WARP0) {

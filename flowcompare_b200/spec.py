@@ -43,44 +43,91 @@ def _attn_shapes(prefix, cfg, out):
     out[f"{prefix}.norm.bias"] = (cfg["attn_input_dim"],)
 
 
+def _coupling_shapes(p, cfg, D, ex, out):
+    """PreConditionApplier(flow_type, CouplingPreconditionerAttn | Global): reference models/cif_block.py:42-46,
+    model_initialization.py:95-108 (parameters of a module precede those of its sub-modules)."""
+    half = D // 2
+    if not cfg["global"]:
+        _attn_shapes(f"{p}.pre_conditioner.attn", cfg, out)
+        _mlp_shapes(f"{p}.pre_conditioner.pre_attention_mlp", half,
+                    cfg["pre_attention_mlp_hidden_dims"], cfg["attn_input_dim"], out)
+        ctx_dim = cfg["attn_dim"] + ex
+    else:
+        ctx_dim = cfg["input_embedding_dim"] + ex
+    kind = cfg["flow_type"]
+    if kind == "AffineCoupling":                       # models/affine_coupling.py:17
+        out_dim = (D - half) * 2
+    elif kind == "RationalQuadraticSplineCoupling":    # models/spline_coupling.py:179
+        out_dim = (cfg["num_bins_spline"] * 3 + 1) * half
+    else:                                              # models/exponential_coupling.py:22-31
+        for leaf in ("scale", "shift", "rescale", "reshift"):
+            out[f"{p}.transform.{leaf}"] = (1,)
+        out_dim = (D - half) ** 2 + (D - half)
+    _mlp_shapes(f"{p}.transform.nn", half + ctx_dim, cfg["hidden_dims"], out_dim, out)
+
+
+def _cif_shapes(p, cfg, out):
+    """CIFblock, reference models/cif_block.py:50-68 (registration order; augmenter and slicer share ONE net)."""
+    D, D2 = cfg["latent_dim"], cfg["cif_latent_dim"]
+    S = D2 - D
+    out[f"{p}.act_norm.shift"] = (1, D2)
+    out[f"{p}.act_norm.log_scale"] = (1, D2)
+    out[f"{p}.act_norm.initialized"] = (1,)
+    _mlp_shapes(f"{p}.augmenter.noise_dist.net", D, cfg["net_cif_dist_hidden_dims"], S * 2, out)
+    _mlp_shapes(f"{p}.affine_cif.nn", S, cfg["affine_cif_hidden"], D * 2, out)
+    _coupling_shapes(f"{p}.flow", cfg, D, 0, out)
+    _mlp_shapes(f"{p}.slicer.noise_dist.net", D, cfg["net_cif_dist_hidden_dims"], S * 2, out)
+    out[f"{p}.reverse.permutation"] = (D2,)
+    out[f"{p}.reverse.inv_permutation"] = (D2,)
+
+
 def flow_param_shapes(config) -> "OrderedDict[str, tuple]":
     """Key -> shape of `models_dict['flow'].state_dict()` for the supported architectures."""
     cfg = derive(config)
     _check_supported(cfg)
     D, d_in, ex = cfg["latent_dim"], cfg["input_dim"], cfg["extra_context_dim"]
-    half = D // 2
     out = OrderedDict()
     out["base_dist.buffer"] = (1,)
     out["sample_dist.loc"] = (1,)
     out["sample_dist.scale"] = (1,)
     out["sample_dist.std_normal.buffer"] = (1,)
-    # transforms.0 = AugmentAttentionPreconditioner (model_initialization.py:73-81)
-    _mlp_shapes("transforms.0.augment.noise_dist.net", cfg["attn_dim"] + d_in + ex,
-                cfg["net_augmenter_dist_hidden_dims"], (D - d_in) * 2, out)
-    _attn_shapes("transforms.0.attn", cfg, out)
-    _mlp_shapes("transforms.0.pre_attn_mlp", d_in, cfg["hidden_dims"], cfg["attn_input_dim"], out)
+    if D > d_in:
+        # transforms.0 = AugmentAttentionPreconditioner (model_initialization.py:73-81); latent_dim == input_dim makes it
+        # an IdentityTransform without parameters (:93-94)
+        _mlp_shapes("transforms.0.augment.noise_dist.net", cfg["attn_dim"] + d_in + ex,
+                    cfg["net_augmenter_dist_hidden_dims"], (D - d_in) * 2, out)
+        _attn_shapes("transforms.0.attn", cfg, out)
+        _mlp_shapes("transforms.0.pre_attn_mlp", d_in, cfg["hidden_dims"], cfg["attn_input_dim"], out)
     L = cfg["n_flow_layers"]
+    cif = D < cfg["cif_latent_dim"]
     t = 1
     for layer in range(L):
         p = f"transforms.{t}"
-        if not cfg["global"]:
-            _attn_shapes(f"{p}.pre_conditioner.attn", cfg, out)
-            _mlp_shapes(f"{p}.pre_conditioner.pre_attention_mlp", half,
-                        cfg["pre_attention_mlp_hidden_dims"], cfg["attn_input_dim"], out)
-            ctx_dim = cfg["attn_dim"] + ex
+        if cif:
+            _cif_shapes(p, cfg, out)
         else:
-            ctx_dim = cfg["input_embedding_dim"] + ex
-        _mlp_shapes(f"{p}.transform.nn", half + ctx_dim, cfg["hidden_dims"], (D - half) * 2, out)
+            _coupling_shapes(p, cfg, D, ex, out)
         t += 1
         if layer != L - 1:
-            out[f"transforms.{t}.shift"] = (1, D)
-            out[f"transforms.{t}.log_scale"] = (1, D)
-            out[f"transforms.{t}.initialized"] = (1,)
-            t += 1
-            ntri = (D - 1) * D // 2
-            out[f"transforms.{t}.lower_entries"] = (ntri,)
-            out[f"transforms.{t}.upper_entries"] = (ntri,)
-            out[f"transforms.{t}.unconstrained_upper_diag"] = (D,)
+            if cfg["act_norm"]:
+                out[f"transforms.{t}.shift"] = (1, D)
+                out[f"transforms.{t}.log_scale"] = (1, D)
+                out[f"transforms.{t}.initialized"] = (1,)
+                t += 1
+            kind = cfg["permuter_type"]
+            if kind == "LinearLU":
+                ntri = (D - 1) * D // 2
+                out[f"transforms.{t}.lower_entries"] = (ntri,)
+                out[f"transforms.{t}.upper_entries"] = (ntri,)
+                out[f"transforms.{t}.unconstrained_upper_diag"] = (D,)
+            elif kind == "random_permute":
+                out[f"transforms.{t}.permutation"] = (D,)
+                out[f"transforms.{t}.inv_permutation"] = (D,)
+            else:   # FullCombiner / ExponentialCombiner (models/permuters.py:15-52)
+                out[f"transforms.{t}.w"] = (D, D)
+                if kind == "ExponentialCombiner":
+                    for leaf in ("scale", "shift", "rescale", "reshift"):
+                        out[f"transforms.{t}.{leaf}"] = (1,)
             t += 1
     return out
 
@@ -124,19 +171,26 @@ def _bn_shapes(prefix, c, out):
 
 
 def _check_supported(cfg):
-    if cfg["flow_type"] != "AffineCoupling" or cfg["affine_scale_fn"] != "sigmoid":
-        raise NotImplementedError("only AffineCoupling/sigmoid (all shipped configs) is built so far")
-    if cfg["permuter_type"] != "LinearLU" or not cfg["act_norm"]:
-        raise NotImplementedError("only ActNorm + LinearLU (all shipped configs) is built so far")
-    if cfg["latent_dim"] != cfg["cif_latent_dim"]:
-        raise NotImplementedError("CIF block (latent_dim < cif_latent_dim) is not built yet")
-    if cfg["augmenter_dist"] != "ConditionalNormal" or not cfg["use_attn_augment"]:
-        raise NotImplementedError("only the attention-conditioned ConditionalNormal augmenter is built so far")
-    if cfg["coupling_block_nonlinearity"] != "GELU":
-        raise NotImplementedError("only GELU conditioners (all shipped configs) are built so far")
-    if cfg["cross_heads"] != 1:
-        # the reference never splits heads (perceiver.py:99-115); inner_dim = heads*dim_head
-        pass
+    """Everything `initialize_flow` (reference model_initialization.py:30-202) can build AND `inner_loop` can run: the
+    StandardNormal / context-free augmenters raise a TypeError inside the reference's own `Flow.log_prob`
+    (`Augment.forward()` takes no `extra_context`), `affine_scale_fn='exp'` and ELU conditioners are not built here."""
+    if cfg["flow_type"] not in ("AffineCoupling", "RationalQuadraticSplineCoupling", "ExponentialCoupling"):
+        raise NotImplementedError(f"flow_type {cfg['flow_type']!r}")
+    if cfg["flow_type"] == "AffineCoupling" and cfg["affine_scale_fn"] != "sigmoid":
+        raise NotImplementedError("affine_scale_fn: only 'sigmoid' (all shipped configs) is built")
+    if cfg["permuter_type"] not in ("LinearLU", "random_permute", "FullCombiner", "ExponentialCombiner"):
+        raise NotImplementedError(f"permuter_type {cfg['permuter_type']!r}")
+    if cfg["latent_dim"] > cfg["cif_latent_dim"]:
+        raise ValueError("Augment dim smaller than main latent!")           # as reference models/cif_block.py:48
+    if cfg["latent_dim"] < cfg["cif_latent_dim"] and (cfg["using_extra_context"] or cfg["global"]):
+        raise NotImplementedError("CIF block with extra context / a global embedding: the reference raises too "
+                                  "(models/cif_block.py:33-36)")
+    if cfg["latent_dim"] < cfg["input_dim"]:
+        raise ValueError("Latent dim < Input dim")                          # as reference model_initialization.py:96
+    if cfg["latent_dim"] > cfg["input_dim"] and (cfg["augmenter_dist"] != "ConditionalNormal" or not cfg["use_attn_augment"]):
+        raise NotImplementedError("only the attention-conditioned ConditionalNormal augmenter runs in the reference")
+    if cfg["coupling_block_nonlinearity"] not in ("GELU", "RELU"):
+        raise NotImplementedError("conditioner non-linearity: GELU (all shipped configs) or RELU")
 
 
 # ----------------------------------------------------------------------------- weights
@@ -153,6 +207,11 @@ def random_state_dicts(config, seed: int = 0, perturb: bool = True):
     flow = OrderedDict()
     for k, shp in flow_param_shapes(config).items():
         flow[k] = _draw(k, shp, g, perturb, config)
+    for k in list(flow):
+        if k.endswith(".inv_permutation") and flow[k] is None:
+            flow[k] = torch.argsort(flow[k[:-len("inv_permutation")] + "permutation"])
+        if ".slicer.noise_dist.net." in k:   # the CIF block's slicer scores with the augmenter's own net (cif_block.py:58)
+            flow[k] = flow[k.replace(".slicer.", ".augmenter.")]
     emb = OrderedDict()
     for k, shp in embedder_param_shapes(config).items():
         emb[k] = _draw(k, shp, g, perturb, config)
@@ -190,6 +249,20 @@ def _draw(key, shape, g, perturb, config):
         return torch.ones(shape)
     if leaf == "num_batches_tracked":
         return torch.tensor(1, dtype=torch.long)
+    if leaf in ("permutation", "inv_permutation"):
+        if key.endswith("reverse.permutation") or key.endswith("reverse.inv_permutation"):
+            return torch.arange(shape[0] - 1, -1, -1)                       # models/permuters.py:84 (its own inverse)
+        if leaf == "permutation":
+            return torch.randperm(shape[0], generator=g)
+        return None                                                         # filled in from `permutation` by the caller
+    if len(shape) == 1 and shape[0] == 1 and leaf in ("scale", "shift", "rescale", "reshift"):
+        # ExponentialCoupling / ExponentialCombiner squashing scalars (models/exponential_coupling.py:22-25)
+        base = {"scale": 0.125, "shift": 0.0, "rescale": 1.0, "reshift": 0.0}[leaf]
+        return torch.full(shape, base) + (_randn(shape, g) * 0.02 if perturb else 0.0)
+    if leaf == "w":   # FullCombiner (orthogonal at init) / ExponentialCombiner (randn): any well-conditioned matrix will do
+        if config["permuter_type"] == "ExponentialCombiner":
+            return _randn(shape, g)
+        return torch.eye(shape[0]) + _randn(shape, g) * (0.3 / math.sqrt(shape[0]))
     if leaf == "shift":
         return _randn(shape, g) * 0.05 if perturb else torch.zeros(shape)
     if leaf == "log_scale":  # slightly positive mean keeps |z| ~ 1 through 115 random layers
@@ -234,7 +307,7 @@ def synthetic_batch(config, batch: int, seed: int = 0, n_context=None, n_target=
     context xyz ~ U([-1.1,1.1]^2 x [-2.1,2.1]), target xyz ~ U([-1,1]^2 x [-2,2])
     (voxel sizes, reference config/*.yaml:179-184), rgb ~ U[0,1], then joint zero-mean /
     unit-ball normalisation of xyz (reference utils.py:259-280 `co_unit_sphere`).
-    Returns dict(extract_0[B,Nc,6], extract_1[B,N,6], extra_context[B,1]|None, eps[B,N,D-6]).
+    Returns dict(extract_0[B,Nc,6], extract_1[B,N,6], extra_context[B,1]|None, eps[B,N,D-6] (+ eps_cif[L,B,N,S])).
     `eps` is the single standard-normal draw the reference makes per forward
     (models/distributions.py:148-153 via Normal.rsample), so it can be injected.
     """
@@ -259,5 +332,8 @@ def synthetic_batch(config, batch: int, seed: int = 0, n_context=None, n_target=
     e1[..., :3] = joint[:, Nc:]
     extra = torch.rand(batch, 1, generator=g) if cfg["using_extra_context"] else None
     eps = _randn((batch, N, cfg["latent_dim"] - cfg["input_dim"]), g)
-    return {"extract_0": e0.contiguous(), "extract_1": e1.contiguous(),
-            "extra_context": extra, "eps": eps}
+    out = {"extract_0": e0.contiguous(), "extract_1": e1.contiguous(), "extra_context": extra, "eps": eps}
+    if cfg["latent_dim"] < cfg["cif_latent_dim"]:
+        # one more draw per CIF block (reference models/cif_block.py:74 -> distributions.py:148-153), in list order
+        out["eps_cif"] = _randn((cfg["n_flow_layers"], batch, N, cfg["cif_latent_dim"] - cfg["latent_dim"]), g)
+    return out
