@@ -141,16 +141,16 @@ int fc_run_mlp_hidden(const FcMlp& m, const FcMlpIn& in, int M, float* bufA, flo
     // reference models/nets.py:19-30: x = act(in(x)); even hidden i: res = x, x = act(layer(x));
     // odd i: x = act(res + layer(x))
     int rc = gemm_plain(m.in, in.A1, in.lda1, in.A2, in.lda2, in.bias, in.bias_ld, in.bias_group, nullptr, 0,
-                        FC_ACT_GELU, bufA, ldh, M, precision, stream);
+                        m.act, bufA, ldh, M, precision, stream);
     if (rc) return rc;
     float* cur = bufA; float* other = bufB;
     for (int i = 0; i < m.n_hidden; ++i) {
         if ((i & 1) == 0) {
-            rc = gemm_plain(m.hidden[i], cur, ldh, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_GELU, other, ldh, M,
+            rc = gemm_plain(m.hidden[i], cur, ldh, nullptr, 0, nullptr, 0, 0, nullptr, 0, m.act, other, ldh, M,
                             precision, stream);
         } else {
             // residual source is `other` (the activation before the previous layer); write in place over it
-            rc = gemm_plain(m.hidden[i], cur, ldh, nullptr, 0, nullptr, 0, 0, other, ldh, FC_ACT_GELU, other, ldh, M,
+            rc = gemm_plain(m.hidden[i], cur, ldh, nullptr, 0, nullptr, 0, 0, other, ldh, m.act, other, ldh, M,
                             precision, stream);
         }
         if (rc) return rc;
@@ -183,9 +183,22 @@ extern "C" int fc_flow_create(const int32_t* header, int n_header, const int64_t
     f->hid = header[11]; f->n_hid = header[12]; f->pre_hid = header[13]; f->n_pre_hid = header[14];
     f->aug_hid = header[15]; f->n_aug_hid = header[16]; f->augpre_hid = header[17]; f->n_augpre_hid = header[18];
     f->arena = arena; f->arena_floats = arena_floats;
-    bool dims_ok = f->L >= 1 && f->D >= 2 && f->D <= 512 && f->d_in >= 1 && f->d_in < f->D && f->half == f->D / 2 &&
+    if (n_header >= 29) {
+        f->cpl_kind = header[19]; f->num_bins = header[20]; f->act = header[21]; f->has_aug = header[22];
+        f->cif_dim = header[23]; f->cif_hid = header[24]; f->n_cif_hid = header[25]; f->affcif_hid = header[26];
+        f->n_affcif_hid = header[27];
+        memcpy(&f->cif_clamp, &header[28], sizeof(float));
+    }
+    const int n2 = f->D - f->half, S = f->cif_dim ? f->cif_dim - f->D : 0;
+    bool dims_ok = f->L >= 1 && f->D >= 2 && f->D <= 512 && f->d_in >= 1 && f->d_in <= f->D && f->half == f->D / 2 &&
                    f->inner == 64 && f->attn_in <= 512 && f->hid <= 512 && f->pre_hid <= 512 && f->aug_hid <= 512 &&
-                   f->augpre_hid <= 512 && f->hid == f->aug_hid && (f->D % 2) == 0 && ((f->D - f->d_in) % 2) == 0;
+                   f->augpre_hid <= 512 && (f->D % 2) == 0 && ((f->D - f->d_in) % 2) == 0 &&
+                   (f->has_aug ? (f->d_in < f->D && f->hid == f->aug_hid) : f->d_in == f->D) &&
+                   f->cpl_kind >= FC_CPL_AFFINE && f->cpl_kind <= FC_CPL_EXPO && (f->act == FC_ACT_GELU || f->act == FC_ACT_RELU) &&
+                   (f->cpl_kind != FC_CPL_SPLINE || (f->num_bins >= 1 && f->num_bins <= 16)) &&
+                   (f->cpl_kind != FC_CPL_EXPO || n2 <= fc_expm_max_n()) &&
+                   (f->cif_dim == 0 || (S > 0 && f->cif_dim <= 512 && f->cif_hid <= 512 && f->affcif_hid <= 512 &&
+                                        f->cif_hid > 0 && f->affcif_hid > 0 && !f->extra && !f->is_global));
     if (!dims_ok) { delete f; return FC_ERR_UNSUPPORTED; }
     f->layers = new (std::nothrow) FcFlowLayer[f->L];
     if (!f->layers) { delete f; return FC_ERR_MODEL; }
@@ -195,20 +208,36 @@ extern "C" int fc_flow_create(const int32_t* header, int n_header, const int64_t
     const int64_t cbits = c.next();
     memcpy(&f->ldj_const, &cbits, sizeof(double));
     const int attn_k2 = f->is_global ? 0 : f->inner;
-    if (!f->is_global) {
-        f->augpre = c.mlp(f->d_in, 0, f->augpre_hid, f->n_augpre_hid, f->attn_in);
-        f->augattn = read_attn(c, *f);
+    if (f->has_aug) {
+        if (!f->is_global) {
+            f->augpre = c.mlp(f->d_in, 0, f->augpre_hid, f->n_augpre_hid, f->attn_in);
+            f->augpre.act = f->act;
+            f->augattn = read_attn(c, *f);
+        }
+        f->aug = c.mlp(f->d_in, attn_k2, f->aug_hid, f->n_aug_hid, 2 * (f->D - f->d_in));
+        f->aug.act = f->act;
     }
-    f->aug = c.mlp(f->d_in, attn_k2, f->aug_hid, f->n_aug_hid, 2 * (f->D - f->d_in));
+    const int cpl_out = f->cpl_kind == FC_CPL_AFFINE ? 2 * n2 : f->cpl_kind == FC_CPL_SPLINE ? (3 * f->num_bins + 1) * f->half
+                                                                                              : n2 * n2 + n2;
     f->has_cb = f->extra || f->is_global;
     if (f->has_cb) f->cb = c.linear(f->extra + (f->is_global ? f->E : 0), 0, (f->L + 1) * f->hid);
     for (int l = 0; l < f->L; ++l) {
         FcFlowLayer& y = f->layers[l];
+        if (f->cif_dim) {
+            y.cifnet = c.mlp(f->D, 0, f->cif_hid, f->n_cif_hid, 2 * S);                 // GELU (cif_block.py:54)
+            y.affcif = c.mlp(S, 0, f->affcif_hid, f->n_affcif_hid, 2 * f->D);           // GELU (cif_block.py:64)
+            y.cif_sc = c.ptr(c.next(), f->cif_dim);
+            y.cif_bi = c.ptr(c.next(), f->cif_dim);
+            if (!y.cif_sc || !y.cif_bi) c.ok = false;
+        }
         if (!f->is_global) {
             y.pre = c.mlp(f->half, 0, f->pre_hid, f->n_pre_hid, f->attn_in);
+            y.pre.act = f->cif_dim ? FC_ACT_GELU : f->act;                              // the CIF block's own MLP is GELU (:62)
             y.attn = read_attn(c, *f);
         }
-        y.cpl = c.mlp(f->half, attn_k2, f->hid, f->n_hid, 2 * (f->D - f->half));
+        if (f->cpl_kind == FC_CPL_EXPO) { y.expo_sq = c.ptr(c.next(), 4); if (!y.expo_sq) c.ok = false; }
+        y.cpl = c.mlp(f->half, attn_k2, f->hid, f->n_hid, cpl_out);
+        y.cpl.act = f->act;
         y.has_lu = (l != f->L - 1);
         if (y.has_lu) {
             y.lu = c.linear(f->D, 0, f->D);
@@ -230,20 +259,34 @@ extern "C" void fc_flow_destroy(fc_flow* f) {
 // ------------------------------------------------------------------------------------------ workspace
 namespace {
 struct FlowWs {
-    float *lat0, *lat1, *hA, *hB, *hC, *q, *o, *mu, *rstd, *cpart, *apart, *kv, *kvs, *cb, *cbA;
-    int ldx, ldh, n_cpart, n_apart, cb_ld, cbA_ld;
+    float *lat0, *lat1, *hA, *hB, *q, *o, *mu, *rstd, *cpart, *apart, *kv, *kvs, *cb, *cbA, *pbuf;
+    int ldx, ldh, n_cpart, n_apart, cb_ld, cbA_ld, ldp, p_rows, ldp_cif;
     int64_t total_bytes;
 };
 
 FlowWs carve_flow_ws(const fc_flow* f, int B, int N, int Nc, void* base) {
     FlowWs w{};
     const int64_t M = (int64_t)B * N;
-    w.ldx = fc_round_up(f->D, 4);
+    w.ldx = fc_round_up(f->cif_dim > f->D ? f->cif_dim : f->D, 4);
     w.ldh = 512;
     // one partial log-det slab per N-tile of whichever GEMM kernel runs (FFMA: 128-wide tiles, tcgen05: <= 96-wide)
     auto slabs = [](int n) { const int a = fc_gemm_n_tiles(n), b = fc_tc_n_tiles(n); return a > b ? a : b; };
     w.n_cpart = slabs(2 * (f->D - f->half));
-    w.n_apart = slabs(2 * (f->D - f->d_in));
+    if (f->cif_dim) { const int a = slabs(2 * f->D); if (a > w.n_cpart) w.n_cpart = a; }
+    w.n_apart = f->has_aug ? slabs(2 * (f->D - f->d_in)) : 1;
+    // raw conditioner outputs of the spline / exponential couplings and of the CIF block's ConditionalNormal net; the
+    // exponential coupling's (n^2 + n floats per point) are produced and consumed in chunks of whole clouds
+    w.ldp = 0; w.p_rows = 0; w.ldp_cif = 0;
+    {
+        const int n2 = f->D - f->half;
+        if (f->cpl_kind == FC_CPL_SPLINE) { w.ldp = fc_round_up((3 * f->num_bins + 1) * f->half, 4); w.p_rows = (int)M; }
+        if (f->cpl_kind == FC_CPL_EXPO) {
+            w.ldp = fc_round_up(n2 * n2 + n2, 4);
+            const long long clouds = (1ll << 28) / ((long long)w.ldp * N);     // ~1 GB of parameters at a time
+            w.p_rows = (int)((clouds < 1 ? 1 : (clouds > B ? B : clouds)) * N);
+        }
+        if (f->cif_dim) w.ldp_cif = fc_round_up(2 * (f->cif_dim - f->D), 4);
+    }
     w.cb_ld = (f->L + 1) * f->hid;
     w.cbA_ld = fc_round_up(f->extra + (f->is_global ? f->E : 0), 4);
     if (w.cbA_ld == 0) w.cbA_ld = 4;
@@ -251,7 +294,7 @@ FlowWs carve_flow_ws(const fc_flow* f, int B, int N, int Nc, void* base) {
     auto take = [&](int64_t floats) { float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
                                       off += fc_round_up_ll(floats * 4, 256); return p; };
     w.lat0 = take(M * w.ldx); w.lat1 = take(M * w.ldx);
-    w.hA = take(M * w.ldh); w.hB = take(M * w.ldh); w.hC = take(M * w.ldh);
+    w.hA = take(M * w.ldh); w.hB = take(M * w.ldh);
     w.q = take(M * 64); w.o = take(M * 64);
     w.mu = take(M); w.rstd = take(M);
     w.cpart = take(M * w.n_cpart); w.apart = take(M * w.n_apart);
@@ -259,6 +302,10 @@ FlowWs carve_flow_ws(const fc_flow* f, int B, int N, int Nc, void* base) {
     w.kvs = take(fc_attention_tc_scratch_floats(B, Nc));   // TF32 hi/lo copies of k, v^T for the tcgen05 attention
     w.cb = take((int64_t)B * w.cb_ld);
     w.cbA = take((int64_t)B * w.cbA_ld);
+    {
+        const int64_t a = (int64_t)w.ldp * w.p_rows, b = (int64_t)w.ldp_cif * M;
+        w.pbuf = take(a > b ? a : b);
+    }
     w.total_bytes = off;
     return w;
 }
@@ -316,10 +363,47 @@ static int run_attention_block(const fc_flow* f, const FcMlp& pre, const FcAttn&
     return fc_launch_cross_attention(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
 }
 
+// CIF block up to (not including) its attention-conditioned coupling, reference models/cif_block.py:71-93.  In the
+// reference's order: Augment -> Reverse -> AffineCoupling(split = cif_dim - D) -> ActNorm -> Reverse -> Slice.  The two
+// Reverse permutations cancel once the affine coupling's weights and the ActNorm vectors are re-indexed at pack time
+// (packing.py: _pack_cif), so on the device the block is: z2 ~ N(mean(x), sigma(x)) into columns [D, cif_dim);
+// x = x * s(z2) + t(z2); every column c: a*sc[c] + bi[c]; log N(z2; mean(x), sigma(x)) with the SAME net (cif_block.py:58).
+static int run_cif_block(const fc_flow* f, const FcFlowLayer& y, float* lat, FlowWs& w, int M, const float* eps_l,
+                         int precision, cudaStream_t s) {
+    const int D = f->D, S = f->cif_dim - f->D;
+    int rc;
+    for (int pass = 0; pass < 2; ++pass) {
+        FcMlpIn in{lat, w.ldx, nullptr, 0, nullptr, 0, 0};
+        float* last = nullptr;
+        rc = fc_run_mlp_hidden(y.cifnet, in, M, w.hA, w.hB, w.ldh, precision, s, &last);
+        if (rc) return rc;
+        rc = gemm_plain(y.cifnet.out, last, w.ldh, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, w.pbuf, w.ldp_cif, M,
+                        precision, s);
+        if (rc) return rc;
+        rc = fc_launch_cond_normal(w.pbuf, w.ldp_cif, lat, w.ldx, D, S, eps_l, M, f->cif_clamp, w.cpart, pass, s);
+        if (rc || pass == 1) return rc;
+        FcMlpIn in2{lat + D, w.ldx, nullptr, 0, nullptr, 0, 0};
+        rc = fc_run_mlp_hidden(y.affcif, in2, M, w.hA, w.hB, w.ldh, precision, s, &last);
+        if (rc) return rc;
+        GemmArgs g = fc_gemm_args_zero();
+        const FcLinear& o = y.affcif.out;
+        g.A1 = last; g.lda1 = w.ldh; g.K1 = o.K1; g.Wt = o.w; g.ldw = o.ldw; g.bias = o.b; g.Whi = o.whi; g.Wlo = o.wlo; g.ldk = o.ldk;
+        g.tc_fmt = o.tc_fmt; g.M = M; g.N = o.N; g.epi = FC_EPI_COUPLING; g.x = lat; g.ldx = w.ldx; g.col0 = 0; g.part = w.cpart;
+        g.precision = precision;
+        rc = fc_launch_gemm(g, s);
+        if (rc) return rc;
+        rc = fc_launch_col_affine(lat, w.ldx, f->cif_dim, M, y.cif_sc, y.cif_bi, s);
+        if (rc) return rc;
+    }
+    return FC_OK;
+}
+
 static int flow_forward(const fc_flow* f, const float* x, const float* context, const float* extra, const float* eps,
-                        float* log_prob_out, float* z_out, int B, int N, int Nc, void* workspace, int64_t workspace_bytes,
-                        int precision, fc_stream_t stream_) {
-    FC_REQUIRE(f && x && context && eps && log_prob_out && B > 0 && N > 0 && Nc > 0);
+                        const float* eps_cif, float* log_prob_out, float* z_out, int B, int N, int Nc, void* workspace,
+                        int64_t workspace_bytes, int precision, fc_stream_t stream_) {
+    FC_REQUIRE(f && x && context && log_prob_out && B > 0 && N > 0 && Nc > 0);
+    FC_REQUIRE(eps || !f->has_aug);
+    FC_REQUIRE(eps_cif || !f->cif_dim);
     FC_REQUIRE((f->extra != 0) == (extra != nullptr));
     FC_REQUIRE((int64_t)B * N < (1ll << 31) && (int64_t)B * Nc < (1ll << 31));
     cudaStream_t s = (cudaStream_t)stream_;
@@ -352,12 +436,12 @@ static int flow_forward(const fc_flow* f, const float* x, const float* context, 
     }
     auto cb_ptr = [&](int slot) -> const float* { return f->has_cb ? w.cb + (size_t)slot * f->hid : nullptr; };
 
-    // ---- transforms.0: augment (reference models/augmenter.py:15-19, :49-63)
-    if (!f->is_global) {
+    // ---- transforms.0: augment (reference models/augmenter.py:15-19, :49-63); latent_dim == input_dim: IdentityTransform
+    if (f->has_aug && !f->is_global) {
         rc = run_attention_block(f, f->augpre, f->augattn, w.lat0, w.ldx, f->d_in, context, B, N, Nc, w, precision, s);
         if (rc) return rc;
     }
-    {
+    if (f->has_aug) {
         FcMlpIn in{w.lat0, w.ldx, f->is_global ? nullptr : w.o, 64, cb_ptr(0), w.cb_ld, N};
         if (!f->has_cb) { in.bias = nullptr; in.bias_ld = 0; in.bias_group = 0; }
         float* last = nullptr;
@@ -375,6 +459,10 @@ static int flow_forward(const fc_flow* f, const float* x, const float* context, 
     float* lat = w.lat0; float* lat_next = w.lat1;
     for (int l = 0; l < f->L; ++l) {
         const FcFlowLayer& y = f->layers[l];
+        if (f->cif_dim) {
+            rc = run_cif_block(f, y, lat, w, M, eps_cif + (size_t)l * M * (f->cif_dim - f->D), precision, s);
+            if (rc) return rc;
+        }
         if (!f->is_global) {
             rc = run_attention_block(f, y.pre, y.attn, lat, w.ldx, f->half, context, B, N, Nc, w, precision, s);
             if (rc) return rc;
@@ -384,7 +472,23 @@ static int flow_forward(const fc_flow* f, const float* x, const float* context, 
         float* last = nullptr;
         rc = fc_run_mlp_hidden(y.cpl, in, M, w.hA, w.hB, w.ldh, precision, s, &last);
         if (rc) return rc;
-        {
+        if (f->cpl_kind == FC_CPL_SPLINE) {
+            // reference models/spline_coupling.py:187-210: the conditioner's raw output, then the spline on x2 in place
+            rc = gemm_plain(y.cpl.out, last, w.ldh, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, w.pbuf, w.ldp, M, precision, s);
+            if (rc) return rc;
+            rc = fc_launch_rq_spline(w.pbuf, w.ldp, lat, w.ldx, f->half, f->D - f->half, f->num_bins, M, w.cpart, 0, s);
+            if (rc) return rc;
+        } else if (f->cpl_kind == FC_CPL_EXPO) {
+            // reference models/exponential_coupling.py:44-58, n^2 + n conditioner outputs per point: whole clouds at a time
+            for (int r0 = 0; r0 < M; r0 += w.p_rows) {
+                const int rows = M - r0 < w.p_rows ? M - r0 : w.p_rows;
+                rc = gemm_plain(y.cpl.out, last + (size_t)r0 * w.ldh, w.ldh, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE,
+                                w.pbuf, w.ldp, rows, precision, s);
+                if (rc) return rc;
+                rc = fc_launch_expm_action(w.pbuf, w.ldp, lat, w.ldx, f->half, f->D - f->half, y.expo_sq, w.cpart, r0, rows, 0, s);
+                if (rc) return rc;
+            }
+        } else {
             GemmArgs g = fc_gemm_args_zero();
             g.A1 = last; g.lda1 = w.ldh; g.K1 = f->hid; g.Wt = y.cpl.out.w; g.ldw = y.cpl.out.ldw; g.bias = y.cpl.out.b; g.Whi = y.cpl.out.whi; g.Wlo = y.cpl.out.wlo; g.ldk = y.cpl.out.ldk; g.tc_fmt = y.cpl.out.tc_fmt;
             g.M = M; g.N = y.cpl.out.N; g.epi = FC_EPI_COUPLING; g.x = lat; g.ldx = w.ldx; g.col0 = f->half;
@@ -424,14 +528,24 @@ static int flow_forward(const fc_flow* f, const float* x, const float* context, 
 extern "C" int fc_flow_log_prob(const fc_flow* f, const float* x, const float* context, const float* extra,
                                 const float* eps, float* log_prob_out, int B, int N, int Nc, void* workspace,
                                 int64_t workspace_bytes, int precision, fc_stream_t stream_) {
-    return flow_forward(f, x, context, extra, eps, log_prob_out, nullptr, B, N, Nc, workspace, workspace_bytes, precision, stream_);
+    return flow_forward(f, x, context, extra, eps, nullptr, log_prob_out, nullptr, B, N, Nc, workspace, workspace_bytes, precision, stream_);
 }
+
+// Same pass for flows built with CIF blocks (latent_dim < cif_latent_dim): `eps_cif` [L, B, N, cif_latent_dim - latent_dim] holds
+// the draw of every block's augmenter (reference models/cif_block.py:74), in transform-list order.
+extern "C" int fc_flow_log_prob_cif(const fc_flow* f, const float* x, const float* context, const float* extra,
+                                    const float* eps, const float* eps_cif, float* log_prob_out, int B, int N, int Nc,
+                                    void* workspace, int64_t workspace_bytes, int precision, fc_stream_t stream_) {
+    return flow_forward(f, x, context, extra, eps, eps_cif, log_prob_out, nullptr, B, N, Nc, workspace, workspace_bytes, precision, stream_);
+}
+
+extern "C" int fc_flow_cif_noise_dim(const fc_flow* f) { return f ? (f->cif_dim ? f->cif_dim - f->D : 0) : FC_ERR_INVALID_ARG; }
 
 extern "C" int fc_flow_forward(const fc_flow* f, const float* x, const float* context, const float* extra, const float* eps,
                                float* log_prob_out, float* z_out, int B, int N, int Nc, void* workspace, int64_t workspace_bytes,
                                int precision, fc_stream_t stream_) {
     FC_REQUIRE(z_out != nullptr);
-    return flow_forward(f, x, context, extra, eps, log_prob_out, z_out, B, N, Nc, workspace, workspace_bytes, precision, stream_);
+    return flow_forward(f, x, context, extra, eps, nullptr, log_prob_out, z_out, B, N, Nc, workspace, workspace_bytes, precision, stream_);
 }
 
 // ------------------------------------------------------------------------------------------ inverse / sampling pass
@@ -466,6 +580,7 @@ extern "C" int fc_flow_sample(const fc_flow* f, const float* z, const float* con
     FC_REQUIRE((f->extra != 0) == (extra != nullptr));
     FC_REQUIRE((int64_t)B * P < (1ll << 31) && (int64_t)B * Nc < (1ll << 31));
     if (!f->has_inverse) return FC_ERR_MODEL;
+    if (f->cpl_kind != FC_CPL_AFFINE || f->cif_dim || !f->has_aug) return FC_ERR_UNSUPPORTED;   // sampling: shipped architectures only
     cudaStream_t s = (cudaStream_t)stream_;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return FC_ERR_WORKSPACE;
     FlowWs w = carve_flow_ws(f, B, P, Nc, workspace);

@@ -256,8 +256,8 @@ int fc_launch_gemm_ffma(const GemmArgs& a, cudaStream_t stream) {
     FC_REQUIRE((reinterpret_cast<uintptr_t>(a.Wt) & 15) == 0);
     if (a.epi == FC_EPI_STORE || a.epi == FC_EPI_LNQ) FC_REQUIRE(a.C != nullptr);
     if (a.epi == FC_EPI_LNQ) FC_REQUIRE(a.row_mu && a.row_rstd && a.csum && a.bias && a.bias_group == 0);
-    if (a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) FC_REQUIRE(a.x && a.part && (a.N % 4) == 0);
-    if (a.epi == FC_EPI_COUPLING_INV) FC_REQUIRE(a.x && (a.N % 4) == 0);
+    if (a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) FC_REQUIRE(a.x && a.part && (a.N % 2) == 0);
+    if (a.epi == FC_EPI_COUPLING_INV) FC_REQUIRE(a.x && (a.N % 2) == 0);
     if (a.epi == FC_EPI_AUGMENT) FC_REQUIRE(a.eps != nullptr);
     if (a.N <= 64) return launch<64>(a, stream);
     return launch<128>(a, stream);

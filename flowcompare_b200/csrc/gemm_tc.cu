@@ -83,12 +83,28 @@ constexpr int TC_STAGES = 5;                   // shared-memory stages: a load i
 #define TC_CONV_WARPS 8                        // 4: one converter thread per tile row; 8: two (one per half k-block; measured +10 % in 3xFP16 mode)
 #endif
 #ifndef TC_WARP_ARRIVE
-#define TC_WARP_ARRIVE 1                       // converter / epilogue warps arrive on their mbarriers ONCE PER WARP (lane 0 after a
+#define TC_WARP_ARRIVE 0                       // (measured: no gain, 437 vs 441 pairs/s) converter / epilogue warps arrive on their mbarriers ONCE PER WARP (lane 0 after a
 #endif                                         // __syncwarp) instead of once per thread: 8 arrivals per barrier phase instead of 256
+#ifndef TC_CONV_PARITY
+#define TC_CONV_PARITY 1                       // 3xFP16 mode, 8 converter warps: warps 2-5 convert the even k-blocks, 6-9 the odd ones
+#endif                                         // (whole rows), so TWO k-blocks are in conversion at any time
+#ifndef TC_NO_AFREE
+#define TC_NO_AFREE 1                          // the TMA producer waits on w_free[] only: MMAs that have retired imply that the
+#endif                                         // converters finished reading the stage's activation tile long before
+#ifndef TC_SPLIT_ISSUE
+#define TC_SPLIT_ISSUE 0                       // 1: two MMA issuer warps, one per ACCUMULATOR (warp 1 the main product Ahi Whi, warp 2 the
+#endif                                         // two compensation products; each accumulator keeps ONE issuer in program order, so the
+                                               // bits stay reproducible).  Measured equal to one issuer (146.2 vs 145.4 us at
+                                               // M=65536 N=K=512): the issuer is not what paces the k-block, see DESIGN.md section 4
+#ifndef TC_PROBE
+#define TC_PROBE 1                             // issuer probes the next k-block's barrier before it blocks in the issue
+#endif
 constexpr int TC_CONV_WARPS_N = TC_CONV_WARPS;
 static_assert(TC_CONV_WARPS_N == 4 || TC_CONV_WARPS_N == 8, "converter warps: 4 or 8");
-constexpr int TC_EPI_WARP0 = 2 + TC_CONV_WARPS_N;             // first epilogue warp (a multiple of 2 past a multiple of 4: TMEM quadrants line up)
-constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + 8);           // TMA, MMA, converter warps, 8 epilogue warps
+constexpr int TC_MMA_WARPS = TC_SPLIT_ISSUE ? 2 : 1;
+constexpr int TC_CONV_WARP0 = 1 + TC_MMA_WARPS;               // first converter warp (any 4 consecutive warps cover the 4 TMEM lane quadrants)
+constexpr int TC_EPI_WARP0 = TC_CONV_WARP0 + TC_CONV_WARPS_N; // first epilogue warp
+constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + 8);           // TMA, MMA issuer(s), converter warps, 8 epilogue warps
 // Per operand format: F16 = false 3xTF32 (weights as fp32 TF32 hi/lo), true 3xFP16 (weights as fp16 hi / 2^11-scaled lo)
 template <bool F16> struct TcCfg {
     static constexpr int STAGES = F16 ? TC_STAGES_F16 : TC_STAGES;
@@ -146,6 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     constexpr int TC_STAGES = TcCfg<F16>::STAGES, TC_TSTAGES = TcCfg<F16>::TSTAGES, TS_COLS = TcCfg<F16>::TS_COLS;   // shadow the globals
+    constexpr bool PARITY = F16 && TC_CONV_PARITY && TC_CONV_WARPS_N == 8;
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 4];
     __shared__ uint32_t tmem_base_slot;
@@ -188,9 +205,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
 
     if (threadIdx.x == 0) {
         constexpr int PER_WARP = TC_WARP_ARRIVE ? 1 : 32;   // arrivals a warp contributes per event
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], PER_WARP * TC_CONV_WARPS_N); mbar_init(&w_free[s], 1); }
-        for (int s = 0; s < TC_TSTAGES / 2; ++s) { mbar_init(&conv[s], PER_WARP * 8); mbar_init(&tfree[s], 1); }   // one pair per K-BLOCK of A in tensor memory
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], PER_WARP * 8); }
+        constexpr int CONV_GROUPS = PARITY ? 2 : 1;         // converter groups that take turns on k-blocks
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], PER_WARP * TC_CONV_WARPS_N / CONV_GROUPS); mbar_init(&w_free[s], TC_MMA_WARPS); }
+        for (int s = 0; s < TC_TSTAGES / 2; ++s) { mbar_init(&conv[s], PER_WARP * 8 / CONV_GROUPS); mbar_init(&tfree[s], TC_MMA_WARPS); }   // one pair per K-BLOCK of A in tensor memory
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], TC_MMA_WARPS); mbar_init(&acc_free[s], PER_WARP * 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -219,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 for (int t = 0; t < T; ++t, ++g) {
                     const int s = g % TC_STAGES;
                     const uint32_t ph = (g / TC_STAGES) & 1;
-                    mbar_wait(&a_free[s], ph ^ 1, 100 + t);
+                    if (!TC_NO_AFREE) mbar_wait(&a_free[s], ph ^ 1, 100 + t);
                     mbar_wait(&w_free[s], ph ^ 1, 150 + t);
                     mbar_expect_tx(&full[s], (uint32_t)((TC_KO_ATMA ? 0 : TC_A_BYTES) + (TC_KO_WTMA ? 0 : 2 * w_bytes)));
                     if (!TC_KO_ATMA) {
@@ -233,8 +251,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer
+    } else if (warp < TC_CONV_WARP0) {
+        // ===================================================== MMA issuer(s)
+        const int role = TC_SPLIT_ISSUE ? warp : 0;   // 0: every product; 1: main product only; 2: compensation products only
         // The whole warp runs the loop and ONE ELECTED lane issues: inside a divergent `if (lane == 0)` the compiler
         // cannot keep the descriptors in uniform registers and wraps every UTCHMMA in an ELECT/vote loop with R2UR moves.
         //
@@ -276,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 {   // probe the NEXT group's first k-block now: a wait after the issue is dead time for the tensor pipe
                     int kn = ks + nb; uint32_t pn = kph;
                     if (kn >= TC_TSTAGES / 2) { kn -= TC_TSTAGES / 2; pn ^= 1; }
-                    conv_seen = mbar_test(&conv[kn], pn);
+                    conv_seen = TC_PROBE ? mbar_test(&conv[kn], pn) : false;
                 }
                 TC_T(mp1);
                 TC_ACC(m_probe, mc1, mp1);
@@ -293,17 +312,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                             if (F16) {
                                 // one kind::f16 MMA covers the half k-block (16 k = 32 bytes of the 64-byte weight row)
                                 const uint64_t adv = (uint64_t)(h * 32 >> 4);
-                                umma_f16_ts(d_corr, t_lo, dbh + adv, idesc, (tt | h) != 0);   // (A - Ahi) 2^11 . Whi
-                                umma_f16_ts(d_corr, t_hi, dbl + adv, idesc, 1);               // Ahi . (W - Whi) 2^11
-                                umma_f16_ts(d_main, t_hi, dbh + adv, idesc, (tt | h) != 0);
+                                if (role != 1) {
+                                    umma_f16_ts(d_corr, t_lo, dbh + adv, idesc, (tt | h) != 0);   // (A - Ahi) 2^11 . Whi
+                                    umma_f16_ts(d_corr, t_hi, dbl + adv, idesc, 1);               // Ahi . (W - Whi) 2^11
+                                }
+                                if (role != 2) umma_f16_ts(d_main, t_hi, dbh + adv, idesc, (tt | h) != 0);
                             } else {
 #pragma unroll
                                 for (int kk = 0; kk < 2; ++kk) {
                                     const int k = 2 * h + kk;
                                     const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes per k-step
-                                    umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (tt | k) != 0);
-                                    umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
-                                    umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (tt | k) != 0);
+                                    if (role != 1) {
+                                        umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (tt | k) != 0);
+                                        umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
+                                    }
+                                    if (role != 2) umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (tt | k) != 0);
                                 }
                             }
                         }
@@ -324,7 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             __syncwarp();
         }
 #if TC_PHASE_TIMERS
-        if (lane == 0) {
+        if (lane == 0 && warp == TC_MMA_WARPS) {   // the busier issuer (all products, or the compensation products)
             atomicAdd(&fc_tc_dbg[0], 1ull); atomicAdd(&fc_tc_dbg[1], (unsigned long long)(clock64() - m_t0));
             atomicAdd(&fc_tc_dbg[3], (unsigned long long)m_conv); atomicAdd(&fc_tc_dbg[4], (unsigned long long)m_acc);
             atomicAdd(&fc_tc_dbg[10], (unsigned long long)m_probe); atomicAdd(&fc_tc_dbg[11], (unsigned long long)m_issue);
@@ -335,7 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
         const int row_in_tile = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const int my_half = (warp - 2) >> 2;         // 8 converter warps: warps 2-5 take the first half of every k-block, 6-9 the second
+        const int my_half = (warp - TC_CONV_WARP0) >> 2;   // 8 converter warps: the first four take the first half of every k-block, the others the second
         // Software pipelined by one half k-block: the tcgen05.st of a half is in flight while the next one is loaded and
         // split; only then is it awaited and published (one arrival per thread and half on the k-block's conv[] barrier,
         // 256 arrivals per k-block with 4 or 8 converter warps), so the store latency is off the critical path.
@@ -344,6 +367,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         int pending = -1;              // k-block stage whose store has been issued but not yet published
         long long c_full = 0, c_tfree = 0;
         TC_T(c_t0);
+        if constexpr (PARITY) {
+            // Two converter groups take turns on k-blocks: every role of this kernel pays ~100 cycles per mbarrier wait (even on a
+            // completed phase) plus the tcgen05.st round trip, so ONE group working through every k-block was a ~500-cycle serial
+            // chain per k-block (knock-out builds: the pipeline ran at that pace with all the work removed).  A thread converts
+            // its whole 32-float row of the k-block and writes it with one 32-column tcgen05.st.
+            const int grp = (warp - TC_CONV_WARP0) >> 2;
+            uint32_t g = 0;
+            for (int L = blockIdx.x; L < total_tiles; L += gridDim.x) {
+                for (int t = 0; t < T; ++t, ++g) {
+                    if ((int)(g & 1) == grp) {
+                        if (pending >= 0) {
+                            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            warp_arrive(&conv[pending]);
+                            pending = -1;
+                        }
+                        TC_T(cf0);
+                        mbar_wait(&full[s], sph, 400 + t);
+                        TC_T(cf1);
+                        TC_ACC(c_full, cf0, cf1);
+                        const float4* rowp = reinterpret_cast<const float4*>(a_raw(s) + row_in_tile * 128);
+                        uint32_t hl[32];   // [half 0: hi x8 | lo x8 | half 1: hi x8 | lo x8], two fp16 per column
+#pragma unroll
+                        for (int j = 0; j < (TC_KO_CONV ? 0 : 8); ++j) {
+                            const float4 x = rowp[j ^ (row_in_tile & 7)];
+                            const float xv[4] = {x.x, x.y, x.z, x.w};
+                            const int base = 16 * (j >> 2) + 2 * (j & 3);
+#pragma unroll
+                            for (int e = 0; e < 4; e += 2) {
+                                const uint32_t hp = pack_f16x2(xv[e], xv[e + 1]);
+                                float h0, h1;
+                                unpack_f16x2(hp, h0, h1);
+                                hl[base + (e >> 1)] = hp;
+                                hl[base + 8 + (e >> 1)] = pack_f16x2((xv[e] - h0) * 2048.0f, (xv[e + 1] - h1) * 2048.0f);
+                            }
+                        }
+                        if (!TC_NO_AFREE) warp_arrive(&a_free[s]);
+                        TC_T(ct0);
+                        mbar_wait(&tfree[ks], kph ^ 1, 450 + t);
+                        TC_T(ct1);
+                        TC_ACC(c_tfree, ct0, ct1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t dst = tmem + lane_addr + TC_COL_A + TS_COLS * (2 * ks);
+                        if constexpr (TC_KO_CONV) { (void)hl; (void)dst; }
+                        else tmem_st32(dst, hl);
+                        pending = ks;
+                    }
+                    s = s + 1 == TC_STAGES ? 0 : s + 1; if (s == 0) sph ^= 1;
+                    ks = ks + 1 == TC_TSTAGES / 2 ? 0 : ks + 1; if (ks == 0) kph ^= 1;
+                }
+            }
+        } else
         for (int L = blockIdx.x; L < total_tiles; L += gridDim.x) {
             for (int t = 0; t < T; ++t) {
                 if (pending >= 0) {      // never hold a finished stage back while waiting for the next k-block's data
@@ -391,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                             }
                         }
                     }
-                    if (h == 1 || TC_CONV_WARPS_N == 8) warp_arrive(&a_free[s]);   // this thread's part of the row is in registers: the A smem stage may be refilled
+                    if (!TC_NO_AFREE && (h == 1 || TC_CONV_WARPS_N == 8)) warp_arrive(&a_free[s]);   // this thread's part of the row is in registers: the A smem stage may be refilled
                     if (pending >= 0) {
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -420,7 +495,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             warp_arrive(&conv[pending]);
         }
 #if TC_PHASE_TIMERS
-        if (threadIdx.x == 64) {
+        if (threadIdx.x == 32 * TC_CONV_WARP0) {
             atomicAdd(&fc_tc_dbg[5], (unsigned long long)(clock64() - c_t0));
             atomicAdd(&fc_tc_dbg[6], (unsigned long long)c_full); atomicAdd(&fc_tc_dbg[7], (unsigned long long)c_tfree);
         }
@@ -821,8 +896,8 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     FC_REQUIRE(fc_gemm_tc_supported(a));
     if (a.epi == FC_EPI_STORE || a.epi == FC_EPI_LNQ) FC_REQUIRE(a.C != nullptr);
     if (a.epi == FC_EPI_LNQ) FC_REQUIRE(a.row_mu && a.row_rstd && a.csum && a.bias && a.bias_group == 0);
-    if (a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) FC_REQUIRE(a.x && a.part && (a.N % 4) == 0);
-    if (a.epi == FC_EPI_COUPLING_INV) FC_REQUIRE(a.x && (a.N % 4) == 0);
+    if (a.epi == FC_EPI_COUPLING || a.epi == FC_EPI_AUGMENT) FC_REQUIRE(a.x && a.part && (a.N % 2) == 0);
+    if (a.epi == FC_EPI_COUPLING_INV) FC_REQUIRE(a.x && (a.N % 2) == 0);
     if (a.epi == FC_EPI_KVSPLIT)
         FC_REQUIRE(a.N == 128 && fc_tc_bn(a.N) == 64 && a.C && a.kv_klo && a.kv_vthi && a.kv_vtlo && a.kv_nc > 0 &&
                    a.kv_ncp >= a.kv_nc && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 &&

@@ -25,6 +25,7 @@ struct FcMlp {
     FcLinear hidden[FC_MAX_HIDDEN];
     int n_hidden = 0;
     FcLinear out;
+    int act = FC_ACT_GELU;   // non-linearity of the in / hidden layers (reference models/nets.py:10)
 };
 
 struct FcAttn {
@@ -44,6 +45,13 @@ struct FcFlowLayer {
     // sampling pass (fc_flow_set_inverse): (ActNorm + LinearLU)^-1 = Wp^-1 z' + shift, same diagonal / off-diagonal split
     FcLinear lu_inv;
     const float* lu_inv_diag = nullptr;
+    // exponential coupling: the four squashing scalars (scale, shift, rescale, reshift; models/exponential_coupling.py:22-25)
+    const float* expo_sq = nullptr;
+    // CIF block (models/cif_block.py:50-68): the ConditionalNormal net shared by the augmenter and the slicer, the affine
+    // coupling that conditions x on the augmented part (both Reverse permutations folded into its weights), and the
+    // ActNorm between them as one per-column affine map over the cif_dim columns
+    FcMlp cifnet, affcif;
+    const float* cif_sc = nullptr; const float* cif_bi = nullptr;
 };
 
 struct fc_flow {
@@ -59,7 +67,13 @@ struct fc_flow {
     const float* arena = nullptr;
     int64_t arena_floats = 0;
     bool has_inverse = false;    // fc_flow_set_inverse was called (needed by fc_flow_sample)
+    // transforms no shipped config builds (header words 19..): coupling kind 0 affine / 1 rational-quadratic
+    // spline / 2 exponential, conditioner non-linearity, identity augmenter (latent_dim == input_dim), CIF block
+    int cpl_kind = 0, num_bins = 0, act = FC_ACT_GELU, has_aug = 1;
+    int cif_dim = 0, cif_hid = 0, n_cif_hid = 0, affcif_hid = 0, n_affcif_hid = 0;
+    float cif_clamp = 0.f;
 };
+enum { FC_CPL_AFFINE = 0, FC_CPL_SPLINE = 1, FC_CPL_EXPO = 2 };
 
 struct FcEdgeConv { FcLinear pq; int Cin, Cout; };
 
@@ -128,6 +142,16 @@ int fc_knn_launch(const float* q, int ldq, long long q_bstride, const float* t, 
                   int B, int Nq, int Nt, int C, int k, int mode, int32_t* idx32, int64_t* idx64, float* norms_scratch,
                   cudaStream_t stream);
 int64_t fc_knn_scratch_floats(int B, int Nq, int Nt, bool self);   // floats of `norms_scratch` (squared norms of the points)
+
+// elementwise tails of the spline / exponential couplings and the CIF block (transforms.cu)
+int fc_launch_rq_spline(const float* params, int ldp, float* lat, int ldx, int col0, int n2, int nb, int M, float* part,
+                        int inverse, cudaStream_t s);
+int fc_launch_cond_normal(const float* params, int ldp, float* lat, int ldx, int col0, int S, const float* eps, int M,
+                          float clamp, float* part, int mode, cudaStream_t s);
+int fc_launch_col_affine(float* lat, int ldx, int cols, long long M, const float* sc, const float* bi, cudaStream_t s);
+int fc_launch_expm_action(const float* params, int ldp, float* lat, int ldx, int col0, int n2, const float* squash4,
+                          float* part, long long row0, int rows, int inverse, cudaStream_t s);
+int fc_expm_max_n();
 
 // runs in/hidden layers of an MLP; returns the buffer holding the last hidden activation.
 // bufA/bufB: [M][ldh] scratch (ldh >= hidden width).  `in_bias`/group override the in-layer bias.

@@ -67,6 +67,9 @@ class FlowCompareB200:
         self.is_global = bool(self.config["global"])
         self.has_extra = bool(self.config["using_extra_context"])
         self.k = self.config["n_neighbors"]
+        self.L = self.config["n_flow_layers"]
+        # CIF blocks (latent_dim < cif_latent_dim, reference models/cif_block.py:30-37) draw their own noise
+        self.cif_S = max(0, self.config["cif_latent_dim"] - self.D)
         with torch.cuda.device(self.device):
             self._flow = self._create(packing.pack_flow(flow_sd, self.config, tc_format), self.lib.fc_flow_create,
                                       "fc_flow_create")
@@ -144,24 +147,43 @@ class FlowCompareB200:
             _lib.check(self.lib.fc_fill_normal(eps.data_ptr(), eps.numel(), seed, 0, _stream()), "fc_fill_normal")
         return eps
 
-    def log_prob(self, x, context, extra_context=None, eps=None):
+    def draw_eps_cif(self, B, N, seed=None):
+        """The CIF blocks' draws [L, B, N, cif_latent_dim - latent_dim] (reference models/cif_block.py:74), on the device."""
+        with torch.cuda.device(self.device):
+            eps = torch.empty((self.L, B, N, self.cif_S), dtype=torch.float32, device=self.device)
+            if seed is None:
+                self._seed_counter += 1
+                seed = 0x5EED0000 + self._seed_counter
+            _lib.check(self.lib.fc_fill_normal(eps.data_ptr(), eps.numel(), seed, 1 << 40, _stream()), "fc_fill_normal")
+        return eps
+
+    def log_prob(self, x, context, extra_context=None, eps=None, eps_cif=None):
         """`Flow.log_prob(x, context=, extra_context=)` (reference models/transform.py:70-76).
 
         x [B,N,input_dim]; context [B,Nc,E] (or [B,E] / repeated [B,N,E] for the global embedder);
         extra_context [B], [B,1] or the repeated [B,N,1] the reference passes; eps [B,N,latent-input_dim]
-        optional (default: drawn on the device)."""
+        optional (default: drawn on the device); eps_cif [L,B,N,cif_latent_dim-latent_dim] likewise, CIF flows only."""
         with torch.cuda.device(self.device):
             x = _f32c(x[..., :self.d_in], self.device)
             B, N = x.shape[0], x.shape[1]
             context, Nc, extra = self._prep_context(context, extra_context, B)
             eps = self.draw_eps(B, N) if eps is None else _f32c(eps, self.device)
             assert eps.shape == (B, N, self.D - self.d_in), eps.shape
+            eps_arg = eps if self.D > self.d_in else None      # identity augmenter: no draw
             out = torch.empty((B, N), dtype=torch.float32, device=self.device)
             nbytes = self.lib.fc_flow_workspace_bytes(self._flow["handle"], B, N, Nc)
             ws = self._workspace(nbytes)
-            rc = self.lib.fc_flow_log_prob(self._flow["handle"], x.data_ptr(), context.data_ptr(), _ptr(extra),
-                                           eps.data_ptr(), out.data_ptr(), B, N, Nc, ws, nbytes, self.precision, _stream())
-            _lib.check(rc, "fc_flow_log_prob")
+            if self.cif_S:
+                eps_cif = self.draw_eps_cif(B, N) if eps_cif is None else _f32c(eps_cif, self.device)
+                assert eps_cif.shape == (self.L, B, N, self.cif_S), eps_cif.shape
+                rc = self.lib.fc_flow_log_prob_cif(self._flow["handle"], x.data_ptr(), context.data_ptr(), _ptr(extra),
+                                                   _ptr(eps_arg), eps_cif.data_ptr(), out.data_ptr(), B, N, Nc, ws, nbytes,
+                                                   self.precision, _stream())
+                _lib.check(rc, "fc_flow_log_prob_cif")
+            else:
+                rc = self.lib.fc_flow_log_prob(self._flow["handle"], x.data_ptr(), context.data_ptr(), _ptr(extra),
+                                               _ptr(eps_arg), out.data_ptr(), B, N, Nc, ws, nbytes, self.precision, _stream())
+                _lib.check(rc, "fc_flow_log_prob")
         return out
 
     def _prep_context(self, context, extra_context, B):
@@ -240,11 +262,16 @@ class FlowCompareB200:
         return self.sample(n_points, emb, extra_context=extra_context, z=z, seed=seed).squeeze()
 
     # ------------------------------------------------------------------ whole path
-    def inner_loop(self, batch, eps=None):
+    def inner_loop(self, batch, eps=None, eps_cif=None):
         """`inner_loop(batch, models_dict, config)` (reference model_initialization.py:206-228).
         batch = (extract_0 [B,Nc,>=6], extract_1 [B,N,>=6], extra_context [B,1] | None).
         Returns (loss, log_prob [B,N], bpd) as CUDA tensors."""
         e0, e1, extra = batch
+        if self.cif_S or self.D == self.d_in:
+            # flows outside the shipped architectures (CIF blocks / identity augmenter): embed, then the flow, as two calls
+            lp = self.log_prob(e1, self.embed(e0), extra_context=extra, eps=eps, eps_cif=eps_cif)
+            loss = -lp.mean()
+            return loss, lp, loss * math.log2(math.e) / self.d_in
         with torch.cuda.device(self.device):
             e0 = _f32c(e0[:, :, :self.d_in], self.device)
             e1 = _f32c(e1[:, :, :self.d_in], self.device)

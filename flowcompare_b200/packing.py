@@ -249,6 +249,77 @@ def pack_flow_inverse(flow_sd, config, tc_format="tf32"):
     return header, table, arena
 
 
+CPL_KINDS = {"AffineCoupling": 0, "RationalQuadraticSplineCoupling": 1, "ExponentialCoupling": 2}
+ACT_CODES = {"GELU": 1, "RELU": 3}   # csrc/gemm.cuh FC_ACT_*
+
+
+def _squash(sd, p, w):
+    """reference models/exponential_coupling.py:50 / models/permuters.py:50 (fp64)."""
+    return _d(sd, f"{p}.rescale") * torch.tanh(_d(sd, f"{p}.scale") * w + _d(sd, f"{p}.shift")) + _d(sd, f"{p}.reshift") + 1e-8
+
+
+def permuter_matrix(flow_sd, t, cfg):
+    """(W [D,D] fp64 with z' = W z, log|det W|) of the permuter at transforms.<t> (reference model_initialization.py:117-131):
+    LinearLU (permuters.py:148-169), Permuter (`random_permute`, :55-66), FullCombiner (:15-26), ExponentialCombiner (:36-52)."""
+    D = cfg["latent_dim"]
+    kind = cfg["permuter_type"]
+    p = f"transforms.{t}"
+    if kind == "LinearLU":
+        lo, up = _d(flow_sd, f"{p}.lower_entries"), _d(flow_sd, f"{p}.upper_entries")
+        dg = _d(flow_sd, f"{p}.unconstrained_upper_diag")
+        Lm = torch.eye(D, dtype=torch.float64)
+        il = np.tril_indices(D, k=-1)
+        Lm[il[0], il[1]] = lo
+        Um = torch.zeros(D, D, dtype=torch.float64)
+        iu = np.triu_indices(D, k=1)
+        Um[iu[0], iu[1]] = up
+        diag = F.softplus(dg) + cfg["linear_lu_eps"]
+        Um[range(D), range(D)] = diag
+        return Lm @ Um, float(torch.log(diag).sum())
+    if kind == "random_permute":
+        perm = flow_sd[f"{p}.permutation"].long().cpu()
+        W = torch.zeros(D, D, dtype=torch.float64)
+        W[torch.arange(D), perm] = 1.0          # y_j = x_{perm[j]}  (index_select)
+        return W, 0.0
+    if kind == "FullCombiner":
+        W = _d(flow_sd, f"{p}.w")
+        return W, float(torch.linalg.slogdet(W)[1])
+    if kind == "ExponentialCombiner":
+        Wm = _squash(flow_sd, p, _d(flow_sd, f"{p}.w"))
+        return torch.matrix_exp(Wm), float(torch.diagonal(Wm).sum())
+    raise NotImplementedError(kind)
+
+
+def _pack_cif(ar, sd, p, cfg):
+    """CIF block minus its coupling (reference models/cif_block.py:50-68, :71-93).  Both `Reverse` permutations are folded away:
+    with a = [x | z2] the block computes, per column j of the UN-reversed vector,
+        j <  D:  a'_j = (x_j * s_{D-1-j} + t_{D-1-j} - shift_{D2-1-j}) * exp(-log_scale_{D2-1-j}),  (s, t) = affine_cif.nn(rev(z2))
+        j >= D:  a'_j = (z2_j - shift_{D2-1-j}) * exp(-log_scale_{D2-1-j})
+    so the affine coupling's first layer gets its input columns reversed, its last layer its s / t rows reversed (then
+    interleaved for the coupling epilogue), and the ActNorm becomes a per-column (scale, bias) pair in reversed order."""
+    D, D2 = cfg["latent_dim"], cfg["cif_latent_dim"]
+    S = D2 - D
+    for k in sd:
+        if k.startswith(f"{p}.slicer.noise_dist.net."):
+            assert torch.equal(sd[k], sd[k.replace(".slicer.", ".augmenter.")]), "slicer and augmenter share one net (cif_block.py:58)"
+    cif_hid, n_cif = _pack_plain_mlp(ar, sd, f"{p}.augmenter.noise_dist.net", D)
+    (w_in, b_in), hidden, (w_out, b_out) = _mlp_tensors(sd, f"{p}.affine_cif.nn")
+    hid = w_in.shape[0]
+    ar.linear(w_in.flip(1), b_in, S)
+    for w, b in hidden:
+        assert w.shape[0] == w.shape[1] == hid
+        ar.linear(w, b, hid)
+    w_o = torch.cat((w_out[:D].flip(0), w_out[D:].flip(0)), dim=0)
+    b_o = torch.cat((b_out[:D].flip(0), b_out[D:].flip(0)), dim=0)
+    w_o, b_o = _interleave_rows(w_o, b_o)
+    ar.linear(w_o, b_o, hid)
+    shift, log_scale = _d(sd, f"{p}.act_norm.shift")[0], _d(sd, f"{p}.act_norm.log_scale")[0]
+    sc = torch.exp(-log_scale).flip(0)
+    ar.vector(sc)
+    ar.vector(-shift.flip(0) * sc)
+    return cif_hid, n_cif, hid, len(hidden), float((-log_scale).sum())
+
+
 def pack_flow(flow_sd, config, tc_format="tf32"):
     cfg = derive(config)
     from .spec import _check_supported
@@ -259,12 +330,17 @@ def pack_flow(flow_sd, config, tc_format="tf32"):
     E = cfg["input_embedding_dim"]
     inner = cfg["cross_heads"] * cfg["cross_dim_head"]
     assert inner == 64, "only inner_dim 64 (all shipped configs) is built"
+    cpl_kind = CPL_KINDS[cfg["flow_type"]]
+    has_aug = D > d_in
+    cif = D < cfg["cif_latent_dim"]
+    n2 = D - half
+    cpl_out = {0: 2 * n2, 1: (cfg["num_bins_spline"] * 3 + 1) * half, 2: n2 * n2 + n2}[cpl_kind]
     ar = Arena(tc_format)
     ar.table.append(0)  # placeholder for the fp64 log-det constant
     has_cb = bool(ex) or is_global
     cb_cols, cb_bias = [], []
 
-    def pack_conditioner(mlp_prefix, attn_prefix, k_x, out_dim):
+    def pack_conditioner(mlp_prefix, attn_prefix, k_x, out_dim, interleave=True):
         w_g, b_fold, w_e, w_emb = _conditioner_first_layer(flow_sd, mlp_prefix, attn_prefix, k_x, ex, is_global, E)
         (_, _), hidden, (w_out, b_out) = _mlp_tensors(flow_sd, mlp_prefix)
         hid = w_g.shape[0]
@@ -272,8 +348,8 @@ def pack_flow(flow_sd, config, tc_format="tf32"):
         for w, b in hidden:
             assert w.shape[0] == w.shape[1] == hid
             ar.linear(w, b, hid)
-        assert w_out.shape[0] == out_dim
-        w_o, b_o = _interleave_rows(w_out, b_out)
+        assert w_out.shape[0] == out_dim, (w_out.shape, out_dim)
+        w_o, b_o = _interleave_rows(w_out, b_out) if interleave else (w_out, b_out)
         ar.linear(w_o, b_o, hid)
         if has_cb:
             rows = [w_e] if ex else []
@@ -283,46 +359,53 @@ def pack_flow(flow_sd, config, tc_format="tf32"):
             cb_bias.append(b_fold)
         return hid, len(hidden)
 
-    # transforms.0
-    augpre_hid = n_augpre = 0
-    if not is_global:
-        augpre_hid, n_augpre = _pack_plain_mlp(ar, flow_sd, "transforms.0.pre_attn_mlp", d_in)
-        _pack_attn(ar, flow_sd, "transforms.0.attn")
-    else:
-        augpre_hid, n_augpre = cfg["hidden_dims"][0], len(cfg["hidden_dims"]) - 1
-    aug_hid, n_aug = pack_conditioner("transforms.0.augment.noise_dist.net", "transforms.0.attn", d_in, 2 * (D - d_in))
+    # transforms.0 (absent -- IdentityTransform -- when latent_dim == input_dim, model_initialization.py:93-94)
+    augpre_hid = n_augpre = aug_hid = n_aug = 0
+    if has_aug:
+        if not is_global:
+            augpre_hid, n_augpre = _pack_plain_mlp(ar, flow_sd, "transforms.0.pre_attn_mlp", d_in)
+            _pack_attn(ar, flow_sd, "transforms.0.attn")
+        else:
+            augpre_hid, n_augpre = cfg["hidden_dims"][0], len(cfg["hidden_dims"]) - 1
+        aug_hid, n_aug = pack_conditioner("transforms.0.augment.noise_dist.net", "transforms.0.attn", d_in, 2 * (D - d_in))
+    elif has_cb:
+        # slot 0 of the per-cloud bias GEMM belongs to the augmenter: keep the slot numbering with an empty block
+        hid0 = cfg["hidden_dims"][0]
+        cb_cols.append(torch.zeros(hid0, ex + (E if is_global else 0), dtype=torch.float64))
+        cb_bias.append(torch.zeros(hid0, dtype=torch.float64))
     cb_slot = len(ar.table)
     if has_cb:
         ar.table.extend([0, 0, -1, -1])  # (w, b, whi, wlo): w/b patched below once every layer's columns are known
     ldj_const = 0.0
     t = 1
     hid = n_hid = pre_hid = n_pre = 0
+    cif_hid = n_cif = affcif_hid = n_affcif = 0
     for layer in range(L):
         p = f"transforms.{t}"
+        if cif:
+            cif_hid, n_cif, affcif_hid, n_affcif, ldj_cif = _pack_cif(ar, flow_sd, p, cfg)
+            ldj_const += ldj_cif
+            p = f"{p}.flow"
         if not is_global:
             pre_hid, n_pre = _pack_plain_mlp(ar, flow_sd, f"{p}.pre_conditioner.pre_attention_mlp", half)
             _pack_attn(ar, flow_sd, f"{p}.pre_conditioner.attn")
+        if cpl_kind == 2:
+            ar.vector(torch.cat([_d(flow_sd, f"{p}.transform.{leaf}") for leaf in ("scale", "shift", "rescale", "reshift")]))
         hid, n_hid = pack_conditioner(f"{p}.transform.nn", None if is_global else f"{p}.pre_conditioner.attn",
-                                      half, 2 * (D - half))
+                                      half, cpl_out, interleave=(cpl_kind == 0))
         t += 1
         if layer != L - 1:
-            shift, log_scale = _d(flow_sd, f"transforms.{t}.shift")[0], _d(flow_sd, f"transforms.{t}.log_scale")[0]
-            t += 1
-            lo, up = _d(flow_sd, f"transforms.{t}.lower_entries"), _d(flow_sd, f"transforms.{t}.upper_entries")
-            dg = _d(flow_sd, f"transforms.{t}.unconstrained_upper_diag")
-            Lm = torch.eye(D, dtype=torch.float64)
-            il = np.tril_indices(D, k=-1)
-            Lm[il[0], il[1]] = lo
-            Um = torch.zeros(D, D, dtype=torch.float64)
-            iu = np.triu_indices(D, k=1)
-            Um[iu[0], iu[1]] = up
-            diag = F.softplus(dg) + cfg["linear_lu_eps"]
-            Um[range(D), range(D)] = diag
-            Wp = Lm @ Um @ torch.diag(torch.exp(-log_scale))
+            if cfg["act_norm"]:
+                shift, log_scale = _d(flow_sd, f"transforms.{t}.shift")[0], _d(flow_sd, f"transforms.{t}.log_scale")[0]
+                t += 1
+            else:
+                shift, log_scale = torch.zeros(D, dtype=torch.float64), torch.zeros(D, dtype=torch.float64)
+            Wperm, ldj_perm = permuter_matrix(flow_sd, t, cfg)
+            Wp = Wperm @ torch.diag(torch.exp(-log_scale))
             wdiag = torch.diagonal(Wp).clone()
             ar.linear(Wp - torch.diag(wdiag), -(Wp @ shift), D)   # off-diagonal part in the GEMM ...
             ar.vector(wdiag)                                      # ... the diagonal in its epilogue (fp32, exact input)
-            ldj_const += float((-log_scale).sum() + torch.log(diag).sum())
+            ldj_const += float((-log_scale).sum()) + ldj_perm
             t += 1
     if not is_global:
         pre_hid = pre_hid or cfg["pre_attention_mlp_hidden_dims"][0]
@@ -335,12 +418,16 @@ def pack_flow(flow_sd, config, tc_format="tf32"):
         w_off, b_off = ar.table[:2]
         ar.table = saved
         ar.table[cb_slot], ar.table[cb_slot + 1] = w_off, b_off
-    assert hid == aug_hid, "coupling and augment conditioners must share the hidden width"
+    assert not has_aug or hid == aug_hid, "coupling and augment conditioners must share the hidden width"
     ar.table[0] = struct.unpack("<q", struct.pack("<d", ldj_const))[0]
     arena, table = ar.finish()
+    clamp = cfg["clamp_dist"] if cif and cfg["clamp_dist"] else 0.0
+    clamp_bits = struct.unpack("<i", struct.pack("<f", float(clamp)))[0]
     header = np.asarray([FLOW_MAGIC, TC_FORMATS[tc_format], L, D, d_in, half, ex, int(is_global), E, inner,
                          cfg["attn_input_dim"], hid, n_hid, pre_hid or 0, n_pre, aug_hid, n_aug,
-                         augpre_hid, n_augpre], dtype=np.int32)
+                         augpre_hid, n_augpre,
+                         cpl_kind, cfg["num_bins_spline"], ACT_CODES[cfg["coupling_block_nonlinearity"]], int(has_aug),
+                         cfg["cif_latent_dim"] if cif else 0, cif_hid, n_cif, affcif_hid, n_affcif, clamp_bits], dtype=np.int32)
     return header, table, arena
 
 

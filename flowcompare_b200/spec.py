@@ -258,7 +258,10 @@ def _draw(key, shape, g, perturb, config):
     if len(shape) == 1 and shape[0] == 1 and leaf in ("scale", "shift", "rescale", "reshift"):
         # ExponentialCoupling / ExponentialCombiner squashing scalars (models/exponential_coupling.py:22-25)
         base = {"scale": 0.125, "shift": 0.0, "rescale": 1.0, "reshift": 0.0}[leaf]
-        return torch.full(shape, base) + (_randn(shape, g) * 0.02 if perturb else 0.0)
+        # shift / reshift move EVERY entry of the n x n generator: a rank-one part with eigenvalue n * offset, so their
+        # perturbation shrinks with n (expm would otherwise amplify the latent by e^(n * 0.04) per layer)
+        amp = 0.02 if leaf in ("scale", "rescale") else 0.25 / config["latent_dim"]
+        return torch.full(shape, base) + (_randn(shape, g) * amp if perturb else 0.0)
     if leaf == "w":   # FullCombiner (orthogonal at init) / ExponentialCombiner (randn): any well-conditioned matrix will do
         if config["permuter_type"] == "ExponentialCombiner":
             return _randn(shape, g)
@@ -293,7 +296,13 @@ def _draw(key, shape, g, perturb, config):
         return _randn(shape, g) * 0.05 if perturb else torch.zeros(shape)
     if leaf == "weight":
         fan_in = int(np.prod(shape[1:]))
-        return _uniform(shape, 1.0 / math.sqrt(fan_in), g)
+        w = _uniform(shape, 1.0 / math.sqrt(fan_in), g)
+        if config.get("flow_type") == "ExponentialCoupling" and key.endswith("transform.nn.out_layer.weight"):
+            # the n x n generator of expm: keep its norm (hence the growth of |z| per layer) independent of n, so that
+            # log-probs of a 150-wide coupling stay O(100) and an absolute 1e-3 tolerance is meaningful in fp32
+            n2 = config["latent_dim"] - config["latent_dim"] // 2
+            w = w * min(1.0, 8.0 / n2)
+        return w
     if leaf == "bias":
         return _uniform(shape, 0.05, g)
     raise KeyError(f"no initialiser for {key}")

@@ -179,6 +179,35 @@ FC_API int fc_flow_log_prob(const fc_flow* h, const float* x, const float* conte
                      const float* eps, float* log_prob_out, int B, int N, int Nc,
                      void* workspace, int64_t workspace_bytes, int precision, fc_stream_t stream);
 
+/* Flows built from the transforms no shipped config selects (reference model_initialization.py:95-131): the packed model
+ * says which coupling it carries -- `RationalQuadraticSplineCoupling.forward` (models/spline_coupling.py:187-210 over
+ * :24-169), `ExponentialCoupling.forward` (models/exponential_coupling.py:44-58) -- which permuter (`Permuter`,
+ * `FullCombiner`, `ExponentialCombiner`, models/permuters.py:15-66, folded with ActNorm into the same 300x300 GEMM as
+ * LinearLU), ReLU conditioners, and the identity augmenter (latent_dim == input_dim: pass eps = NULL); fc_flow_log_prob
+ * runs all of them.  `CIFblock.forward` (models/cif_block.py:71-100: `Augment`, `Reverse`, `AffineCoupling`, ActNorm,
+ * `Reverse`, `Slice` of models/slice.py:31-44, then the coupling) draws noise of its own in every block, so flows with
+ * latent_dim < cif_latent_dim go through fc_flow_log_prob_cif: eps_cif [L, B, N, fc_flow_cif_noise_dim(h)] holds the
+ * blocks' N(0,1) draws in transform-list order.                                                                  */
+FC_API int fc_flow_log_prob_cif(const fc_flow* h, const float* x, const float* context, const float* extra,
+                         const float* eps, const float* eps_cif, float* log_prob_out, int B, int N, int Nc,
+                         void* workspace, int64_t workspace_bytes, int precision, fc_stream_t stream);
+FC_API int fc_flow_cif_noise_dim(const fc_flow* h);
+
+/* Op-level entry points of the two couplings' elementwise tails (the conditioner MLP is a chain of fc_gemm calls).
+ * fc_rq_spline replaces `unconstrained_rational_quadratic_spline(inputs, unnormalized_widths, unnormalized_heights,
+ * unnormalized_derivatives, inverse)` (reference models/spline_coupling.py:24-66 over :69-169; 'linear' tails, tail bound 3,
+ * num_bins <= 16): params [M][ldp], element j's (3*num_bins+1) values contiguous as [widths | heights | derivatives] (the
+ * reshape + split of :197-198); x [M][ldx], n elements per row, transformed in place; forward ADDS the row's summed
+ * log|det| to logabsdet_rowsum[row] (zero it first), inverse ignores it.
+ * fc_expm_action replaces the x2 update of `ExponentialCoupling.forward / .inverse` (reference
+ * models/exponential_coupling.py:48-58, :68-77): params [M][ldp] = [w n*n | b n] per row, squash4 = device pointer to
+ * (scale, shift, rescale, reshift); forward x <- expm(W) x + b and trace_rowsum[row] += trace W, inverse
+ * x <- expm(-W)(x - b); n <= 256.  expm(W) is never formed: its action on the vector is computed.               */
+FC_API int fc_rq_spline(const float* params, int ldp, float* x, int ldx, int n, int num_bins, int M,
+                 float* logabsdet_rowsum, int inverse, fc_stream_t stream);
+FC_API int fc_expm_action(const float* params, int ldp, float* x, int ldx, int n, const float* squash4,
+                   float* trace_rowsum, int M, int inverse, fc_stream_t stream);
+
 /* Same pass, additionally returning the final latent z_out [B,N,latent] (the point of the base density; the input of
  * the sampling pass run backwards).                                                                              */
 FC_API int fc_flow_forward(const fc_flow* h, const float* x, const float* context, const float* extra,

@@ -24,6 +24,7 @@ from oracle import refload
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
+_T = dict(n_flow_layers=3, sample_size=96, n_samples_context=128)
 # name -> (arch label, config overrides, batch, weight seed, input seed)
 FIXTURES = {
     "tiny_dgcnn_attn": ("dgcnn_attn", dict(n_flow_layers=3, sample_size=96, n_samples_context=128), 2, 11, 21),
@@ -37,7 +38,24 @@ FIXTURES = {
     "full_dgcnn_global": ("dgcnn_global", {}, 1, 3, 5),
     "full_paconv_attn": ("paconv_attn", {}, 1, 4, 6),
     "full_paconv_attn_extra": ("paconv_attn_extra", {}, 1, 5, 7),
+    # transforms north_star names but no shipped YAML selects, built by editing the config keys
+    # `initialize_flow` reads (reference model_initialization.py:95-131, models/cif_block.py:30-46)
+    "a18_spline": ("dgcnn_attn", dict(_T, flow_type="RationalQuadraticSplineCoupling", latent_dim=24, cif_latent_dim=24), 2, 31, 41),
+    "a18_spline_extra300": ("dgcnn_attn_extra", dict(_T, n_flow_layers=2, flow_type="RationalQuadraticSplineCoupling"), 1, 32, 42),
+    "a18_expo": ("dgcnn_attn", dict(_T, flow_type="ExponentialCoupling", latent_dim=24, cif_latent_dim=24), 2, 33, 43),
+    "a18_expo_global300": ("dgcnn_global", dict(_T, n_flow_layers=2, sample_size=48, flow_type="ExponentialCoupling",
+                                                coupling_expm_algo="original"), 1, 34, 44),
+    "a18_cif": ("dgcnn_attn", dict(_T, latent_dim=24, cif_latent_dim=32), 2, 35, 45),
+    "a18_cif_spline_clamp": ("dgcnn_attn", dict(_T, latent_dim=24, cif_latent_dim=30, clamp_dist=0.9,
+                                                flow_type="RationalQuadraticSplineCoupling"), 2, 36, 46),
+    "a18_permute_relu": ("dgcnn_attn", dict(_T, permuter_type="random_permute", coupling_block_nonlinearity="RELU",
+                                            latent_dim=24, cif_latent_dim=24), 2, 37, 47),
+    "a18_fullcombiner_noactnorm": ("dgcnn_attn", dict(_T, permuter_type="FullCombiner", act_norm=False, latent_dim=24,
+                                                      cif_latent_dim=24), 2, 38, 48),
+    "a18_expcombiner_global": ("dgcnn_global", dict(_T, permuter_type="ExponentialCombiner", latent_dim=24, cif_latent_dim=24), 2, 39, 49),
+    "a18_identity_augmenter": ("dgcnn_attn", dict(_T, latent_dim=6, cif_latent_dim=6), 2, 40, 50),
 }
+A18 = [k for k in FIXTURES if k.startswith("a18_")]
 
 
 def fixture_inputs(name):
@@ -62,7 +80,11 @@ def run_reference(cfg, fsd, esd, batch):
         md["input_embedder"].load_state_dict(esd)
         dcfg = configs.derive(cfg)
         orig = tdn._standard_normal
-        tdn._standard_normal = lambda shape, dtype, device: batch["eps"].to(dtype).reshape(shape)
+        # every RNG draw of the forward, in the order the reference makes them: the augmenter's (absent for the identity
+        # augmenter), then one per CIF block
+        draws = ([batch["eps"]] if dcfg["latent_dim"] > dcfg["input_dim"] else []) + list(batch.get("eps_cif", []))
+        it = iter(draws)
+        tdn._standard_normal = lambda shape, dtype, device: next(it).to(dtype).reshape(shape)
         try:
             loss, lp, bpd = mi.inner_loop((batch["extract_0"], batch["extract_1"], batch["extra_context"]), md, dcfg)
         finally:

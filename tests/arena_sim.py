@@ -83,14 +83,14 @@ def lin(l, A1, A2=None, bias=None):
     return y + b if b is not None else y
 
 
-def mlp_hidden(m, A1, A2=None, bias=None):
-    h = F.gelu(lin(m["inp"], A1, A2, bias))
+def mlp_hidden(m, A1, A2=None, bias=None, act=F.gelu):
+    h = act(lin(m["inp"], A1, A2, bias))
     res = None
     for i, l in enumerate(m["hidden"]):
         if i % 2 == 0:
-            res, h = h, F.gelu(lin(l, h))
+            res, h = h, act(lin(l, h))
         else:
-            h = F.gelu(res + lin(l, h))
+            h = act(res + lin(l, h))
     return h
 
 
@@ -99,8 +99,8 @@ def read_attn(c, attn_in, E, inner):
                 kv=c.linear(E, 0, 2 * inner, False))
 
 
-def attention_block(pre, at, lat_cols, context, B, N, inner):
-    h = mlp_hidden(pre, lat_cols)
+def attention_block(pre, at, lat_cols, context, B, N, inner, act=F.gelu):
+    h = mlp_hidden(pre, lat_cols, act=act)
     h4 = lin(pre["out"], h)
     mu = h4.mean(-1, keepdim=True)
     rstd = torch.rsqrt(((h4 - mu) ** 2).mean(-1, keepdim=True) + 1e-5)
@@ -113,19 +113,30 @@ def attention_block(pre, at, lat_cols, context, B, N, inner):
     return (w @ kv[..., inner:]).reshape(B * N, inner)
 
 
-def flow_log_prob(packed, x, context, extra, eps):
+def flow_log_prob(packed, x, context, extra, eps, eps_cif=None):
+    """Mirrors csrc/flow.cu: flow_forward (header words 19.. select the coupling kind, the conditioner non-linearity, the
+    identity augmenter and the CIF block; see packing.pack_flow)."""
+    from oracle import port
     header, table, arena = packed
+    hd = [int(v) for v in header]
     (_, _, L, D, d_in, half, ex, is_global, E, inner, attn_in, hid, n_hid, pre_hid, n_pre, aug_hid, n_aug,
-     augpre_hid, n_augpre) = [int(v) for v in header]
+     augpre_hid, n_augpre) = hd[:19]
+    cpl_kind, nb, act_code, has_aug, D2, cif_hid, n_cif, affcif_hid, n_affcif = hd[19:28] if len(hd) >= 29 else (0, 0, 1, 1, 0, 0, 0, 0, 0)
+    clamp = struct.unpack("<f", struct.pack("<i", hd[28]))[0] if len(hd) >= 29 else 0.0
+    act = {1: F.gelu, 3: F.relu}[act_code]
+    n2 = D - half
+    S = D2 - D if D2 else 0
+    cpl_out = {0: 2 * n2, 1: (3 * nb + 1) * half, 2: n2 * n2 + n2}[cpl_kind]
     c = Cursor(table, arena)
     ldj_const = struct.unpack("<d", struct.pack("<q", c.next()))[0]
     B, N = x.shape[0], x.shape[1]
     M = B * N
     k2 = 0 if is_global else inner
-    if not is_global:
-        augpre = c.mlp(d_in, 0, augpre_hid, n_augpre, attn_in)
-        augattn = read_attn(c, attn_in, E, inner)
-    aug = c.mlp(d_in, k2, aug_hid, n_aug, 2 * (D - d_in))
+    if has_aug:
+        if not is_global:
+            augpre = c.mlp(d_in, 0, augpre_hid, n_augpre, attn_in)
+            augattn = read_attn(c, attn_in, E, inner)
+        aug = c.mlp(d_in, k2, aug_hid, n_aug, 2 * (D - d_in))
     has_cb = bool(ex) or bool(is_global)
     cb = None
     if has_cb:
@@ -142,34 +153,68 @@ def flow_log_prob(packed, x, context, extra, eps):
             return None
         return cb[:, slot * hid:(slot + 1) * hid].repeat_interleave(N, dim=0)
 
-    lat = torch.zeros(M, D)
+    lat = torch.zeros(M, max(D, D2))
     lat[:, :d_in] = x.reshape(M, d_in)
     o = None
-    if not is_global:
-        o = attention_block(augpre, augattn, lat, context, B, N, inner)
-    h = mlp_hidden(aug, lat, o, cloud_bias(0))
-    st = lin(aug["out"], h)
-    mean, log_std = st[:, 0::2], st[:, 1::2]
-    e = eps.reshape(M, D - d_in)
-    lat[:, d_in:] = mean + torch.exp(log_std) * e
-    logp = (0.5 * e * e + log_std + 0.5 * math.log(2 * math.pi)).sum(-1)
+    logp = torch.zeros(M)
+    if has_aug:
+        if not is_global:
+            o = attention_block(augpre, augattn, lat, context, B, N, inner, act)
+        h = mlp_hidden(aug, lat, o, cloud_bias(0), act)
+        st = lin(aug["out"], h)
+        mean, log_std = st[:, 0::2], st[:, 1::2]
+        e = eps.reshape(M, D - d_in)
+        lat[:, d_in:D] = mean + torch.exp(log_std) * e
+        logp = (0.5 * e * e + log_std + 0.5 * math.log(2 * math.pi)).sum(-1)
     for l in range(L):
+        if D2:
+            cifnet = c.mlp(D, 0, cif_hid, n_cif, 2 * S)
+            affcif = c.mlp(S, 0, affcif_hid, n_affcif, 2 * D)
+            sc, bi = c.vec(D2), c.vec(D2)
+
+            def cond_normal():
+                pr = lin(cifnet["out"], mlp_hidden(cifnet, lat))
+                sigma = torch.exp(pr[:, S:])
+                return pr[:, :S], (sigma.clamp_max(clamp) if clamp > 0 else sigma)
+            mean, sigma = cond_normal()
+            e = eps_cif[l].reshape(M, S)
+            lat[:, D:D2] = mean + sigma * e
+            logp = logp + (0.5 * e * e + torch.log(sigma) + 0.5 * math.log(2 * math.pi)).sum(-1)
+            st = lin(affcif["out"], mlp_hidden(affcif, lat[:, D:D2]))
+            s = (2 * torch.sigmoid(st[:, 0::2]) - 1) + 1
+            lat[:, :D] = lat[:, :D] * s + st[:, 1::2]
+            logp = logp + torch.log(s).sum(-1)
+            lat = lat * sc + bi
+            mean, sigma = cond_normal()
+            e = (lat[:, D:D2] - mean) / sigma
+            logp = logp - (0.5 * e * e + torch.log(sigma) + 0.5 * math.log(2 * math.pi)).sum(-1)
         if not is_global:
             pre = c.mlp(half, 0, pre_hid, n_pre, attn_in)
             at = read_attn(c, attn_in, E, inner)
-            o = attention_block(pre, at, lat, context, B, N, inner)
-        cpl = c.mlp(half, k2, hid, n_hid, 2 * (D - half))
-        h = mlp_hidden(cpl, lat, o, cloud_bias(l + 1))
+            o = attention_block(pre, at, lat, context, B, N, inner, F.gelu if D2 else act)
+        sq = c.vec(4) if cpl_kind == 2 else None
+        cpl = c.mlp(half, k2, hid, n_hid, cpl_out)
+        h = mlp_hidden(cpl, lat, o, cloud_bias(l + 1), act)
         st = lin(cpl["out"], h)
-        s_raw, t = st[:, 0::2], st[:, 1::2]
-        s = (2 * torch.sigmoid(s_raw) - 1) + 1
-        lat = torch.cat((lat[:, :half], lat[:, half:] * s + t), dim=1)
-        logp = logp + torch.log(s).sum(-1)
+        if cpl_kind == 0:
+            s_raw, t = st[:, 0::2], st[:, 1::2]
+            s = (2 * torch.sigmoid(s_raw) - 1) + 1
+            y2, ldj = lat[:, half:D] * s + t, torch.log(s).sum(-1)
+        elif cpl_kind == 1:
+            pr = st.reshape(M, half, 3 * nb + 1)
+            y2, lad = port.rq_spline(lat[:, half:D], pr[..., :nb], pr[..., nb:2 * nb], pr[..., 2 * nb:])
+            ldj = lad.sum(-1)
+        else:
+            W = (sq[2] * torch.tanh(sq[0] * st[:, :n2 * n2] + sq[1]) + sq[3] + 1e-8).reshape(M, n2, n2)
+            y2 = torch.matmul(torch.matrix_exp(W), lat[:, half:D].unsqueeze(-1)).squeeze(-1) + st[:, n2 * n2:]
+            ldj = W.diagonal(dim1=-2, dim2=-1).sum(-1)
+        lat = torch.cat((lat[:, :half], y2, lat[:, D:]), dim=1)
+        logp = logp + ldj
         if l != L - 1:
             lu = c.linear(D, 0, D)
-            lat = lin(lu, lat) + c.vec(D) * lat
+            lat = torch.cat((lin(lu, lat[:, :D]) + c.vec(D) * lat[:, :D], lat[:, D:]), dim=1)
     assert c.pos == len(c.table), (c.pos, len(c.table))
-    logp = logp + ldj_const + (-0.5 * math.log(2 * math.pi) - 0.5 * lat ** 2).sum(-1)
+    logp = logp + ldj_const + (-0.5 * math.log(2 * math.pi) - 0.5 * lat[:, :D] ** 2).sum(-1)
     return logp.view(B, N)
 
 

@@ -294,3 +294,72 @@ def test_port_sampling_pass_matches_reference_golden(name):
     ex = None if extra is None else extra.unsqueeze(1).expand(-1, P, -1)
     got = port.flow_sample(fsd, dcfg, z, ctx, ex)
     assert (got - gold["x"]).abs().max().item() < 1e-4
+
+
+# --------------------------------------------------------------------------- transforms no shipped config selects
+from oracle.make_golden import A18  # noqa: E402
+
+
+def _a18_port_inputs(name):
+    cfg, fsd, esd, batch = fixture_inputs(name)
+    dcfg = configs.derive(cfg)
+    B, N = batch["extract_1"].shape[:2]
+    if dcfg["global"]:
+        g, _ = port.dgcnn_embed_global(esd, batch["extract_0"], cfg["n_neighbors"])
+        ctx_port, ctx = g.unsqueeze(1).expand(B, N, g.shape[1]), g
+    else:
+        ctx, _ = port.dgcnn_embed(esd, batch["extract_0"], cfg["n_neighbors"])
+        ctx_port = ctx
+    extra = batch["extra_context"]
+    ex_port = None if extra is None else extra.unsqueeze(1).expand(B, N, 1)
+    return cfg, dcfg, fsd, batch, ctx_port, ctx, ex_port, extra
+
+
+@pytest.mark.parametrize("name", A18)
+def test_port_a18_transforms_match_reference_golden(name):
+    """oracle/port.py: rq_spline / spline and exponential couplings / CIF block / Permuter, FullCombiner, ExponentialCombiner /
+    ReLU conditioners / identity augmenter against the UNMODIFIED reference's outputs (tests/golden/a18_*.pt)."""
+    gold = load_golden(name)
+    cfg, dcfg, fsd, batch, ctx_port, _, ex_port, _ = _a18_port_inputs(name)
+    lp = port.flow_log_prob(fsd, dcfg, batch["extract_1"], ctx_port, ex_port, batch["eps"], eps_cif=batch.get("eps_cif"))
+    assert (lp - gold["log_prob"]).abs().max().item() < 1e-3
+    assert abs(-lp.mean().item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
+
+
+@pytest.mark.parametrize("name", A18)
+def test_packed_a18_algebra_matches_port(name):
+    """pack_flow for the same variants (Reverse folded into the CIF block's affine coupling, every permuter as one matrix with
+    ActNorm, un-interleaved spline / exponential conditioner outputs), interpreted on the CPU, against the port."""
+    cfg, dcfg, fsd, batch, ctx_port, ctx, ex_port, extra = _a18_port_inputs(name)
+    want = port.flow_log_prob(fsd, dcfg, batch["extract_1"], ctx_port, ex_port, batch["eps"], eps_cif=batch.get("eps_cif"))
+    packed = packing.pack_flow(fsd, cfg, "tf32")
+    got = arena_sim.flow_log_prob(packed, batch["extract_1"], ctx, extra, batch["eps"], batch.get("eps_cif"))
+    assert (got - want).abs().max().item() < 2e-4
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_a18_state_dict_layout_matches_reference():
+    models, mi = refload.load()
+    from oracle.make_golden import FIXTURES
+    for name in A18:
+        label, over, *_ = FIXTURES[name]
+        cfg = configs.get_config(label, **dict(over, n_flow_layers=2))
+        md = mi.initialize_flow(dict(cfg), "cpu", "test")
+        fsd, _ = spec.random_state_dicts(cfg, seed=0)
+        rf = md["flow"].state_dict()
+        assert list(rf.keys()) == list(fsd.keys()), name
+        assert all(tuple(rf[k].shape) == tuple(fsd[k].shape) and rf[k].dtype == fsd[k].dtype for k in rf), name
+
+
+def test_rq_spline_port_inverse_round_trip():
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(64, 40, generator=g) * 8 - 4)           # some elements in the linear tails
+    uw, uh, ud = torch.randn(64, 40, 8, generator=g), torch.randn(64, 40, 8, generator=g), torch.randn(64, 40, 9, generator=g)
+    y, lad = port.rq_spline(x, uw, uh, ud)
+    xb, _ = port.rq_spline(y, uw, uh, ud, inverse=True)
+    assert (xb - x).abs().max().item() < 1e-3                # fp32: bins with slope ~1e-3 amplify the rounding of y
+    y64, _ = port.rq_spline(x.double(), uw.double(), uh.double(), ud.double())
+    xb64, _ = port.rq_spline(y64, uw.double(), uh.double(), ud.double(), inverse=True)
+    assert (xb64 - x.double()).abs().max().item() < 1e-9
+    outside = x.abs() > 3
+    assert torch.equal(y[outside], x[outside]) and (lad[outside] == 0).all()
