@@ -101,7 +101,16 @@ constexpr int TC_STAGES = 5;                   // shared-memory stages: a load i
 #endif
 constexpr int TC_CONV_WARPS_N = TC_CONV_WARPS;
 static_assert(TC_CONV_WARPS_N == 4 || TC_CONV_WARPS_N == 8, "converter warps: 4 or 8");
-constexpr int TC_MMA_WARPS = TC_SPLIT_ISSUE ? 2 : 1;
+#ifndef TC_PINGPONG
+#define TC_PINGPONG 0                          // 1: two MMA issuer warps that take turns on K-BLOCKS, ordered by a hand-off barrier.
+#endif                                         // Bitwise reproducible (tested) and 12 % faster with loads / conversion / epilogue knocked out
+                                               // (499 vs 569 cycles per k-block), but equal in the real kernel (145.2 vs 145.6 us): with
+                                               // fp16 operands the k-block is paced by SHARED-MEMORY traffic, not by the issuer
+#ifndef TC_PP_FENCE
+#define TC_PP_FENCE 1                          // tcgen05 fences around the hand-off (the PTX memory model's ordering of the two issuers' MMAs)
+#endif
+static_assert(!(TC_PINGPONG && TC_SPLIT_ISSUE), "one issuer scheme at a time");
+constexpr int TC_MMA_WARPS = (TC_SPLIT_ISSUE || TC_PINGPONG) ? 2 : 1;
 constexpr int TC_CONV_WARP0 = 1 + TC_MMA_WARPS;               // first converter warp (any 4 consecutive warps cover the 4 TMEM lane quadrants)
 constexpr int TC_EPI_WARP0 = TC_CONV_WARP0 + TC_CONV_WARPS_N; // first epilogue warp
 constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + 8);           // TMA, MMA issuer(s), converter warps, 8 epilogue warps
@@ -165,6 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     constexpr bool PARITY = F16 && TC_CONV_PARITY && TC_CONV_WARPS_N == 8;
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 4];
+    __shared__ __align__(8) uint64_t turn_bar;   // ping-pong issuers: phase g completes when k-block g has been issued
     __shared__ uint32_t tmem_base_slot;
     __shared__ float ldj_sm[TC_BM];
     __shared__ __align__(16) float bias_sm2[2][96];   // the tile's bias (and LayerNorm-q column sums), by accumulator buffer
@@ -206,9 +216,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     if (threadIdx.x == 0) {
         constexpr int PER_WARP = TC_WARP_ARRIVE ? 1 : 32;   // arrivals a warp contributes per event
         constexpr int CONV_GROUPS = PARITY ? 2 : 1;         // converter groups that take turns on k-blocks
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], PER_WARP * TC_CONV_WARPS_N / CONV_GROUPS); mbar_init(&w_free[s], TC_MMA_WARPS); }
-        for (int s = 0; s < TC_TSTAGES / 2; ++s) { mbar_init(&conv[s], PER_WARP * 8 / CONV_GROUPS); mbar_init(&tfree[s], TC_MMA_WARPS); }   // one pair per K-BLOCK of A in tensor memory
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&a_free[s], PER_WARP * TC_CONV_WARPS_N / CONV_GROUPS); mbar_init(&w_free[s], TC_SPLIT_ISSUE ? 2 : 1); }
+        for (int s = 0; s < TC_TSTAGES / 2; ++s) { mbar_init(&conv[s], PER_WARP * 8 / CONV_GROUPS); mbar_init(&tfree[s], TC_SPLIT_ISSUE ? 2 : 1); }   // one pair per K-BLOCK of A in tensor memory
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], TC_MMA_WARPS); mbar_init(&acc_free[s], PER_WARP * 8); }
+        mbar_init(&turn_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -268,6 +279,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         constexpr int KBI = (TC_TSTAGES / 2 >= 4) ? TC_ISSUE_KBLOCK : 1;   // 3xTF32 has only 2 k-blocks of A stages in tensor memory
         int it = 0;
         long long m_conv = 0, m_acc = 0, m_probe = 0, m_issue = 0;
+        if constexpr (TC_PINGPONG) {
+            // TWO issuers taking turns on k-blocks.  Knock-out builds showed the single issuer's loop to be ADDITIVE: ~285 cycles
+            // of barrier work per k-block (wait, fence, probe, commits) plus the ~288 cycles it sits blocked in the issue of its
+            // six MMAs (the tensor queue holds about two), 569 together with everything else removed -- the tensor pipe idled
+            // while the warp did its bookkeeping.  Here warp 1 issues the even k-blocks and warp 2 the odd ones; each does its
+            // bookkeeping while the other is blocked issuing.  The accumulation ORDER stays fixed (bitwise reproducible
+            // results): k-block g is only issued after the hand-off barrier says that k-block g-1 has been issued completely,
+            // and the MMAs of one CTA execute in issue order.
+            const int me = warp - 1;
+            uint32_t g = 0;
+            int s = 0, ks = 0; uint32_t kph = 0;
+            TC_T(m_t0);
+            for (int L = blockIdx.x; L < total_tiles; L += gridDim.x, ++it) {
+                const int n_tile = L % n_tiles;
+                const int tile_bn = tile_bn_of(n_tile);
+                const int buf = it & 1;
+                const uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(tile_bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                const uint32_t d_main = tmem + TC_COL_ACC * buf, d_corr = d_main + TC_COL_CORR;
+                bool acc_ok = false;
+                for (int t = 0; t < T; ++t, ++g) {
+                    if ((int)(g & 1) == me) {
+                        if (!acc_ok) { mbar_wait(&acc_free[buf], ((it >> 1) & 1) ^ 1, 190); acc_ok = true; }   // epilogue of tile it-2 drained this buffer
+                        TC_T(mc0);
+                        mbar_wait(&conv[ks], kph, 300 + t);
+                        TC_T(mc1);
+                        TC_ACC(m_conv, mc0, mc1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (g > 0) {
+                            mbar_wait(&turn_bar, (g - 1) & 1, 360);                  // k-block g-1 has been issued
+                            if (TC_PP_FENCE) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+                        TC_T(mp1);
+                        TC_ACC(m_probe, mc1, mp1);
+                        if (elect_one()) {
+                            const uint64_t dbh = F16 ? make_kmajor_sw64_desc(smem_u32(w_hi(s))) : make_kmajor_sw128_desc(smem_u32(w_hi(s)));
+                            const uint64_t dbl = F16 ? make_kmajor_sw64_desc(smem_u32(w_lo(s))) : make_kmajor_sw128_desc(smem_u32(w_lo(s)));
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t t_hi = tmem + TC_COL_A + TS_COLS * (2 * ks + h), t_lo = t_hi + TS_COLS / 2;
+                                if (F16) {
+                                    const uint64_t adv = (uint64_t)(h * 32 >> 4);
+                                    umma_f16_ts(d_corr, t_lo, dbh + adv, idesc, (t | h) != 0);
+                                    umma_f16_ts(d_corr, t_hi, dbl + adv, idesc, 1);
+                                    umma_f16_ts(d_main, t_hi, dbh + adv, idesc, (t | h) != 0);
+                                } else {
+#pragma unroll
+                                    for (int kk = 0; kk < 2; ++kk) {
+                                        const int k = 2 * h + kk;
+                                        const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                                        umma_tf32_ts(d_corr, t_lo + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                                        umma_tf32_ts(d_corr, t_hi + 8 * kk, dbl + adv, idesc, 1);
+                                        umma_tf32_ts(d_main, t_hi + 8 * kk, dbh + adv, idesc, (t | k) != 0);
+                                    }
+                                }
+                            }
+                            if (TC_PP_FENCE) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            mbar_arrive(&turn_bar);                      // the other issuer may go
+                            umma_commit(&tfree[ks]);
+                            umma_commit(&w_free[s]);
+                        }
+                        TC_T(mi1);
+                        TC_ACC(m_issue, mp1, mi1);
+                        __syncwarp();
+                    }
+                    s = s + 1 == TC_STAGES ? 0 : s + 1;
+                    ks = ks + 1 == TC_TSTAGES / 2 ? 0 : ks + 1; if (ks == 0) kph ^= 1;
+                }
+                // both issuers sign the tile off (an issuer without a k-block in this tile has nothing outstanding)
+                if (elect_one()) umma_commit(&acc_full[buf]);
+                __syncwarp();
+            }
+#if TC_PHASE_TIMERS
+            if (lane == 0 && warp == 1) {
+                atomicAdd(&fc_tc_dbg[0], 1ull); atomicAdd(&fc_tc_dbg[1], (unsigned long long)(clock64() - m_t0));
+                atomicAdd(&fc_tc_dbg[3], (unsigned long long)m_conv); atomicAdd(&fc_tc_dbg[4], (unsigned long long)m_acc);
+                atomicAdd(&fc_tc_dbg[10], (unsigned long long)m_probe); atomicAdd(&fc_tc_dbg[11], (unsigned long long)m_issue);
+            }
+#endif
+        } else {
         bool conv_seen = false;   // the next k-block's barrier was seen complete by the probe
         int s = 0;                // shared-memory stage of the next k-block
         int ks = 0; uint32_t kph = 0;   // tensor-memory A stage (one per k-block) of the next k-block and its barrier phase
@@ -353,6 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             atomicAdd(&fc_tc_dbg[10], (unsigned long long)m_probe); atomicAdd(&fc_tc_dbg[11], (unsigned long long)m_issue);
         }
 #endif
+        }   // single issuer / per-accumulator issuers
     } else if (warp < TC_EPI_WARP0) {
         // ===================================================== converters: fp32 smem row -> (hi, lo) in TMEM
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch

@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_transforms_gpu.py -q -s -k "rq_spline" 2>&1 | grep -E "passed|failed|^FAILED|spline n|inverse:"
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --no-extras > gpurun_out/ab5_bench.json 2>gpurun_out/ab5_bench.err; python -c "import json; d=json.load(open('gpurun_out/ab5_bench.json')); print('bench', d['value'], d['e2e']['value'], d['roofline']['achieved'], d['precision_check'], d['kernel_classes'])"
+python -m pytest tests/test_gpu_parity.py -x -q -k "gemm or deterministic" 2>&1 | tail -2
+python scripts/determinism_check.py 2>&1 | tail -3
+python scripts/gemm_time.py 2>&1 | tail -1
+for v in nofence single mmaonly koepi koconv noload; do FLOWCOMPARE_B200_LIB=flowcompare_b200/variants/lib_$v.so python scripts/gemm_time.py 2>&1 | tail -1; done
+FLOWCOMPARE_B200_LIB=flowcompare_b200/variants/lib_timers.so python scripts/tc_phases.py 2>&1 | tail -6 | head -3
