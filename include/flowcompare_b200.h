@@ -157,6 +157,20 @@ FC_API int fc_cross_attention_tc(const float* q, int ldq, const float* kv, int l
                           int B, int N, int Nc, int d, float scale, void* scratch, int64_t scratch_bytes,
                           fc_stream_t stream);
 
+/* ------------------------------------------------------------------ data-side ops ----------
+ * What the reference's loader does between reading a voxel and calling `inner_loop`.
+ * fc_fps_points replaces `voxel[fps(voxel, batch, ratio=n_samples/len(voxel), random_start=False)][:n_samples]`
+ * (reference dataloaders/ams_voxel_loader.py:298-307; torch_cluster.fps): furthest point sampling over ALL C point
+ * columns (C = 3 or 6), first pick = point 0, ties to the lowest index.  pts [B][n][ld]; idx_out [B][m];
+ * pts_out [B][m][ld_out] (first C columns written) or NULL.
+ * fc_co_unit_sphere replaces `co_unit_sphere(points_0, points_1, return_inverse=True)` (reference utils.py:259-280,
+ * called by ams_voxel_loader.py:357-358): the xyz columns of both clouds of a pair are shifted by their JOINT mean and
+ * divided by the largest norm, in place; inverse_out [B][4] = (mean xyz, furthest_distance) or NULL.            */
+FC_API int fc_fps_points(const float* pts, int ld, int B, int n, int C, int m, int32_t* idx_out, float* pts_out,
+                  int ld_out, fc_stream_t stream);
+FC_API int fc_co_unit_sphere(float* points_0, int n0, int ld0, float* points_1, int n1, int ld1, int B,
+                      float* inverse_out, fc_stream_t stream);
+
 /* ------------------------------------------------------------------ model handles ---------
  * A model is described by (header int32[], table int64[], arena fp32[] on the device), produced by
  * flowcompare_b200/packing.py from the reference's own `state_dict`s.  The arena

@@ -363,3 +363,17 @@ def test_rq_spline_port_inverse_round_trip():
     assert (xb64 - x.double()).abs().max().item() < 1e-9
     outside = x.abs() > 3
     assert torch.equal(y[outside], x[outside]) and (lad[outside] == 0).all()
+
+
+def test_fps_oracle_is_furthest_point_sampling():
+    """oracle/dataops_ref.py: fps (restating torch_cluster.fps as called by reference dataloaders/ams_voxel_loader.py:298-307):
+    starts at point 0, every pick maximises the distance to the already selected set (checked in float64), no repeats."""
+    import numpy as np
+    from oracle import dataops_ref
+    pts = np.random.RandomState(1).rand(400, 6).astype(np.float32)
+    idx = dataops_ref.fps(pts, 40)
+    assert idx[0] == 0 and len(set(idx.tolist())) == 40
+    x = pts.astype(np.float64)
+    for j in range(1, 40):
+        d = ((x[:, None, :] - x[None, idx[:j], :]) ** 2).sum(-1).min(1)
+        assert d[idx[j]] >= d.max() * (1 - 1e-6)
