@@ -288,6 +288,50 @@ def extras_single_gpu(args, eng, cfg, dev, precision, t_end, note):
     return out
 
 
+def extras_multi_gpu(args, eng, dev, precision, world, rank, note):
+    """Extra keys at N > 1 (every rank takes part; times are CUDA-event times, max over ranks, pairs are sharded with no
+    data-path collective): BASELINE configs[3] "dulcet-universe (DGCNN Attention + extra context) ... sharded over 2/4/8" at
+    SURVEY 8d's 20 pairs per GPU, and configs[4], the point-count sweep Nc = N in {2k..32k} of the bench architecture, with the
+    pairs of every point count sharded over the ranks."""
+    import torch.distributed as dist
+    from flowcompare_b200 import configs, engine, spec
+    out = {}
+
+    def timed_all(fn, steps, warmup=1):
+        ms = _timed(fn, steps, warmup=warmup)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    c4 = configs.get_config("dgcnn_attn_extra")
+    fsd, esd = spec.random_state_dicts(c4, seed=0)
+    e4 = engine.FlowCompareB200((fsd, esd), c4, device=dev, precision=precision)
+    del fsd, esd
+    for B4 in (20, args.batch):
+        b = spec.synthetic_batch(c4, B4, seed=200 + rank)
+        e0, e1, eps, ex = b["extract_0"].to(dev), b["extract_1"].to(dev), b["eps"].to(dev), b["extra_context"].to(dev)
+        ms = timed_all(lambda: e4.inner_loop((e0, e1, ex), eps=eps), 3, warmup=2)
+        out[f"pairs_per_gpu_{B4}"] = {"pairs_per_s": round(world * B4 / ms * 1e3, 2), "ms_per_step": round(ms, 3)}
+    e4.close()
+    del e4
+    torch.cuda.empty_cache()
+    note("extras: config 4 sharded done")
+    sweep = {}
+    for npts in (2048, 4096, 8192, 16384, 32768):
+        B = max(1, min(64, 131072 // npts))
+        g = torch.Generator().manual_seed(npts * 31 + rank)
+        e0 = (torch.rand(B, npts, 6, generator=g) * 2 - 1).to(dev)
+        e1 = (torch.rand(B, npts, 6, generator=g) * 2 - 1).to(dev)
+        ms = timed_all(lambda: eng.inner_loop((e0, e1, None), eps=None), 2, warmup=1)
+        sweep[str(npts)] = {"pairs_per_s": round(world * B / ms * 1e3, 3), "points_per_s": round(world * B * npts / ms * 1e3, 1),
+                            "ms_per_step": round(ms, 2), "pairs_per_step_per_gpu": B}
+        del e0, e1
+        torch.cuda.empty_cache()
+    note("extras: sharded sweep done")
+    return {"config4_dgcnn_attn_extra_sharded": dict(out, workload=configs.BASELINE_LABEL["dgcnn_attn_extra"], ranks=world),
+            "sweep_sharded": dict(sweep, ranks=world, workload="point-count sweep, Nc = N, dgcnn_attn")}
+
+
 def strong_scaling(eng, cfg, dev, world, rank, B_chunk, total_pairs=1024):
     """A FIXED evaluation set of 1024 pairs sharded over the ranks through flowcompare_b200.sharding.evaluate_sharded (the
     host logic of test_flow.evaluate_on_test: score, reduce to the running nats) with the real engine and NCCL: the one
@@ -505,6 +549,8 @@ def main():
     if not args.no_extras and not args.ncu:
         if world == 1:
             extras = extras_single_gpu(args, eng, cfg, dev, precision, time.perf_counter() + args.extras_budget_s, note)
+        else:
+            extras = extras_multi_gpu(args, eng, dev, precision, world, rank, note)
         try:
             extras["strong_scaling_fixed_set"] = strong_scaling(eng, cfg, dev, world, rank, B)
         except Exception as exc:
