@@ -175,9 +175,9 @@ def workload_config(args, cfg, B, where):
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
-    capture (profiles/r01_gemm_tc_ncu_full_summary.csv, made by scripts/ncu_summarize.py).  Static evidence, not
+    capture (profiles/r02_gemm_tc_ncu_full_summary.csv, made by scripts/ncu_summarize.py).  Static evidence, not
     measured in this run: bench.py never runs under a profiler."""
-    path = os.path.join(ROOT, "profiles", "r01_gemm_tc_ncu_full_summary.csv")
+    path = os.path.join(ROOT, "profiles", "r02_gemm_tc_ncu_full_summary.csv")   # first row: M=65536, N=K=512, GELU
     try:
         import csv
         with open(path) as f:
@@ -185,10 +185,10 @@ def ncu_traffic():
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tot = 0.0
         for k, v in row.items():
-            if k.startswith("dram__bytes_read.sum") or k.startswith("dram__bytes_write.sum"):
+            if k.startswith("dram__bytes_read.sum [") or k.startswith("dram__bytes_write.sum ["):
                 tot += float(v) * mult[k[k.index("[") + 1:-1]]
         return int(tot), ("ncu --set full, one gemm_tc_kernel launch M=65536 N=512 K=512 GELU (scripts/gemm_one.py): DRAM bytes of "
-                          "that launch; its algorithmic bytes are 4*(M*K + M*N) + 8*N*K = 270.5e6, i.e. no re-reads (L2 keeps "
+                          "that launch; its algorithmic bytes are 4*(M*K + M*N) + 4*N*K = 269.5e6 (fp16 hi + lo weights), i.e. no re-reads (L2 keeps "
                           "part of the output)")
     except Exception as exc:  # profile not present
         return None, f"no committed ncu capture readable: {exc}"

@@ -298,8 +298,9 @@ FlowWs carve_flow_ws(const fc_flow* f, int B, int N, int Nc, void* base) {
     w.q = take(M * 64); w.o = take(M * 64);
     w.mu = take(M); w.rstd = take(M);
     w.cpart = take(M * w.n_cpart); w.apart = take(M * w.n_apart);
-    w.kv = take((int64_t)B * Nc * 128);
-    w.kvs = take(fc_attention_tc_scratch_floats(B, Nc));   // TF32 hi/lo copies of k, v^T for the tcgen05 attention
+    // attention configs only (the global embedder's flow never runs an attention kernel)
+    w.kv = take(f->is_global ? 0 : (int64_t)B * Nc * 128);
+    w.kvs = take(f->is_global ? 0 : fc_attention_tc_scratch_floats(B, Nc));   // TF32 hi/lo copies of k, v^T for the tcgen05 attention
     w.cb = take((int64_t)B * w.cb_ld);
     w.cbA = take((int64_t)B * w.cbA_ld);
     {

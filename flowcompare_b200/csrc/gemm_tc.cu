@@ -76,6 +76,15 @@ constexpr int TC_STAGES = 5;                   // shared-memory stages: a load i
 #ifndef TC_KO_EPI
 #define TC_KO_EPI 0     // epilogue reads the accumulators but touches no global memory
 #endif
+#ifndef TC_CPL_STAGED
+#define TC_CPL_STAGED 1 // coupling epilogue: latent chunk through the staging tile (coalesced global accesses)
+#endif
+#ifndef TC_KO_CPLMEM
+#define TC_KO_CPLMEM 0  // coupling epilogue: no latent load / store (math stays)
+#endif
+#ifndef TC_KO_CPLMATH
+#define TC_KO_CPLMATH 0 // coupling epilogue: no exp / log (memory traffic stays)
+#endif
 #ifndef TC_ISSUE_KBLOCK
 #define TC_ISSUE_KBLOCK 1                      // MMA issuer: one synchronisation point per k-block (0: per half k-block)
 #endif
@@ -104,8 +113,8 @@ static_assert(TC_CONV_WARPS_N == 4 || TC_CONV_WARPS_N == 8, "converter warps: 4 
 #ifndef TC_PINGPONG
 #define TC_PINGPONG 0                          // 1: two MMA issuer warps that take turns on K-BLOCKS, ordered by a hand-off barrier.
 #endif                                         // Bitwise reproducible (tested) and 12 % faster with loads / conversion / epilogue knocked out
-                                               // (499 vs 569 cycles per k-block), but equal in the real kernel (145.2 vs 145.6 us): with
-                                               // fp16 operands the k-block is paced by SHARED-MEMORY traffic, not by the issuer
+                                               // (499 vs 569 cycles per k-block), but equal in the real kernel (145.2 vs 145.6 us): the
+                                               // k-block is paced by the TMA -> converter -> MMA -> commit latency chain
 #ifndef TC_PP_FENCE
 #define TC_PP_FENCE 1                          // tcgen05 fences around the hand-off (the PTX memory model's ordering of the two issuers' MMAs)
 #endif
@@ -140,7 +149,7 @@ constexpr int TC_COL_A = 4 * TC_BN_CAP;        // + TS_COLS * stage: first half 
 
 struct TcParams {
     GemmArgs g;
-    int BN;        // N tile (multiple of 16, <= 192)
+    int BN;        // widest N tile of the launch (multiple of 16, <= TC_BN_CAP = 96)
     int T1, T2;    // k-blocks of segment 1 / 2
     int n_tiles, m_tiles;
     int pdl;       // launched with programmatic stream serialization
@@ -647,18 +656,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             const bool vec_base = row0 + 32 <= a.M && (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0;
             const bool vec_res = RES && (a.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0 &&
                                  (!a.res_scale || (reinterpret_cast<uintptr_t>(a.res_scale) & 15) == 0);
+            // the accumulator loads of chunk c+1 are in flight while chunk c goes through its bias / activation / stores
+            uint32_t r[16], rc[16];
+            if (half * 16 < tile_bn) tmem_ld16x2_issue(acc_main + (uint32_t)(half * 16), acc_corr + (uint32_t)(half * 16), r, rc);
             for (int c0 = half * 16; c0 < tile_bn; c0 += 32) {
-                uint32_t r[16];
                 float v[16];
                 __syncwarp();
-                tmem_ld16(acc_main + (uint32_t)c0, r);
+                tmem_ld16x2_wait(r, rc);
     #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                {
-                    tmem_ld16(acc_corr + (uint32_t)c0, r);
-    #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = F16 ? fmaf(__uint_as_float(r[j]), 4.8828125e-4f, v[j]) : v[j] + __uint_as_float(r[j]);
-                }
+                for (int j = 0; j < 16; ++j)
+                    v[j] = F16 ? fmaf(__uint_as_float(rc[j]), 4.8828125e-4f, __uint_as_float(r[j])) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+                if (c0 + 32 < tile_bn) tmem_ld16x2_issue(acc_main + (uint32_t)(c0 + 32), acc_corr + (uint32_t)(c0 + 32), r, rc);
                 const int col = n0 + c0;
                 if (col >= a.N) continue;                     // warp-uniform
                 if (TC_KO_EPI) { if (v[0] == 123.456f) a.C[0] = v[1]; continue; }
@@ -667,8 +675,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     for (int j = 0; j < 16; ++j)
                         if (col + j < a.N) v[j] = rstd * (v[j] - mu * csum_sm[c0 + j]) + bias_sm[c0 + j];
                 } else if (bias_row && bias_smem) {
+                    // four 16-byte broadcast loads (bias_sm is 16-byte aligned and c0 a multiple of 16); zero beyond N
     #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += bias_sm[c0 + j];   // zero beyond N
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_sm + c0 + 4 * q);
+                        v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+                    }
                 } else if (bias_row) {
                     if (col + 15 < a.N && ((reinterpret_cast<uintptr_t>(bias_row + col) & 15) == 0)) {
                         // four 16-byte loads at a warp-uniform address (issued back to back) instead of 16 predicated ones
@@ -804,6 +816,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     #pragma unroll
                         for (int j = 0; j < 16; ++j) { th[(size_t)j * a.kv_ncp] = v[j]; tl[(size_t)j * a.kv_ncp] = lo16[j]; }
                     }
+                } else if (EPI == FC_EPI_COUPLING && !TC_KO_CPLMEM && TC_CPL_STAGED && row0 + 32 <= a.M && col + 16 <= a.N &&
+                           ((a.ldx | a.col0) & 1) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 7) == 0) {
+                    // reference models/affine_coupling.py:40-46.  Interior chunk of a full 32-row quadrant: the chunk's 8 latent
+                    // values per row go through the warp's staging tile so that the global accesses are COALESCED (a warp
+                    // instruction moves 8 rows x 32 contiguous bytes; one thread per row touched 32 different sectors per
+                    // instruction and every sector twice: the latent accesses were 4.7 % of the whole GEMM class)
+                    const int r8 = lane >> 2, c2 = (lane & 3) * 2;
+                    float* gx = a.x + (size_t)(row0 + r8) * a.ldx + a.col0 + (col >> 1) + c2;
+                    float2 lx[4];
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) lx[i] = *reinterpret_cast<const float2*>(gx + (size_t)(8 * i) * a.ldx);
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(stg + (r8 + 8 * i) * 20 + c2) = lx[i];
+                    __syncwarp();
+                    float4* my4 = reinterpret_cast<float4*>(stg + lane * 20);
+                    const float4 xa = my4[0], xb = my4[1];
+                    float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    #pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float sig = 1.0f / (1.0f + expf(-v[2 * q]));
+                        const float sc = (2.0f * sig - 1.0f) + 1.0f;
+                        xs[q] = fmaf(xs[q], sc, v[2 * q + 1]);
+                        ldj += logf(sc);
+                    }
+                    my4[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+                    my4[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
+                    __syncwarp();
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) lx[i] = *reinterpret_cast<const float2*>(stg + (r8 + 8 * i) * 20 + c2);
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(gx + (size_t)(8 * i) * a.ldx) = lx[i];
+                    __syncwarp();
                 } else if (!row_ok) {
                     // nothing: out-of-range rows of the coupling / augment epilogues
                 } else if (EPI == FC_EPI_COUPLING) {
@@ -813,20 +857,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         // interior chunk: the row's 8 latent values move as four 8-byte accesses, loads first
                         float2 xv[4];
     #pragma unroll
-                        for (int q = 0; q < 4; ++q) xv[q] = *reinterpret_cast<const float2*>(xrow + 2 * q);
+                        for (int q = 0; q < 4; ++q) xv[q] = TC_KO_CPLMEM ? make_float2(v[q], v[q + 4]) : *reinterpret_cast<const float2*>(xrow + 2 * q);
     #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float sig0 = 1.0f / (1.0f + expf(-v[4 * q]));
+                            const float sig0 = TC_KO_CPLMATH ? v[4 * q] : 1.0f / (1.0f + expf(-v[4 * q]));
                             const float sc0 = (2.0f * sig0 - 1.0f) + 1.0f;
-                            const float sig1 = 1.0f / (1.0f + expf(-v[4 * q + 2]));
+                            const float sig1 = TC_KO_CPLMATH ? v[4 * q + 2] : 1.0f / (1.0f + expf(-v[4 * q + 2]));
                             const float sc1 = (2.0f * sig1 - 1.0f) + 1.0f;
                             xv[q].x = fmaf(xv[q].x, sc0, v[4 * q + 1]);
                             xv[q].y = fmaf(xv[q].y, sc1, v[4 * q + 3]);
-                            ldj += logf(sc0);
-                            ldj += logf(sc1);
+                            ldj += TC_KO_CPLMATH ? sc0 : logf(sc0);
+                            ldj += TC_KO_CPLMATH ? sc1 : logf(sc1);
                         }
+                        if (TC_KO_CPLMEM) { if (xv[0].x + xv[1].y + xv[2].x + xv[3].y == 123.456f) xrow[0] = 1.f; }
+                        else {
     #pragma unroll
                         for (int q = 0; q < 4; ++q) *reinterpret_cast<float2*>(xrow + 2 * q) = xv[q];
+                        }
                     } else {
     #pragma unroll
                         for (int q = 0; q < 8; ++q) {

@@ -53,6 +53,7 @@ struct KnnSmem {
     unsigned char Js[TM][TN];         // compacted survivor columns of the current tile
     float qn[TM];                     // query norms
     float cn[TN];                     // candidate norms of the current tile
+    float thr_x[2][TM];               // each half list's current k-th best, published for the other half of the same query
     // followed by the final lists of the two column halves: Lk[TM][2][KCAP] keys, Li[TM][2][KCAP] indices
 };
 
@@ -89,6 +90,7 @@ knn_kernel(const float* __restrict__ q, int ldq, long long q_bstride, const floa
 #pragma unroll
     for (int p = 0; p < KCAP; ++p) { lkey[p] = -INFINITY; lidx[p] = 0; }
     if (tid < TM) sm.qn[tid] = (q0 + tid < Nq) ? qnorm[(size_t)b * Nq + q0 + tid] : 0.f;
+    sm.thr_x[shalf][srow] = -INFINITY;
     float thr = -INFINITY;     // this thread's current k-th best key
 
     const int n_chunks = (C + CK - 1) / CK;
@@ -166,11 +168,15 @@ knn_kernel(const float* __restrict__ q, int ldq, long long q_bstride, const floa
             // filter + compact in place (cnt <= j, so the write never overtakes the read); candidates stay in index order
             float* row = &sm.Ks[srow][shalf * 64];
             unsigned char* jr = &sm.Js[srow][shalf * 64];
+            // The query's true k-th best is at least the k-th best of EITHER half list, so a key below the other half's
+            // threshold cannot be in the result; keys EQUAL to it stay (the final merge decides ties by index).  This removes
+            // ~40 % of the insertions (each half alone sees k(1 + ln(N/2k)) record breakers, together k(1 + ln(N/k))).
+            const float oth = sm.thr_x[shalf ^ 1][srow];    // published before this tile's barriers
             int cnt = 0;
 #pragma unroll 8
             for (int j = 0; j < 64; ++j) {
                 const float v = row[j];
-                if (v > thr) { row[cnt] = v; jr[cnt] = (unsigned char)j; ++cnt; }
+                if (v > thr && v >= oth) { row[cnt] = v; jr[cnt] = (unsigned char)j; ++cnt; }
             }
             const int mx = __reduce_max_sync(0xffffffffu, cnt);
             for (int i = 0; i < mx; ++i) {
@@ -197,6 +203,7 @@ knn_kernel(const float* __restrict__ q, int ldq, long long q_bstride, const floa
                 }
             }
         }
+        sm.thr_x[shalf][srow] = thr;
         // the next tile's first barrier orders this selection before Ks / cn are overwritten
     }
     // merge the two half lists of every query under (key desc, index asc)

@@ -114,7 +114,7 @@ class FlowCompareB200:
     def _workspace(self, nbytes):
         if nbytes < 0:
             _lib.check(int(nbytes), "workspace query")
-        if self._ws is None or self._ws.numel() < nbytes:
+        if self._ws is None or self._ws.numel() < nbytes + 256:     # + 256: room to round the base up to the ABI's alignment
             self._ws = None
             self._ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
         base = self._ws.data_ptr()
@@ -137,13 +137,20 @@ class FlowCompareB200:
             _lib.check(rc, "fc_embed")
         return (out, idx) if return_knn else out
 
+    def _next_seed(self):
+        """Default noise seeds follow torch's global seed (like the reference's `Normal.rsample`, `torch.manual_seed` makes
+        a run reproducible) and differ per device and per call, so ranks / engines do not score their pairs with the same
+        noise."""
+        self._seed_counter += 1
+        dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        return (torch.initial_seed() * 0x9E3779B1 + dev * 0x85EBCA6B + self._seed_counter) & 0x7FFFFFFFFFFFFFFF
+
     def draw_eps(self, B, N, seed=None):
         """Device-side N(0,1) draw for the augmentation noise (reference: models/distributions.py:148-153)."""
         with torch.cuda.device(self.device):
             eps = torch.empty((B, N, self.D - self.d_in), dtype=torch.float32, device=self.device)
             if seed is None:
-                self._seed_counter += 1
-                seed = 0x5EED0000 + self._seed_counter
+                seed = self._next_seed()
             _lib.check(self.lib.fc_fill_normal(eps.data_ptr(), eps.numel(), seed, 0, _stream()), "fc_fill_normal")
         return eps
 
@@ -152,8 +159,7 @@ class FlowCompareB200:
         with torch.cuda.device(self.device):
             eps = torch.empty((self.L, B, N, self.cif_S), dtype=torch.float32, device=self.device)
             if seed is None:
-                self._seed_counter += 1
-                seed = 0x5EED0000 + self._seed_counter
+                seed = self._next_seed()
             _lib.check(self.lib.fc_fill_normal(eps.data_ptr(), eps.numel(), seed, 1 << 40, _stream()), "fc_fill_normal")
         return eps
 
@@ -241,8 +247,7 @@ class FlowCompareB200:
             if z is None:
                 z = torch.empty((B, n_points, self.D), dtype=torch.float32, device=self.device)
                 if seed is None:
-                    self._seed_counter += 1
-                    seed = 0x5A3B0000 + self._seed_counter
+                    seed = self._next_seed()
                 _lib.check(self.lib.fc_fill_normal(z.data_ptr(), z.numel(), seed, 0, _stream()), "fc_fill_normal")
                 z = z * self._sample_scale + self._sample_loc
             z = _f32c(z, self.device).reshape(B, n_points, self.D)
@@ -335,7 +340,7 @@ class FlowCompareB200:
     def inner_loop_host(self, e0, e1, extra, eps, out_log_prob=None, out_stats=None):
         """Same path through `fc_inner_loop_host`: HOST (ideally pinned) fp32 contiguous buffers in and out,
         copies on the current stream, synchronous on return.  Used by the end-to-end benchmark."""
-        for t in (e0, e1, eps):
+        for t in (e0, e1, eps) + ((extra,) if extra is not None else ()):
             assert t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
         assert e0.shape[2] == self.d_in and e1.shape[2] == self.d_in
         B, Nc, N = e0.shape[0], e0.shape[1], e1.shape[1]
