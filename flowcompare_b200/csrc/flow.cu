@@ -349,17 +349,18 @@ static int run_attention_block(const fc_flow* f, const FcMlp& pre, const FcAttn&
         g.A1 = context; g.lda1 = f->E; g.K1 = at.kv.K1; g.Wt = at.kv.w; g.ldw = at.kv.ldw; g.bias = at.kv.b;
         g.Whi = at.kv.whi; g.Wlo = at.kv.wlo; g.ldk = at.kv.ldk; g.tc_fmt = at.kv.tc_fmt; g.M = B * Nc; g.N = 128; g.precision = 1;
         g.epi = FC_EPI_KVSPLIT; g.ldc = 64; g.kv_nc = Nc;
-        fc_attention_tc_scratch_layout(B, Nc, w.kvs, &g.C, &g.kv_klo, &g.kv_vthi, &g.kv_vtlo, &g.kv_ncp);
+        g.kv_f16 = at.kv.tc_fmt ? 1 : 0;      // 3xFP16 models run the attention on fp16 operands as well
+        fc_attention_tc_scratch_layout(B, Nc, w.kvs, &g.C, &g.kv_klo, &g.kv_vthi, &g.kv_vtlo, &g.kv_ncp, g.kv_f16);
         rc = fc_launch_gemm(g, s);
         if (rc) return rc;
-        return fc_launch_cross_attention_tc(w.q, 64, nullptr, 0, w.o, 64, B, N, Nc, f->inner, scale, w.kvs, 1, s);
+        return fc_launch_cross_attention_tc(w.q, 64, nullptr, 0, w.o, 64, B, N, Nc, f->inner, scale, w.kvs, 1, g.kv_f16, s);
     }
     rc = gemm_plain(at.kv, context, f->E, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, w.kv, 128, B * Nc,
                     precision, s);
     if (rc) return rc;
     if (precision == 1) {
         if (attn_kind == 1) return fc_launch_cross_attention_mma(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
-        return fc_launch_cross_attention_tc(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, w.kvs, 0, s);
+        return fc_launch_cross_attention_tc(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, w.kvs, 0, at.kv.tc_fmt ? 1 : 0, s);
     }
     return fc_launch_cross_attention(w.q, 64, w.kv, 128, w.o, 64, B, N, Nc, f->inner, scale, s);
 }

@@ -40,6 +40,7 @@ struct GemmArgs {
     const float* eps; int ld_eps;  // FC_EPI_AUGMENT
     // FC_EPI_KVSPLIT: C = k hi (ldc = 64), kv_klo = k lo; v^T hi / lo; rows are (cloud, key) = (row / kv_nc, row % kv_nc)
     float* kv_klo; float* kv_vthi; float* kv_vtlo; int kv_nc; int kv_ncp;
+    int kv_f16;                    // 0: TF32 hi/lo stored as fp32; 1: the four outputs are fp16 hi / fp16 (x - hi) (kv_ncp in halfs)
     int precision;                 // 0 fp32 FFMA, 1 3xTF32 tcgen05 (where available)
     // tcgen05 path: the same weight pre-split into TF32 hi / lo parts, N-major rows, K contiguous:
     // [n_tiles*BN][ldk] with ldk = round32(K1) + round32(K2) (zero padded); null -> FFMA only
@@ -68,7 +69,7 @@ static inline GemmArgs fc_gemm_args_zero() {
     a.res = nullptr; a.ldres = 0; a.res_scale = nullptr; a.act = FC_ACT_NONE; a.C = nullptr; a.ldc = 0; a.M = 0; a.N = 0;
     a.epi = FC_EPI_STORE; a.row_mu = nullptr; a.row_rstd = nullptr; a.csum = nullptr;
     a.x = nullptr; a.ldx = 0; a.col0 = 0; a.part = nullptr; a.eps = nullptr; a.ld_eps = 0;
-    a.kv_klo = nullptr; a.kv_vthi = nullptr; a.kv_vtlo = nullptr; a.kv_nc = 0; a.kv_ncp = 0;
+    a.kv_klo = nullptr; a.kv_vthi = nullptr; a.kv_vtlo = nullptr; a.kv_nc = 0; a.kv_ncp = 0; a.kv_f16 = 0;
     a.precision = 0; a.Whi = nullptr; a.Wlo = nullptr; a.ldk = 0; a.tc_fmt = 0;
     return a;
 }

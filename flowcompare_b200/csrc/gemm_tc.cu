@@ -39,6 +39,7 @@
 // rounding and 16-byte staged stores (+23 %); dropped: a 4-accumulator split of the main product (no accuracy gain),
 // TMA multicast of the weight tile over clusters of 2/4 and halving the weight bytes (no effect: not L2 bound), one
 // N=2*BN MMA for Ahi*[Whi;Wlo], decoupled A/W rings, 64/80-wide tiles, all-warps converters, a staggered start.
+#include <cuda_fp16.h>
 #include "gemm.cuh"
 #include "tcgen05.cuh"
 #include <cuda.h>
@@ -776,6 +777,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         }
                     }
                     __syncwarp();
+                } else if (EPI == FC_EPI_KVSPLIT && a.kv_f16) {
+                    // the same for the 3xFP16 attention: fp16 hi and fp16 (x - hi); k rows are 128 bytes, v^T rows kv_ncp halfs
+                    uint32_t hp[8], lp[8];      // packed pairs (columns 2j, 2j+1)
+                    __half hh[16], lh[16];
+    #pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        hh[j] = __float2half_rn(v[j]);
+                        lh[j] = __float2half_rn(v[j] - __half2float(hh[j]));
+                    }
+    #pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        hp[j] = (uint32_t)__half_as_ushort(hh[2 * j]) | ((uint32_t)__half_as_ushort(hh[2 * j + 1]) << 16);
+                        lp[j] = (uint32_t)__half_as_ushort(lh[2 * j]) | ((uint32_t)__half_as_ushort(lh[2 * j + 1]) << 16);
+                    }
+                    if (col < 64) {
+                        // k: a row's 16 values are 32 contiguous bytes; staged so that a warp instruction writes 8 rows x 32 B
+                        uint32_t* stw = reinterpret_cast<uint32_t*>(stg);
+                        const int r8 = lane >> 2, part = lane & 3;
+    #pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            __half* dstbase = reinterpret_cast<__half*>(pass == 0 ? a.C : a.kv_klo);
+                            uint4* my = reinterpret_cast<uint4*>(stw + lane * 20);
+                            my[0] = pass == 0 ? make_uint4(hp[0], hp[1], hp[2], hp[3]) : make_uint4(lp[0], lp[1], lp[2], lp[3]);
+                            my[1] = pass == 0 ? make_uint4(hp[4], hp[5], hp[6], hp[7]) : make_uint4(lp[4], lp[5], lp[6], lp[7]);
+                            __syncwarp();
+    #pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int gr = row0 + r8 + 8 * i;
+                                if (gr < a.M)
+                                    *reinterpret_cast<uint2*>(dstbase + (size_t)gr * 64 + col + 4 * part) =
+                                        *reinterpret_cast<const uint2*>(stw + (r8 + 8 * i) * 20 + 2 * part);
+                            }
+                            __syncwarp();
+                        }
+                    } else if (row_ok) {
+                        const int bcl = row / a.kv_nc, key = row - bcl * a.kv_nc;
+                        __half* th = reinterpret_cast<__half*>(a.kv_vthi) + ((size_t)bcl * 64 + (col - 64)) * a.kv_ncp + key;
+                        __half* tl = reinterpret_cast<__half*>(a.kv_vtlo) + ((size_t)bcl * 64 + (col - 64)) * a.kv_ncp + key;
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) { th[(size_t)j * a.kv_ncp] = hh[j]; tl[(size_t)j * a.kv_ncp] = lh[j]; }
+                    }
                 } else if (EPI == FC_EPI_KVSPLIT) {
                     // to_kv feeding the tcgen05 attention (attention_tc.cu): TF32 hi/lo copies, v transposed per cloud.
                     // BN = 64, so N-tile 0 is k and N-tile 1 is v.

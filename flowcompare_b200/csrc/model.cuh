@@ -133,9 +133,9 @@ int fc_launch_cross_attention_mma(const float* q, int ldq, const float* kv, int 
 // tcgen05 / TMEM version (attention_tc.cu); scratch holds the TF32 hi/lo copies of k and v^T
 int64_t fc_attention_tc_scratch_floats(int B, int Nc);
 void fc_attention_tc_scratch_layout(int B, int Nc, float* scratch, float** khi, float** klo, float** vthi, float** vtlo,
-                                    int* ncp);
+                                    int* ncp, int fmt);
 int fc_launch_cross_attention_tc(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo, int B, int N,
-                                 int Nc, int d, float scale, float* scratch, int presplit, cudaStream_t stream);
+                                 int Nc, int d, float scale, float* scratch, int presplit, int fmt, cudaStream_t stream);
 int fc_launch_edgeconv_gather_max(const float* PQ, int ldpq, const int32_t* idx, int B, int N, int k, int Cout,
                                   float* out, int ldo, cudaStream_t stream);
 int fc_knn_launch(const float* q, int ldq, long long q_bstride, const float* t, int ldt, long long t_bstride,

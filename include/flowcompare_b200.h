@@ -150,12 +150,17 @@ FC_API int fc_cross_attention(const float* q, int ldq, const float* kv, int ldkv
 FC_API int fc_cross_attention_tf32x3(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
                               int B, int N, int Nc, int d, float scale, fc_stream_t stream);
 
-/* Same product on the 5th-gen tensor cores (tcgen05 + TMEM, 3xTF32); the one the flow uses when precision = 1.
- * Needs caller-provided device scratch (TF32 hi/lo copies of k and of v transposed), 128-byte aligned.  */
+/* Same product on the 5th-gen tensor cores (tcgen05 + TMEM); the one the flow uses when precision = 1: 3xTF32 operands
+ * (fc_cross_attention_tc, models packed with TF32 copies) or 3xFP16 operands (fc_cross_attention_tc_f16, models packed with
+ * fp16 copies: half the operand bytes, twice the tensor rate).  Needs caller-provided device scratch (hi/lo copies of k and
+ * of v transposed), 128-byte aligned.                                                                              */
 FC_API int64_t fc_cross_attention_tc_scratch_bytes(int B, int Nc);
 FC_API int fc_cross_attention_tc(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
                           int B, int N, int Nc, int d, float scale, void* scratch, int64_t scratch_bytes,
                           fc_stream_t stream);
+FC_API int fc_cross_attention_tc_f16(const float* q, int ldq, const float* kv, int ldkv, float* out, int ldo,
+                              int B, int N, int Nc, int d, float scale, void* scratch, int64_t scratch_bytes,
+                              fc_stream_t stream);
 
 /* ------------------------------------------------------------------ data-side ops ----------
  * What the reference's loader does between reading a voxel and calling `inner_loop`.

@@ -1,6 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -x -q -k "inner_loop or full_depth or deterministic" 2>&1 | tail -2
-for v in main nostaged main nostaged; do
-  if [ $v = main ]; then unset FLOWCOMPARE_B200_LIB; else export FLOWCOMPARE_B200_LIB=flowcompare_b200/variants/lib_$v.so; fi
-  python bench.py --no-extras --no-cpu-baseline --steps 3 > gpurun_out/cpl_$v.json 2>/dev/null; python -c "import json; d=json.load(open('gpurun_out/cpl_$v.json')); print('$v', d['value'], d['kernel_classes']['gemm_tcgen05_3x']['ms'])"
-done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; python -c "import json; d=json.load(open('gpurun_out/r02_bench_final.json')); print('bench', d['value'], d['e2e']['value'], d['roofline']['achieved'], d['precision_check']['max_abs_diff_nats'], {k:(v['ms'],v['tflops']) for k,v in d['kernel_classes'].items()}); print(d['per_batch']); print(d['per_config']); print(d['sweep_one_gpu'])"

@@ -17,15 +17,15 @@ flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
 
 
 def run(kind):
-    if kind == "tcgen05":
-        return lib.fc_cross_attention_tc(q.data_ptr(), 64, kv.data_ptr(), 128, out.data_ptr(), 64, B, N, Nc, 64, 0.125,
-                                         scratch.data_ptr(), nbytes, st)
+    if kind.startswith("tcgen05"):
+        fn = lib.fc_cross_attention_tc_f16 if kind == "tcgen05_f16" else lib.fc_cross_attention_tc
+        return fn(q.data_ptr(), 64, kv.data_ptr(), 128, out.data_ptr(), 64, B, N, Nc, 64, 0.125, scratch.data_ptr(), nbytes, st)
     fn = lib.fc_cross_attention_tf32x3 if kind == "mma" else lib.fc_cross_attention
     return fn(q.data_ptr(), 64, kv.data_ptr(), 128, out.data_ptr(), 64, B, N, Nc, 64, 0.125, st)
 
 
 ref = None
-for kind in ("mma", "tcgen05"):
+for kind in ("mma", "tcgen05", "tcgen05_f16"):
     for _ in range(3):
         assert run(kind) == 0
     torch.cuda.synchronize()
