@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; python -c "import json; d=json.load(open('gpurun_out/r02_bench_final.json')); print('bench', d['value'], d['e2e']['value'], d['roofline']['achieved'], d['precision_check']['max_abs_diff_nats'], {k:(v['ms'],v['tflops']) for k,v in d['kernel_classes'].items()}); print(d['per_batch']); print(d['per_config']); print(d['sweep_one_gpu'])"
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_transforms_gpu.py tests/test_dataops_gpu.py -q -x -k "not expo_global300 and not spline_extra300" > gpurun_out/sanitizer_r02.log 2>&1; echo "memcheck exit $?" >> gpurun_out/sanitizer_r02.log
+tail -15 gpurun_out/sanitizer_r02.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_transforms_gpu.py tests/test_dataops_gpu.py -q -x -k "op_matches or fps_subsample or co_unit" > gpurun_out/racecheck_r02.log 2>&1; echo "racecheck exit $?" >> gpurun_out/racecheck_r02.log
+tail -8 gpurun_out/racecheck_r02.log
