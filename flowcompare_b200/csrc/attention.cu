@@ -4,6 +4,7 @@
 // [B, N, Nc] score matrix (5 MB per cloud per layer, x116 layers).  Here a CTA owns 64 queries of one
 // cloud, streams 64-key tiles of K and V through shared memory and keeps the running max / sum /
 // output accumulator in registers; nothing of size N*Nc touches HBM.
+#include <atomic>
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -150,11 +151,13 @@ int fc_launch_cross_attention(const float* q, int ldq, const float* kv, int ldkv
     FC_REQUIRE((ldq & 3) == 0 && (ldkv & 3) == 0 && (ldo & 3) == 0 && ldkv >= 2 * AD);
     FC_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(kv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
     FC_REQUIRE(B <= 65535);
-    static bool configured = false;
-    if (!configured) {
+    int dev = 0;
+    FC_CUDA_OK(cudaGetDevice(&dev));
+    static std::atomic<uint64_t> configured{0};     // the dynamic shared-memory opt-in is per device
+    if (!(configured.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
         FC_CUDA_OK(cudaFuncSetAttribute(cross_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(AttnSmem)));
-        configured = true;
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     dim3 grid((N + AQ - 1) / AQ, B);
     FcProfScope prof(FC_CLS_ATTENTION, 4.0 * B * (double)N * Nc * d, 4.0 * B * ((double)N * d * 2 + (double)Nc * d * 2), stream);

@@ -9,6 +9,7 @@
 // key order inside each 8-key step (k-slot t <-> key 2t, slot t+4 <-> key 2t+1) and reading V with the same
 // permutation -- no shuffles, no shared-memory round trip.
 // (A tcgen05/TMEM version is the next step; the GEMMs, 3/4 of the step, went first.)
+#include <atomic>
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -178,10 +179,12 @@ int fc_launch_cross_attention_mma(const float* q, int ldq, const float* kv, int 
     FC_REQUIRE(((reinterpret_cast<uintptr_t>(kv) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0));
     FC_REQUIRE(B <= 65535);
     const int smem = 4 * FK * FLD * (int)sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    int dev = 0;
+    FC_CUDA_OK(cudaGetDevice(&dev));
+    static std::atomic<uint64_t> configured{0};     // the dynamic shared-memory opt-in is per device
+    if (!(configured.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
         FC_CUDA_OK(cudaFuncSetAttribute(cross_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     dim3 grid((N + FQ - 1) / FQ, B);
     FcProfScope prof(FC_CLS_ATTENTION, 4.0 * B * (double)N * Nc * d, 4.0 * B * ((double)N * d * 2 + (double)Nc * d * 2), stream);

@@ -364,8 +364,9 @@ class FlowCompareB200:
         (extract_0, extract_1, extra_context)) are stacked along the batch axis -- cloud pairs are independent and a
         pair's result does not depend on what else is in the batch (tested bitwise) -- and the change scores are then
         formed per direction exactly as the reference does.  eps: optional [4B, N, latent-input_dim] noise.
-        Returns a dict of CUDA tensors: log_prob_{1_0,0_0,0_1,1_1} [B,N], change_1_0, change_0_1 [B,N],
-        nats_{1_0,...} (= -mean log_prob, the reference's `loss`)."""
+        Returns a dict of CUDA tensors: log_prob_{1_0,0_0,0_1,1_1} [B,N], change_1_0, change_0_1 [B,N], loss_{1_0,...}
+        (= -mean log_prob, `inner_loop`'s first return) and nats_{1_0,...} (= loss * log2(e) / input_dim, its third return, which
+        the reference's evaluation prints as "nats", test_flow.py:160,224)."""
         batches = (batch_1_0, batch_0_0, batch_0_1, batch_1_1)
         B = batches[0][0].shape[0]
         for b in batches:
@@ -378,12 +379,28 @@ class FlowCompareB200:
             if any(b[2] is None for b in batches):
                 raise _lib.FlowCompareError("this config uses extra context but a batch has none")
             extra = torch.cat([b[2].reshape(B).to(self.device, torch.float32) for b in batches], dim=0)
-        _, lp, _ = self.inner_loop((e0, e1, extra), eps=eps)
+        # context clouds that are the SAME tensor in several batches (a caller that normalised them once) are embedded once
+        uniq, slot = [], []
+        for b in batches:
+            for j, u in enumerate(uniq):
+                if u is b[0]:
+                    slot.append(j)
+                    break
+            else:
+                slot.append(len(uniq))
+                uniq.append(b[0])
+        if len(uniq) < 4 and not self.cif_S and self.D > self.d_in:
+            emb = self.embed(torch.cat([u[:, :, :self.d_in].to(self.device, torch.float32) for u in uniq], dim=0))
+            ctx = torch.cat([emb[j * B:(j + 1) * B] for j in slot], dim=0)
+            lp = self.log_prob(e1, ctx, extra_context=extra, eps=eps)
+        else:
+            _, lp, _ = self.inner_loop((e0, e1, extra), eps=eps)
         names = ("1_0", "0_0", "0_1", "1_1")
         out = {}
         for i, nm in enumerate(names):
             out["log_prob_" + nm] = lp[i * B:(i + 1) * B]
-            out["nats_" + nm] = -out["log_prob_" + nm].mean()
+            out["loss_" + nm] = -out["log_prob_" + nm].mean()                                   # inner_loop's first return
+            out["nats_" + nm] = out["loss_" + nm] * math.log2(math.e) / self.d_in               # its third: what test_flow.py:160,224 call "nats"
         out["change_1_0"] = log_prob_to_change(out["log_prob_1_0"], out["log_prob_0_0"], multiple, hard_cutoff)
         out["change_0_1"] = log_prob_to_change(out["log_prob_0_1"], out["log_prob_1_1"], multiple, hard_cutoff)
         return out

@@ -279,9 +279,10 @@ FC_API int fc_inner_loop_host(const fc_embedder* e, const fc_flow* f, const floa
 
 /* ------------------------------------------------------------------ consumers -------------
  * fc_change_score replaces `log_prob_to_change` + `clamp_infs`, reference test_flow.py:241-275:
- * per cloud, clamp +-inf to the minimum finite value, mask = lp10 < mean(lp00) - multiple*std(lp00)
- * (unbiased std) or lp10 < hard_cutoff when use_hard_cutoff != 0, change = 1-(lp10-min)/(max-min),
- * zero outside the mask.  lp10, lp00, change_out: [B,N].                                       */
+ * +-inf entries are replaced by the minimum finite value OF THE WHOLE [B,N] TENSOR (what `clamp_infs` does; the inputs are
+ * not modified, unlike the reference's in-place clamp), then per cloud: mask = lp10 < mean(lp00) - multiple*std(lp00)
+ * (unbiased std) or lp10 < hard_cutoff when use_hard_cutoff != 0, change = 1-(lp10-min)/(max-min), zero outside the mask.
+ * lp10, lp00, change_out: [B,N].                                                                */
 FC_API int fc_change_score(const float* lp10, const float* lp00, float* change_out, int B, int N,
                     float multiple, int use_hard_cutoff, float hard_cutoff, fc_stream_t stream);
 

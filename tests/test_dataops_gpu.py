@@ -55,3 +55,31 @@ def test_co_unit_sphere_batched_equals_single():
     for i in range(3):
         ai, bi = dataops.co_unit_sphere(p0[i], p1[i])
         assert torch.equal(a[i], ai) and torch.equal(b[i], bi)
+
+
+def test_dataops_write_only_their_outputs():
+    """Guard bands around the outputs of fc_fps_points and fc_co_unit_sphere (no sanitizer on the GPU pool)."""
+    from flowcompare_b200 import lib as fclib
+    lib = fclib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(1)
+    B, n, C, m, G = 3, 777, 6, 100, 1024
+    pts = torch.rand(B, n, C, generator=g).cuda()
+    widx = torch.full((G + B * m + G,), -7, dtype=torch.int32, device="cuda")
+    wout = torch.full((G + B * m * C + G,), -12345.0, device="cuda")
+    p0 = pts.clone()
+    assert lib.fc_fps_points(pts.data_ptr(), C, B, n, C, m, widx[G:].data_ptr(), wout[G:].data_ptr(), C, st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(pts, p0)
+    assert (widx[:G] == -7).all() and (widx[G + B * m:] == -7).all() and int(widx[G:G + B * m].min()) >= 0 and int(widx[G:G + B * m].max()) < n
+    assert (wout[:G] == -12345.0).all() and (wout[G + B * m * C:] == -12345.0).all()
+    n0, n1 = 300, 200
+    wa = torch.full((G + B * n0 * C + G,), -12345.0, device="cuda"); a = wa[G:G + B * n0 * C].view(B, n0, C); a.copy_(torch.rand(B, n0, C, generator=g).cuda())
+    wb = torch.full((G + B * n1 * C + G,), -12345.0, device="cuda"); b = wb[G:G + B * n1 * C].view(B, n1, C); b.copy_(torch.rand(B, n1, C, generator=g).cuda())
+    winv = torch.full((G + B * 4 + G,), -12345.0, device="cuda")
+    rgb_a, rgb_b = a[..., 3:].clone(), b[..., 3:].clone()
+    assert lib.fc_co_unit_sphere(a.data_ptr(), n0, C, b.data_ptr(), n1, C, B, winv[G:].data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    for w, cnt in ((wa, B * n0 * C), (wb, B * n1 * C), (winv, B * 4)):
+        assert (w[:G] == -12345.0).all() and (w[G + cnt:] == -12345.0).all()
+    assert torch.equal(a[..., 3:], rgb_a) and torch.equal(b[..., 3:], rgb_b)

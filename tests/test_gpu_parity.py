@@ -392,6 +392,14 @@ def test_change_maps_equals_the_four_separate_passes():
     assert torch.equal(got["change_0_1"], eng.log_prob_to_change(lps[2], lps[3], 1.5))
     want = port.log_prob_to_change(lps[0].cpu(), lps[1].cpu(), 1.5)
     assert (got["change_1_0"].cpu() - want).abs().max().item() < 1e-6
+    # loss / "nats" as inner_loop returns them (model_initialization.py:225-227; test_flow.py prints the third as nats)
+    loss, _, bpd = e.inner_loop(batches[0], eps=epss[0])
+    assert abs(got["loss_1_0"].item() - loss.item()) < 1e-5 and abs(got["nats_1_0"].item() - bpd.item()) < 1e-5
+    # context clouds that are the same tensor are embedded once: same result as four independent passes
+    shared = [(batches[0][0], batches[i][1], batches[i][2]) for i in range(4)]
+    got2 = e.change_maps(*shared, multiple=1.5, eps=torch.cat(epss, dim=0))
+    for i, nm in enumerate(("1_0", "0_0", "0_1", "1_1")):
+        assert torch.equal(got2["log_prob_" + nm], e.inner_loop(shared[i], eps=epss[i])[1])
 
 
 def test_drop_in_adapters_follow_reference_call_signature():

@@ -109,3 +109,48 @@ def test_cif_flow_requires_its_noise():
     assert rc == -1   # FC_ERR_INVALID_ARG
     assert e.lib.fc_flow_cif_noise_dim(e._flow["handle"]) == 8
     e.close()
+
+
+def _guarded(rows, ld, guard=2048):
+    whole = torch.full((guard + rows * ld + guard,), -12345.0, device="cuda")
+    return whole, whole[guard:guard + rows * ld].view(rows, ld), guard
+
+
+@pytest.mark.parametrize("n,M", [(150, 131), (7, 5)])
+def test_transform_ops_write_only_their_outputs(n, M):
+    """Guard bands around every buffer fc_rq_spline / fc_expm_action write (compute-sanitizer is not available on the GPU
+    pool): nothing outside the n written columns of the M rows, the row-sum vectors and nothing of the parameters changes."""
+    lib = fclib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(n)
+    nb, ldx = 8, n + 3
+    ldp = (n * (3 * nb + 1) + 3) // 4 * 4
+    wp, P, gp = _guarded(M, ldp)
+    P.copy_(torch.randn(M, ldp, generator=g).cuda())
+    wx, X, gx = _guarded(M, ldx)
+    X.copy_((torch.rand(M, ldx, generator=g) * 6 - 3).cuda())
+    wl, L, gl = _guarded(1, M)
+    L.zero_()
+    p0, x0 = wp.clone(), wx.clone()
+    assert lib.fc_rq_spline(P.data_ptr(), ldp, X.data_ptr(), ldx, n, nb, M, L.data_ptr(), 0, st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(wp, p0)
+    assert torch.equal(wx[:gx], x0[:gx]) and torch.equal(wx[gx + M * ldx:], x0[gx + M * ldx:])
+    assert torch.equal(X[:, n:], x0[gx:gx + M * ldx].view(M, ldx)[:, n:])          # the row padding
+    assert (wl[:gl] == -12345.0).all() and (wl[gl + M:] == -12345.0).all() and torch.isfinite(L).all()
+    # exponential coupling
+    ldp2 = (n * n + n + 3) // 4 * 4
+    wp2, P2, _ = _guarded(M, ldp2)
+    P2.copy_((torch.randn(M, ldp2, generator=g) * 0.2).cuda())
+    wx2, X2, gx2 = _guarded(M, ldx)
+    X2.copy_(torch.randn(M, ldx, generator=g).cuda())
+    wt, T, gt = _guarded(1, M)
+    T.zero_()
+    sq = torch.tensor([0.125, 0.0, 1.0, 0.0], device="cuda")
+    p20, x20 = wp2.clone(), wx2.clone()
+    assert lib.fc_expm_action(P2.data_ptr(), ldp2, X2.data_ptr(), ldx, n, sq.data_ptr(), T.data_ptr(), M, 0, st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(wp2, p20)
+    assert torch.equal(wx2[:gx2], x20[:gx2]) and torch.equal(wx2[gx2 + M * ldx:], x20[gx2 + M * ldx:])
+    assert torch.equal(X2[:, n:], x20[gx2:gx2 + M * ldx].view(M, ldx)[:, n:])
+    assert (wt[:gt] == -12345.0).all() and (wt[gt + M:] == -12345.0).all() and torch.isfinite(X2[:, :n]).all()
