@@ -556,10 +556,16 @@ extern "C" int fc_flow_set_inverse(fc_flow* f, const int32_t* header, int n_head
     FC_REQUIRE(f && header && table && arena && n_header >= 4);
     if (header[0] != FC_INV_MAGIC || (header[1] != FC_ARENA_VERSION && header[1] != FC_ARENA_VERSION_F16)) return FC_ERR_MODEL;
     if (header[2] != f->L || header[3] != f->D || (reinterpret_cast<uintptr_t>(arena) & 15)) return FC_ERR_MODEL;
+    if ((n_header >= 5 ? header[4] : 0) != f->cif_dim) return FC_ERR_MODEL;
     FcCursor c{table, n_table, 0, arena, arena_floats, true};
     c.tc_fmt = header[1] == FC_ARENA_VERSION_F16 ? 1 : 0;
     for (int l = 0; l < f->L; ++l) {
         FcFlowLayer& y = f->layers[l];
+        if (f->cif_dim) {
+            y.cif_isc = c.ptr(c.next(), f->cif_dim);
+            y.cif_ibi = c.ptr(c.next(), f->cif_dim);
+            if (!y.cif_isc || !y.cif_ibi) c.ok = false;
+        }
         if (!y.has_lu) continue;
         y.lu_inv = c.linear(f->D, 0, f->D);
         y.lu_inv_diag = c.ptr(c.next(), f->D);
@@ -576,18 +582,20 @@ extern "C" int fc_flow_set_inverse(fc_flow* f, const int32_t* header, int n_head
 // (models/affine_coupling.py:48-62) in the epilogue of its conditioner's last GEMM, the conditioner itself exactly as in the
 // forward pass (it reads the untouched half y1); the augmenter's inverse keeps the first input_dim columns
 // (models/augmenter.py:20-21,65-67).  z: [B, P, D] base draw, x_out: [B, P, d_in].
-extern "C" int fc_flow_sample(const fc_flow* f, const float* z, const float* context, const float* extra, float* x_out, int B,
-                              int P, int Nc, void* workspace, int64_t workspace_bytes, int precision, fc_stream_t stream_) {
+static int flow_sample(const fc_flow* f, const float* z, const float* context, const float* extra, const float* eps_cif,
+                       float* x_out, int B, int P, int Nc, void* workspace, int64_t workspace_bytes, int precision,
+                       fc_stream_t stream_) {
     FC_REQUIRE(f && z && context && x_out && B > 0 && P > 0 && Nc > 0);
     FC_REQUIRE((f->extra != 0) == (extra != nullptr));
+    FC_REQUIRE(eps_cif || !f->cif_dim);
     FC_REQUIRE((int64_t)B * P < (1ll << 31) && (int64_t)B * Nc < (1ll << 31));
     if (!f->has_inverse) return FC_ERR_MODEL;
-    if (f->cpl_kind != FC_CPL_AFFINE || f->cif_dim || !f->has_aug) return FC_ERR_UNSUPPORTED;   // sampling: shipped architectures only
     cudaStream_t s = (cudaStream_t)stream_;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return FC_ERR_WORKSPACE;
     FlowWs w = carve_flow_ws(f, B, P, Nc, workspace);
     if (w.total_bytes > workspace_bytes) return FC_ERR_WORKSPACE;
     const int M = B * P;
+    const int n2 = f->D - f->half, S = f->cif_dim ? f->cif_dim - f->D : 0;
     int rc;
     {
         const long long tot = (long long)M * f->D;
@@ -604,6 +612,13 @@ extern "C" int fc_flow_sample(const fc_flow* f, const float* z, const float* con
         if (rc) return rc;
     }
     auto cb_ptr = [&](int slot) -> const float* { return f->has_cb ? w.cb + (size_t)slot * f->hid : nullptr; };
+    auto coupling_inv_gemm = [&](const FcLinear& o, const float* last, float* lat) {
+        GemmArgs g = fc_gemm_args_zero();
+        g.A1 = last; g.lda1 = w.ldh; g.K1 = o.K1; g.Wt = o.w; g.ldw = o.ldw; g.bias = o.b; g.Whi = o.whi; g.Wlo = o.wlo;
+        g.ldk = o.ldk; g.tc_fmt = o.tc_fmt; g.M = M; g.N = o.N; g.epi = FC_EPI_COUPLING_INV; g.x = lat; g.ldx = w.ldx;
+        g.precision = precision;
+        return g;
+    };
     float* lat = w.lat0; float* lat_next = w.lat1;
     for (int l = f->L - 1; l >= 0; --l) {
         const FcFlowLayer& y = f->layers[l];
@@ -616,6 +631,7 @@ extern "C" int fc_flow_sample(const fc_flow* f, const float* z, const float* con
             if (rc) return rc;
             float* t = lat; lat = lat_next; lat_next = t;
         }
+        // ---- the coupling's inverse: the conditioner reads the untouched half y1 exactly as in the forward pass
         if (!f->is_global) {
             rc = run_attention_block(f, y.pre, y.attn, lat, w.ldx, f->half, context, B, P, Nc, w, precision, s);
             if (rc) return rc;
@@ -625,16 +641,66 @@ extern "C" int fc_flow_sample(const fc_flow* f, const float* z, const float* con
         float* last = nullptr;
         rc = fc_run_mlp_hidden(y.cpl, in, M, w.hA, w.hB, w.ldh, precision, s, &last);
         if (rc) return rc;
-        GemmArgs g = fc_gemm_args_zero();
-        g.A1 = last; g.lda1 = w.ldh; g.K1 = f->hid; g.Wt = y.cpl.out.w; g.ldw = y.cpl.out.ldw; g.bias = y.cpl.out.b; g.Whi = y.cpl.out.whi; g.Wlo = y.cpl.out.wlo;
-        g.ldk = y.cpl.out.ldk; g.tc_fmt = y.cpl.out.tc_fmt; g.M = M; g.N = y.cpl.out.N; g.epi = FC_EPI_COUPLING_INV; g.x = lat; g.ldx = w.ldx; g.col0 = f->half;
-        g.precision = precision;
-        rc = fc_launch_gemm(g, s);
-        if (rc) return rc;
+        if (f->cpl_kind == FC_CPL_SPLINE) {            // reference models/spline_coupling.py:212-227
+            rc = gemm_plain(y.cpl.out, last, w.ldh, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, w.pbuf, w.ldp, M, precision, s);
+            if (rc) return rc;
+            rc = fc_launch_rq_spline(w.pbuf, w.ldp, lat, w.ldx, f->half, n2, f->num_bins, M, nullptr, 1, s);
+            if (rc) return rc;
+        } else if (f->cpl_kind == FC_CPL_EXPO) {       // reference models/exponential_coupling.py:60-77
+            for (int r0 = 0; r0 < M; r0 += w.p_rows) {
+                const int rows = M - r0 < w.p_rows ? M - r0 : w.p_rows;
+                rc = gemm_plain(y.cpl.out, last + (size_t)r0 * w.ldh, w.ldh, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE,
+                                w.pbuf, w.ldp, rows, precision, s);
+                if (rc) return rc;
+                rc = fc_launch_expm_action(w.pbuf, w.ldp, lat, w.ldx, f->half, n2, y.expo_sq, nullptr, r0, rows, 1, s);
+                if (rc) return rc;
+            }
+        } else {                                       // reference models/affine_coupling.py:48-62
+            GemmArgs g = coupling_inv_gemm(y.cpl.out, last, lat);
+            g.col0 = f->half;
+            rc = fc_launch_gemm(g, s);
+            if (rc) return rc;
+        }
+        if (f->cif_dim) {
+            // CIFblock.inverse after its flow (reference models/cif_block.py:102-111), Reverse folded as in the forward pass:
+            // the sliced-off columns are SAMPLED from the ConditionalNormal of what was kept (models/slice.py:46-58), then the
+            // inverse ActNorm on all cif_dim columns and x = (x - t(z2)) / s(z2); Augment.inverse drops the extra columns.
+            FcMlpIn inc{lat, w.ldx, nullptr, 0, nullptr, 0, 0};
+            rc = fc_run_mlp_hidden(y.cifnet, inc, M, w.hA, w.hB, w.ldh, precision, s, &last);
+            if (rc) return rc;
+            rc = gemm_plain(y.cifnet.out, last, w.ldh, nullptr, 0, nullptr, 0, 0, nullptr, 0, FC_ACT_NONE, w.pbuf, w.ldp_cif, M,
+                            precision, s);
+            if (rc) return rc;
+            rc = fc_launch_cond_normal(w.pbuf, w.ldp_cif, lat, w.ldx, f->D, S, eps_cif + (size_t)l * M * S, M, f->cif_clamp,
+                                       w.cpart /* log-density not needed: scratch */, 0, s);
+            if (rc) return rc;
+            rc = fc_launch_col_affine(lat, w.ldx, f->cif_dim, M, y.cif_isc, y.cif_ibi, s);
+            if (rc) return rc;
+            FcMlpIn in2{lat + f->D, w.ldx, nullptr, 0, nullptr, 0, 0};
+            rc = fc_run_mlp_hidden(y.affcif, in2, M, w.hA, w.hB, w.ldh, precision, s, &last);
+            if (rc) return rc;
+            GemmArgs g = coupling_inv_gemm(y.affcif.out, last, lat);
+            g.col0 = 0;
+            rc = fc_launch_gemm(g, s);
+            if (rc) return rc;
+        }
     }
     const long long tot = (long long)M * f->d_in;
     copy_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(lat, w.ldx, x_out, f->d_in, M, f->d_in);
     fc_count_launch();
     FC_LAUNCH_OK();
     return FC_OK;
+}
+
+extern "C" int fc_flow_sample(const fc_flow* f, const float* z, const float* context, const float* extra, float* x_out, int B,
+                              int P, int Nc, void* workspace, int64_t workspace_bytes, int precision, fc_stream_t stream_) {
+    return flow_sample(f, z, context, extra, nullptr, x_out, B, P, Nc, workspace, workspace_bytes, precision, stream_);
+}
+
+// Flows with CIF blocks: eps_cif [L, B, P, fc_flow_cif_noise_dim(f)] = the N(0,1) draws of every block's `Slice.inverse`
+// (reference models/slice.py:46-58), indexed by the block's position in the FORWARD list.
+extern "C" int fc_flow_sample_cif(const fc_flow* f, const float* z, const float* context, const float* extra,
+                                  const float* eps_cif, float* x_out, int B, int P, int Nc, void* workspace,
+                                  int64_t workspace_bytes, int precision, fc_stream_t stream_) {
+    return flow_sample(f, z, context, extra, eps_cif, x_out, B, P, Nc, workspace, workspace_bytes, precision, stream_);
 }

@@ -52,6 +52,7 @@ struct FcFlowLayer {
     // ActNorm between them as one per-column affine map over the cif_dim columns
     FcMlp cifnet, affcif;
     const float* cif_sc = nullptr; const float* cif_bi = nullptr;
+    const float* cif_isc = nullptr; const float* cif_ibi = nullptr;   // its inverse (sampling pass, fc_flow_set_inverse)
 };
 
 struct fc_flow {

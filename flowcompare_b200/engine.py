@@ -236,9 +236,10 @@ class FlowCompareB200:
             _lib.check(rc, "fc_flow_set_inverse")
             self._inv = {"arena": arena_dev, "header": header, "table": table}
 
-    def sample(self, n_points, context, extra_context=None, z=None, seed=None):
+    def sample(self, n_points, context, extra_context=None, z=None, seed=None, eps_cif=None):
         """`Flow.sample(num_samples=1, n_points=, context=, extra_context=)` (reference models/transform.py:79-84):
         z ~ sample_dist = N(loc, scale) [B, n_points, latent] (or the injected `z`), then every transform's inverse.
+        eps_cif [L, B, n_points, cif_latent_dim - latent_dim]: the CIF blocks' `Slice.inverse` draws (default: drawn on the device).
         Returns x [B, n_points, input_dim]."""
         self._ensure_inverse()
         with torch.cuda.device(self.device):
@@ -254,17 +255,25 @@ class FlowCompareB200:
             out = torch.empty((B, n_points, self.d_in), dtype=torch.float32, device=self.device)
             nbytes = self.lib.fc_flow_workspace_bytes(self._flow["handle"], B, n_points, Nc)
             ws = self._workspace(nbytes)
-            rc = self.lib.fc_flow_sample(self._flow["handle"], z.data_ptr(), context.data_ptr(), _ptr(extra), out.data_ptr(), B,
-                                         n_points, Nc, ws, nbytes, self.precision, _stream())
-            _lib.check(rc, "fc_flow_sample")
+            if self.cif_S:
+                eps_cif = self.draw_eps_cif(B, n_points) if eps_cif is None else _f32c(eps_cif, self.device)
+                assert eps_cif.shape == (self.L, B, n_points, self.cif_S), eps_cif.shape
+                rc = self.lib.fc_flow_sample_cif(self._flow["handle"], z.data_ptr(), context.data_ptr(), _ptr(extra),
+                                                 eps_cif.data_ptr(), out.data_ptr(), B, n_points, Nc, ws, nbytes, self.precision,
+                                                 _stream())
+                _lib.check(rc, "fc_flow_sample_cif")
+            else:
+                rc = self.lib.fc_flow_sample(self._flow["handle"], z.data_ptr(), context.data_ptr(), _ptr(extra), out.data_ptr(), B,
+                                             n_points, Nc, ws, nbytes, self.precision, _stream())
+                _lib.check(rc, "fc_flow_sample")
         return out
 
-    def make_sample(self, n_points, extract_0, extra_context=None, z=None, seed=None):
+    def make_sample(self, n_points, extract_0, extra_context=None, z=None, seed=None, eps_cif=None):
         """`make_sample(n_points, extract_0, models_dict, config, sample_distrib=None, extra_context=None)` (reference
         model_initialization.py:231-245): embed the context cloud, then the generative pass.  Returns what the reference
         returns: x [B, n_points, input_dim] with singleton dimensions squeezed."""
         emb = self.embed(extract_0)
-        return self.sample(n_points, emb, extra_context=extra_context, z=z, seed=seed).squeeze()
+        return self.sample(n_points, emb, extra_context=extra_context, z=z, seed=seed, eps_cif=eps_cif).squeeze()
 
     # ------------------------------------------------------------------ whole path
     def inner_loop(self, batch, eps=None, eps_cif=None):

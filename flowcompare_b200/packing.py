@@ -197,10 +197,39 @@ def _conditioner_first_layer(sd, mlp_prefix, attn_prefix, k_x, ex, is_global, E)
     return w_x, b_in, w_e, w_c
 
 
+def permuter_inverse_matrix(flow_sd, t, cfg):
+    """W^-1 (fp64) of the permuter at transforms.<t>, each by the cheapest exact route: LinearLU by two triangular solves (no general
+    inverse of a 300x300 product; reference models/permuters.py:171-177), Permuter by transposition (:67-69), FullCombiner by
+    `inv` (:22-26), ExponentialCombiner by expm(-W) (:51-53)."""
+    D = cfg["latent_dim"]
+    kind = cfg["permuter_type"]
+    p = f"transforms.{t}"
+    eye = torch.eye(D, dtype=torch.float64)
+    if kind == "LinearLU":
+        lo, up = _d(flow_sd, f"{p}.lower_entries"), _d(flow_sd, f"{p}.upper_entries")
+        dg = _d(flow_sd, f"{p}.unconstrained_upper_diag")
+        Lm = torch.eye(D, dtype=torch.float64)
+        il = np.tril_indices(D, k=-1)
+        Lm[il[0], il[1]] = lo
+        Um = torch.zeros(D, D, dtype=torch.float64)
+        iu = np.triu_indices(D, k=1)
+        Um[iu[0], iu[1]] = up
+        Um[range(D), range(D)] = F.softplus(dg) + cfg["linear_lu_eps"]
+        Linv = torch.linalg.solve_triangular(Lm, eye, upper=False, unitriangular=True)
+        return torch.linalg.solve_triangular(Um, Linv, upper=True)
+    if kind == "random_permute":
+        return permuter_matrix(flow_sd, t, cfg)[0].t().contiguous()
+    if kind == "FullCombiner":
+        return torch.linalg.inv(_d(flow_sd, f"{p}.w"))
+    if kind == "ExponentialCombiner":
+        return torch.matrix_exp(-_squash(flow_sd, p, _d(flow_sd, f"{p}.w")))
+    raise NotImplementedError(kind)
+
+
 def fold_inverse_actnorm_lu(flow_sd, config):
-    """Pack-time algebra of the inverse / sampling pass (reference models/permuters.py:171-177 followed by
-    models/act_norm.py:45-46, i.e. the inverse of one ActNorm + LinearLU pair): with the forward fold
-    z' = Wp z - Wp shift, Wp = L U diag(exp(-log_scale)), the inverse is z = Wp^-1 z' + shift.  Returned per pair, in
+    """Pack-time algebra of the inverse / sampling pass (the permuter's `.inverse` followed by reference
+    models/act_norm.py:45-46, i.e. the inverse of one ActNorm + permuter pair): with the forward fold
+    z' = Wp z - Wp shift, Wp = W diag(exp(-log_scale)), the inverse is z = Wp^-1 z' + shift.  Returned per pair, in
     forward layer order, as (off-diagonal part of Wp^-1, its diagonal, bias) in fp64 -- the same split the forward GEMM
     uses so that the latent's own column is applied in fp32 in the epilogue (consumed by
     pack_flow_inverse -> csrc/flow.cu: fc_flow_sample)."""
@@ -211,21 +240,12 @@ def fold_inverse_actnorm_lu(flow_sd, config):
     for layer in range(L):
         t += 1
         if layer != L - 1:
-            shift, log_scale = _d(flow_sd, f"transforms.{t}.shift")[0], _d(flow_sd, f"transforms.{t}.log_scale")[0]
-            t += 1
-            lo, up = _d(flow_sd, f"transforms.{t}.lower_entries"), _d(flow_sd, f"transforms.{t}.upper_entries")
-            dg = _d(flow_sd, f"transforms.{t}.unconstrained_upper_diag")
-            Lm = torch.eye(D, dtype=torch.float64)
-            il = np.tril_indices(D, k=-1)
-            Lm[il[0], il[1]] = lo
-            Um = torch.zeros(D, D, dtype=torch.float64)
-            iu = np.triu_indices(D, k=1)
-            Um[iu[0], iu[1]] = up
-            Um[range(D), range(D)] = F.softplus(dg) + cfg["linear_lu_eps"]
-            # Wp^-1 = diag(exp(log_scale)) U^-1 L^-1 by two triangular solves (no general inverse of a 300x300 product)
-            Linv = torch.linalg.solve_triangular(Lm, torch.eye(D, dtype=torch.float64), upper=False, unitriangular=True)
-            ULinv = torch.linalg.solve_triangular(Um, Linv, upper=True)
-            Winv = torch.diag(torch.exp(log_scale)) @ ULinv
+            if cfg["act_norm"]:
+                shift, log_scale = _d(flow_sd, f"transforms.{t}.shift")[0], _d(flow_sd, f"transforms.{t}.log_scale")[0]
+                t += 1
+            else:
+                shift, log_scale = torch.zeros(D, dtype=torch.float64), torch.zeros(D, dtype=torch.float64)
+            Winv = torch.diag(torch.exp(log_scale)) @ permuter_inverse_matrix(flow_sd, t, cfg)
             wdiag = torch.diagonal(Winv).clone()
             out.append((Winv - torch.diag(wdiag), wdiag, shift.clone()))
             t += 1
@@ -236,16 +256,29 @@ INV_MAGIC = 0x46435F49
 
 
 def pack_flow_inverse(flow_sd, config, tc_format="tf32"):
-    """Arena of the sampling pass (csrc/flow.cu: fc_flow_set_inverse): per ActNorm+LinearLU pair, in forward layer order,
-    the off-diagonal part of Wp^-1 with bias = shift as a Linear, then its diagonal (fold_inverse_actnorm_lu)."""
+    """Arena of the sampling pass (csrc/flow.cu: fc_flow_set_inverse), per layer in forward order: for a CIF block the inverse of
+    its (Reverse-folded) ActNorm as two per-column vectors (a = a' * isc + ibi, packing._pack_cif); for every ActNorm + permuter
+    pair the off-diagonal part of Wp^-1 with bias = shift as a Linear, then its diagonal (fold_inverse_actnorm_lu)."""
     cfg = derive(config)
     ar = Arena(tc_format)
-    D = cfg["latent_dim"]
-    for w_off, wdiag, shift in fold_inverse_actnorm_lu(flow_sd, config):
-        ar.linear(w_off, shift, D)
-        ar.vector(wdiag)
+    D, L = cfg["latent_dim"], cfg["n_flow_layers"]
+    cif = D < cfg["cif_latent_dim"]
+    pairs = fold_inverse_actnorm_lu(flow_sd, config)
+    stride = 1 + (1 if cfg["act_norm"] else 0) + 1      # transforms per layer: block, [ActNorm], permuter
+    for layer in range(L):
+        if cif:
+            p = f"transforms.{1 + layer * stride}"
+            shift, log_scale = _d(flow_sd, f"{p}.act_norm.shift")[0], _d(flow_sd, f"{p}.act_norm.log_scale")[0]
+            sc = torch.exp(-log_scale).flip(0)
+            bi = -shift.flip(0) * sc
+            ar.vector(1.0 / sc)
+            ar.vector(-bi / sc)
+        if layer != L - 1:
+            w_off, wdiag, shift = pairs[layer]
+            ar.linear(w_off, shift, D)
+            ar.vector(wdiag)
     arena, table = ar.finish()
-    header = np.asarray([INV_MAGIC, TC_FORMATS[tc_format], cfg["n_flow_layers"], D], dtype=np.int32)
+    header = np.asarray([INV_MAGIC, TC_FORMATS[tc_format], L, D, cfg["cif_latent_dim"] if cif else 0], dtype=np.int32)
     return header, table, arena
 
 

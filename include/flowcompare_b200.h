@@ -246,6 +246,14 @@ FC_API int fc_flow_set_inverse(fc_flow* h, const int32_t* header_host, int n_hea
 FC_API int fc_flow_sample(const fc_flow* h, const float* z, const float* context, const float* extra, float* x_out,
                    int B, int P, int Nc, void* workspace, int64_t workspace_bytes, int precision,
                    fc_stream_t stream);
+/* The same pass for flows with CIF blocks (`CIFblock.inverse`, reference models/cif_block.py:102-111): every block's
+ * `Slice.inverse` SAMPLES the columns that were sliced off (models/slice.py:46-58); eps_cif [L, B, P, fc_flow_cif_noise_dim(h)]
+ * holds those N(0,1) draws, indexed by the block's position in the forward list.  fc_flow_sample itself covers every other
+ * flow: the three couplings' inverses (models/affine_coupling.py:48-62, models/spline_coupling.py:212-227,
+ * models/exponential_coupling.py:60-77) and every permuter's (models/permuters.py:22-26, :51-53, :67-69, :171-177).      */
+FC_API int fc_flow_sample_cif(const fc_flow* h, const float* z, const float* context, const float* extra,
+                       const float* eps_cif, float* x_out, int B, int P, int Nc, void* workspace,
+                       int64_t workspace_bytes, int precision, fc_stream_t stream);
 
 FC_API int fc_embedder_create(const int32_t* header_host, int n_header, const int64_t* table_host, int n_table,
                        const float* arena, int64_t arena_floats, fc_embedder** out);

@@ -16,13 +16,28 @@ from oracle import refload
 from oracle.make_golden import GOLDEN_DIR, fixture_inputs
 
 SAMPLE_FIXTURES = {"tiny_dgcnn_attn": 40, "tiny_dgcnn_attn_extra": 33, "tiny_dgcnn_global": 64, "tiny_paconv_attn": 50,
-                   "mid_dgcnn_attn": 48}
+                   "mid_dgcnn_attn": 48,
+                   # the transforms no shipped config selects (oracle/make_golden.py: A18): their `.inverse` paths
+                   "a18_spline": 40, "a18_spline_extra300": 24, "a18_expo": 40, "a18_expo_global300": 24, "a18_cif": 40,
+                   "a18_cif_spline_clamp": 36, "a18_permute_relu": 40, "a18_fullcombiner_noactnorm": 40,
+                   "a18_expcombiner_global": 40, "a18_identity_augmenter": 40}
 
 
 def base_draw(name, cfg, B):
     n_points = SAMPLE_FIXTURES[name]
     g = torch.Generator().manual_seed(4242 + n_points)
     return spec._randn((B, n_points, cfg["latent_dim"]), g) * 0.6      # sample_dist = Normal(0, 0.6)
+
+
+def cif_draws(name, cfg, B):
+    """[L, B, n_points, S] draws of the CIF blocks' `Slice.inverse` (reference models/slice.py:46-58), indexed by forward layer; None
+    for flows without CIF blocks."""
+    S = cfg["cif_latent_dim"] - cfg["latent_dim"]
+    if S <= 0:
+        return None
+    n_points = SAMPLE_FIXTURES[name]
+    g = torch.Generator().manual_seed(777 + n_points)
+    return spec._randn((cfg["n_flow_layers"], B, n_points, S), g)
 
 
 class Injected(torch.nn.Module):
@@ -51,7 +66,15 @@ def main(argv):
         md["input_embedder"].load_state_dict(esd)
         dcfg = configs.derive(cfg)
         z = base_draw(name, cfg, batch["extract_0"].shape[0])
-        x = mi.make_sample(n_points, batch["extract_0"], md, dcfg, sample_distrib=Injected(z), extra_context=batch["extra_context"])
+        ec = cif_draws(name, cfg, batch["extract_0"].shape[0])
+        import torch.distributions.normal as tdn
+        it = iter(reversed(list(ec))) if ec is not None else iter(())       # the reference inverts (and draws) last block first
+        orig = tdn._standard_normal
+        tdn._standard_normal = lambda shape, dtype, device: next(it).to(dtype).reshape(shape)
+        try:
+            x = mi.make_sample(n_points, batch["extract_0"], md, dcfg, sample_distrib=Injected(z), extra_context=batch["extra_context"])
+        finally:
+            tdn._standard_normal = orig
         path = os.path.join(GOLDEN_DIR, f"sample_{name}.pt")
         torch.save({"x": x.clone(), "n_points": n_points,
                     "meta": {"fixture": name, "generator": "oracle/make_sample_golden.py", "source": "unmodified reference make_sample, CPU fp32"}}, path)

@@ -276,10 +276,13 @@ def test_port_change_score_matches_live_reference():
 
 
 # ----------------------------------------------------------------------------- sampling pass goldens
-@pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_attn_extra", "tiny_dgcnn_global"])
+@pytest.mark.parametrize("name", ["tiny_dgcnn_attn", "tiny_dgcnn_attn_extra", "tiny_dgcnn_global", "a18_spline", "a18_spline_extra300",
+                                  "a18_expo", "a18_expo_global300", "a18_cif", "a18_cif_spline_clamp", "a18_permute_relu",
+                                  "a18_fullcombiner_noactnorm", "a18_expcombiner_global", "a18_identity_augmenter"])
 def test_port_sampling_pass_matches_reference_golden(name):
-    """oracle/port.py: flow_sample against the UNMODIFIED reference's make_sample outputs (tests/golden/sample_*.pt)."""
-    from oracle.make_sample_golden import base_draw
+    """oracle/port.py: flow_sample (every coupling's, permuter's and the CIF block's `.inverse`) against the UNMODIFIED
+    reference's make_sample outputs (tests/golden/sample_*.pt)."""
+    from oracle.make_sample_golden import base_draw, cif_draws
     cfg, fsd, esd, batch = fixture_inputs(name)
     dcfg = configs.derive(cfg)
     gold = load_golden("sample_" + name)
@@ -292,8 +295,8 @@ def test_port_sampling_pass_matches_reference_golden(name):
         ctx, _ = port.dgcnn_embed(esd, batch["extract_0"], cfg["n_neighbors"])
     extra = batch["extra_context"]
     ex = None if extra is None else extra.unsqueeze(1).expand(-1, P, -1)
-    got = port.flow_sample(fsd, dcfg, z, ctx, ex)
-    assert (got - gold["x"]).abs().max().item() < 1e-4
+    got = port.flow_sample(fsd, dcfg, z, ctx, ex, eps_cif=cif_draws(name, cfg, batch["extract_0"].shape[0]))
+    assert (got.squeeze() - gold["x"]).abs().max().item() < 1e-4
 
 
 # --------------------------------------------------------------------------- transforms no shipped config selects

@@ -10,7 +10,7 @@ import torch
 from flowcompare_b200 import configs, engine as eng
 from oracle import port
 from oracle.make_golden import fixture_inputs
-from oracle.make_sample_golden import SAMPLE_FIXTURES, base_draw
+from oracle.make_sample_golden import SAMPLE_FIXTURES, base_draw, cif_draws
 from tests.conftest import load_golden
 
 pytestmark = pytest.mark.gpu
@@ -27,8 +27,9 @@ def test_make_sample_matches_reference_golden(name, precision):
     z = base_draw(name, cfg, B)
     e = eng.FlowCompareB200((fsd, esd), cfg, device=DEV, precision=precision)
     extra = batch["extra_context"]
+    ec = cif_draws(name, cfg, B)
     x = e.make_sample(gold["n_points"], batch["extract_0"].to(DEV), extra_context=None if extra is None else extra.to(DEV),
-                      z=z.to(DEV)).cpu()
+                      z=z.to(DEV), eps_cif=None if ec is None else ec.to(DEV)).cpu()
     assert x.shape == gold["x"].shape          # the reference squeezes singleton dimensions
     err = (x - gold["x"]).abs().max().item()
     print(name, precision, "max |x - reference|", err)
@@ -56,21 +57,24 @@ def test_sample_matches_port(name):
     e.close()
 
 
+@pytest.mark.parametrize("name", ["tiny_dgcnn_attn_extra", "a18_spline", "a18_expo", "a18_permute_relu", "a18_expcombiner_global"])
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
-def test_round_trips(precision):
-    """inverse(forward(x)) = x (first input_dim columns of the inverted latent) and forward(inverse(z))'s latent = z."""
-    name = "tiny_dgcnn_attn_extra"
+def test_round_trips(name, precision):
+    """inverse(forward(x)) = x (first input_dim columns of the inverted latent) through fc_flow_forward / fc_flow_sample, for the
+    shipped architecture and for the other couplings / permuters (CIF flows draw noise in both directions: no round trip)."""
     cfg, fsd, esd, batch = fixture_inputs(name)
     e = eng.FlowCompareB200((fsd, esd), cfg, device=DEV, precision=precision)
     emb = e.embed(batch["extract_0"].to(DEV))
-    extra = batch["extra_context"].to(DEV)
+    extra = None if batch["extra_context"] is None else batch["extra_context"].to(DEV)
     x = batch["extract_1"].to(DEV)
     N = x.shape[1]
     lp, z = e.forward(x, emb, extra, eps=batch["eps"].to(DEV))
     lp2 = e.log_prob(x, emb, extra, eps=batch["eps"].to(DEV))
     assert torch.equal(lp, lp2)
     x_back = e.sample(N, emb, extra_context=extra, z=z)
-    assert (x_back - x[..., :6]).abs().max().item() < 2e-5
+    err = (x_back - x[..., :6]).abs().max().item()
+    print(name, precision, "round trip", err)
+    assert err < (2e-5 if name.startswith("tiny") else 2e-4)     # spline bins with slope ~1e-3 amplify fp32 rounding on the way back
     # the augmented columns come back too: feed the sampled x with the eps that reproduces them is not possible from outside,
     # so check the latent round trip on the base draw instead: sample -> forward with eps recovered from the inverse pass
     e.close()
