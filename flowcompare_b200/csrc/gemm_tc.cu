@@ -154,6 +154,7 @@ struct TcParams {
     int T1, T2;    // k-blocks of segment 1 / 2
     int n_tiles, m_tiles;
     int pdl;       // launched with programmatic stream serialization
+    int tma_store; // STORE / LNQ epilogues: full 32 x 16 chunks leave through TMA stores (mapC) instead of per-thread stores
 };
 
 // phase counters (a -DTC_PHASE_TIMERS=1 build, scripts/tc_phases.py): per CTA, cycles
@@ -179,7 +180,8 @@ __device__ unsigned long long fc_tc_dbg[16];
 template <int EPI, int ACT, bool RES, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
-               const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
+               const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo,
+               const __grid_constant__ CUtensorMap mapC, const TcParams p) {
     constexpr int TC_STAGES = TcCfg<F16>::STAGES, TC_TSTAGES = TcCfg<F16>::TSTAGES, TS_COLS = TcCfg<F16>::TS_COLS;   // shadow the globals
     constexpr bool PARITY = F16 && TC_CONV_PARITY && TC_CONV_WARPS_N == 8;
     extern __shared__ unsigned char smem_raw[];
@@ -616,6 +618,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         float* stg = stage_out + ew * (32 * 20);
         int it = 0;
         long long e_wait = 0;
+        bool tma_pending = false;
         TC_T(e_t0);
         for (int L = blockIdx.x; L < total_tiles; L += gridDim.x, ++it) {
             const int n_tile = L % n_tiles, m0 = (L / n_tiles) * TC_BM;
@@ -662,6 +665,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             if (half * 16 < tile_bn) tmem_ld16x2_issue(acc_main + (uint32_t)(half * 16), acc_corr + (uint32_t)(half * 16), r, rc);
             for (int c0 = half * 16; c0 < tile_bn; c0 += 32) {
                 float v[16];
+                if (tma_pending) {       // the previous chunk's TMA store must have READ the staging tile before it is rewritten
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    tma_pending = false;
+                }
                 __syncwarp();
                 tmem_ld16x2_wait(r, rc);
     #pragma unroll
@@ -755,6 +762,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     } else if (ACT == FC_ACT_RELU) {
     #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (vec && p.tma_store) {
+                        // The chunk as a 32-row x 64-byte tile in the 64B-swizzle layout (16-byte chunk q of row r at q ^ ((r >> 1) & 3):
+                        // every thread writes its own row conflict free), handed to the TMA unit by one lane: no transposed
+                        // shared-memory reads, no per-thread global stores or address arithmetic (UTMASTG).
+                        unsigned char* sb = reinterpret_cast<unsigned char*>(stg) + lane * 64;
+                        const int sw = (lane >> 1) & 3;
+    #pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4*>(sb + ((q ^ sw) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&mapC, stg, col, row0);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        tma_pending = true;
+                        continue;
                     }
     #pragma unroll
                     for (int q = 0; q < 4; ++q) my_row4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -966,6 +991,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             warp_arrive(&acc_free[buf]);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // this warp's TMA stores have landed
 #if TC_PHASE_TIMERS
         if (threadIdx.x == 32 * TC_EPI_WARP0) {
             atomicAdd(&fc_tc_dbg[8], (unsigned long long)(clock64() - e_t0)); atomicAdd(&fc_tc_dbg[9], (unsigned long long)e_wait);
@@ -1009,13 +1035,14 @@ bool get_map(const void* base, uint64_t inner, uint64_t outer, uint64_t stride_f
     FcEncodeTiledFn enc = fc_get_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {stride_floats * (f16 ? 2 : 4)};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_outer};
+    // f16 = 2: the OUTPUT map of the TMA-store epilogue: fp32, boxes of 16 columns (64 bytes) x box_outer rows, 64B swizzle
+    cuuint64_t strides[1] = {stride_floats * (f16 == 1 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(f16 == 2 ? 16 : TC_BK), box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
-    CUresult r = enc(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+    CUresult r = enc(&m, f16 == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     f16 == 2 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         fprintf(stderr, "flowcompare_b200: cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu stride=%llu box=%ux%u\n",
                 (int)r, (const void*)base, (unsigned long long)inner, (unsigned long long)outer,
@@ -1042,7 +1069,7 @@ bool fc_gemm_tc_supported(const GemmArgs& a) {
 namespace {
 template <int EPI, int ACT, bool RES, bool F16>
 cudaError_t launch_tc2(cudaLaunchConfig_t cfg, int dev, const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mWh,
-                       const CUtensorMap& mWl, const TcParams& p) {
+                       const CUtensorMap& mWl, const CUtensorMap& mC, const TcParams& p) {
     // the dynamic shared-memory opt-in is PER DEVICE (and per instantiation): one bit per device id
     static std::atomic<uint64_t> configured{0};
     const uint64_t bit = 1ull << (dev & 63);
@@ -1053,13 +1080,13 @@ cudaError_t launch_tc2(cudaLaunchConfig_t cfg, int dev, const CUtensorMap& mA1, 
         configured.fetch_or(bit, std::memory_order_release);
     }
     cfg.dynamicSmemBytes = TcCfg<F16>::SMEM_BYTES;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, ACT, RES, F16>, mA1, mA2, mWh, mWl, p);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, ACT, RES, F16>, mA1, mA2, mWh, mWl, mC, p);
 }
 template <int EPI, int ACT, bool RES>
 cudaError_t launch_tc(const cudaLaunchConfig_t& cfg, int dev, int f16, const CUtensorMap& mA1, const CUtensorMap& mA2,
-                      const CUtensorMap& mWh, const CUtensorMap& mWl, const TcParams& p) {
-    return f16 ? launch_tc2<EPI, ACT, RES, true>(cfg, dev, mA1, mA2, mWh, mWl, p)
-               : launch_tc2<EPI, ACT, RES, false>(cfg, dev, mA1, mA2, mWh, mWl, p);
+                      const CUtensorMap& mWh, const CUtensorMap& mWl, const CUtensorMap& mC, const TcParams& p) {
+    return f16 ? launch_tc2<EPI, ACT, RES, true>(cfg, dev, mA1, mA2, mWh, mWl, mC, p)
+               : launch_tc2<EPI, ACT, RES, false>(cfg, dev, mA1, mA2, mWh, mWl, mC, p);
 }
 int sm_count(int dev) {   // per device, cached
     static std::atomic<int> cache[64];
@@ -1098,6 +1125,15 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     const int f16 = a.tc_fmt ? 1 : 0;
     if (!get_map(a.Whi, (uint64_t)a.ldk, (uint64_t)p.n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWh, f16)) return FC_ERR_CUDA;
     if (!get_map(a.Wlo, (uint64_t)a.ldk, (uint64_t)p.n_tiles * p.BN, (uint64_t)a.ldk, (uint32_t)p.BN, &mWl, f16)) return FC_ERR_CUDA;
+    // TMA-store epilogue (FC_TC_TMASTORE=0 turns it off for A/B runs): plain-store epilogues whose output rows are 16-byte aligned
+    static int tma_store_env = -1;
+    if (tma_store_env < 0) { const char* e = getenv("FC_TC_TMASTORE"); tma_store_env = (e && e[0] == '0') ? 0 : 1; }
+    CUtensorMap mC = mA1;
+    p.tma_store = 0;
+    if (tma_store_env && (a.epi == FC_EPI_STORE || a.epi == FC_EPI_LNQ) && (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0) {
+        if (!get_map(a.C, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldc, 32, &mC, 2)) return FC_ERR_CUDA;
+        p.tma_store = 1;
+    }
     int dev = 0;
     FC_CUDA_OK(cudaGetDevice(&dev));
     const int nsm = sm_count(dev);
@@ -1121,24 +1157,24 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     const bool res = a.res != nullptr;
     cudaError_t le = cudaErrorInvalidValue;
     if (a.epi == FC_EPI_STORE) {
-        if (a.act == FC_ACT_NONE)       le = res ? launch_tc<FC_EPI_STORE, FC_ACT_NONE, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, p)
-                                                 : launch_tc<FC_EPI_STORE, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
-        else if (a.act == FC_ACT_GELU)  le = res ? launch_tc<FC_EPI_STORE, FC_ACT_GELU, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, p)
-                                                 : launch_tc<FC_EPI_STORE, FC_ACT_GELU, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
-        else if (a.act == FC_ACT_LRELU) le = res ? launch_tc<FC_EPI_STORE, FC_ACT_LRELU, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, p)
-                                                 : launch_tc<FC_EPI_STORE, FC_ACT_LRELU, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
-        else if (a.act == FC_ACT_RELU)  le = res ? launch_tc<FC_EPI_STORE, FC_ACT_RELU, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, p)
-                                                 : launch_tc<FC_EPI_STORE, FC_ACT_RELU, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
+        if (a.act == FC_ACT_NONE)       le = res ? launch_tc<FC_EPI_STORE, FC_ACT_NONE, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p);
+        else if (a.act == FC_ACT_GELU)  le = res ? launch_tc<FC_EPI_STORE, FC_ACT_GELU, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_GELU, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p);
+        else if (a.act == FC_ACT_LRELU) le = res ? launch_tc<FC_EPI_STORE, FC_ACT_LRELU, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_LRELU, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p);
+        else if (a.act == FC_ACT_RELU)  le = res ? launch_tc<FC_EPI_STORE, FC_ACT_RELU, true>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p)
+                                                 : launch_tc<FC_EPI_STORE, FC_ACT_RELU, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p);
     } else if (a.epi == FC_EPI_LNQ && a.act == FC_ACT_NONE && !res) {
-        le = launch_tc<FC_EPI_LNQ, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
+        le = launch_tc<FC_EPI_LNQ, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p);
     } else if (a.epi == FC_EPI_COUPLING) {
-        le = launch_tc<FC_EPI_COUPLING, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
+        le = launch_tc<FC_EPI_COUPLING, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p);
     } else if (a.epi == FC_EPI_AUGMENT) {
-        le = launch_tc<FC_EPI_AUGMENT, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
+        le = launch_tc<FC_EPI_AUGMENT, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p);
     } else if (a.epi == FC_EPI_COUPLING_INV) {
-        le = launch_tc<FC_EPI_COUPLING_INV, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
+        le = launch_tc<FC_EPI_COUPLING_INV, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p);
     } else if (a.epi == FC_EPI_KVSPLIT && a.act == FC_ACT_NONE && !res) {
-        le = launch_tc<FC_EPI_KVSPLIT, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, p);
+        le = launch_tc<FC_EPI_KVSPLIT, FC_ACT_NONE, false>(cfg, dev, f16, mA1, mA2, mWh, mWl, mC, p);
     } else {
         return FC_ERR_UNSUPPORTED;
     }
