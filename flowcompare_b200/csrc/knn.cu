@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "gemm.cuh"  // fc_count_launch
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace {
@@ -225,6 +226,295 @@ knn_kernel(const float* __restrict__ q, int ldq, long long q_bstride, const floa
     }
 }
 
+// ----------------------------------------------------------------------------- two-kernel form (the default)
+// The fused kernel above keeps two sorted top-k lists per query IN REGISTERS next to the 8x8 distance tile: 251 registers, two
+// CTAs of four warps per SM, and a data-dependent insertion loop in lock step over 32 queries -- 9 TFLOP/s, 12 % of the FP32
+// bound, and nothing short of separating the two jobs changes that.  So:
+//   knn_dist_kernel    a plain FFMA tile kernel (128 x 128 keys per CTA, 8 x 8 per thread, double-buffered shared memory, 2 CTAs
+//                      per SM) that writes the KEYS of a chunk of clouds (up to 1 GB) to scratch -- the same canonical arithmetic
+//                      (sequential fmaf over the features, then ((-xx_j) - (-2 dot)) - xx_i), so every key is bit-identical to the
+//                      fused form.  Measured 28 TFLOP/s at C = 64 .. 128 (the k-loop is only 4 .. 8 tiles long).
+//   knn_select_kernel  one WARP per query row, no data-dependent loop: every lane loads its 40 strided keys of a 1280-key segment
+//                      into registers, the k-th largest of the 96 lane-local top-3 values is a LOWER BOUND L of the row's k-th
+//                      best (a subset's k-th largest never exceeds the set's), every lane writes its keys >= L (~45-55 in all)
+//                      to shared memory as 64-bit (key, ~index) words at its prefix-sum offset, and the warp sorts them with a
+//                      bitonic network IN REGISTERS (2 words per lane, shuffles); the first k are the answer in (key desc,
+//                      index asc) order.  Longer rows repeat this per segment, carrying the sorted list.  More than 256 survivors
+//                      (masses of exact duplicates) take an exact 32-step bisection with index-ordered ties instead.
+//                      ~1400 warp instructions per row, 64 registers, 0.45 ms per layer at 128 clouds of 1250 points.
+constexpr int DT = 128, DK = 16, DLD = DT + 4;
+
+// VEC: 16-byte loads (C % 4 == 0, rows 16-byte aligned); otherwise scalar loads (the 6-column input layer)
+template <bool VEC>
+__global__ void __launch_bounds__(256, 2)
+knn_dist_kernel(const float* __restrict__ q, int ldq, long long q_bstride, const float* __restrict__ t, int ldt,
+                long long t_bstride, const float* __restrict__ qnorm, const float* __restrict__ tnorm, int Nq, int Nt, int C,
+                int mode, float* __restrict__ keys, int ldk, int b0) {
+    __shared__ __align__(16) float Qs[2][DK][DLD];
+    __shared__ __align__(16) float Ts[2][DK][DLD];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int bl = blockIdx.z, b = b0 + bl;
+    const int q0 = blockIdx.y * DT, t0 = blockIdx.x * DT;
+    const int a_row = tid >> 2, a_kq = (tid & 3) * 4;
+    // this thread's two query rows and two candidate rows (64 apart); rows past the end read row 0 and are zeroed
+    const bool qok0 = q0 + a_row < Nq, qok1 = q0 + a_row + 64 < Nq, tok0 = t0 + a_row < Nt, tok1 = t0 + a_row + 64 < Nt;
+    const float* qp0 = q + (size_t)b * q_bstride + (size_t)(qok0 ? q0 + a_row : 0) * ldq + a_kq;
+    const float* tp0 = t + (size_t)b * t_bstride + (size_t)(tok0 ? t0 + a_row : 0) * ldt + a_kq;
+    const size_t qs1 = (size_t)64 * ldq, ts1 = (size_t)64 * ldt;      // never dereferenced for rows past the end (ld4 checks)
+    float4 rq0, rq1, rt0, rt1;
+    auto ld4 = [&](const float* src, int k, bool ok) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (VEC) { if (ok && k < C) v = *reinterpret_cast<const float4*>(src); }
+        else if (ok) { if (k < C) v.x = src[0]; if (k + 1 < C) v.y = src[1]; if (k + 2 < C) v.z = src[2]; if (k + 3 < C) v.w = src[3]; }
+        return v;
+    };
+    auto load = [&](int c0) {
+        const int k = c0 + a_kq;
+        rq0 = ld4(qp0 + c0, k, qok0); rq1 = ld4(qp0 + qs1 + c0, k, qok1);
+        rt0 = ld4(tp0 + c0, k, tok0); rt1 = ld4(tp0 + ts1 + c0, k, tok1);
+    };
+    auto store = [&](int buf) {
+        Qs[buf][a_kq + 0][a_row] = rq0.x; Qs[buf][a_kq + 1][a_row] = rq0.y; Qs[buf][a_kq + 2][a_row] = rq0.z; Qs[buf][a_kq + 3][a_row] = rq0.w;
+        Qs[buf][a_kq + 0][a_row + 64] = rq1.x; Qs[buf][a_kq + 1][a_row + 64] = rq1.y; Qs[buf][a_kq + 2][a_row + 64] = rq1.z; Qs[buf][a_kq + 3][a_row + 64] = rq1.w;
+        Ts[buf][a_kq + 0][a_row] = rt0.x; Ts[buf][a_kq + 1][a_row] = rt0.y; Ts[buf][a_kq + 2][a_row] = rt0.z; Ts[buf][a_kq + 3][a_row] = rt0.w;
+        Ts[buf][a_kq + 0][a_row + 64] = rt1.x; Ts[buf][a_kq + 1][a_row + 64] = rt1.y; Ts[buf][a_kq + 2][a_row + 64] = rt1.z; Ts[buf][a_kq + 3][a_row + 64] = rt1.w;
+    };
+    float dot[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dot[i][j] = 0.f;
+    const int T = (C + DK - 1) / DK;
+    load(0);
+    store(0);
+    __syncthreads();
+    for (int tt = 0; tt < T; ++tt) {
+        const int buf = tt & 1;
+        if (tt + 1 < T) load((tt + 1) * DK);
+        const int cmax = min(DK, C - tt * DK);      // canonical order: features 0 .. C-1, nothing beyond
+#pragma unroll 4
+        for (int kk = 0; kk < cmax; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&Qs[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&Qs[buf][kk][64 + ty * 4]);
+            const float4 c0 = *reinterpret_cast<const float4*>(&Ts[buf][kk][tx * 4]);
+            const float4 c1 = *reinterpret_cast<const float4*>(&Ts[buf][kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dot[i][j] = fmaf(av[i], cv[j], dot[i][j]);
+        }
+        if (tt + 1 < T) { store(buf ^ 1); __syncthreads(); }
+    }
+    // keys: one 4-column group at a time (the candidate norms are re-read per group: keeps the epilogue's registers low)
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int col = t0 + g * 64 + tx * 4;
+        float xc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xc[j] = col + j < Nt ? tnorm[(size_t)b * Nt + col + j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = q0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+            if (row >= Nq) continue;
+            const float xq = qnorm[(size_t)b * Nq + row];
+            float kv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = dot[i][g * 4 + j];
+                kv[j] = mode == 0 ? __fsub_rn(__fsub_rn(-xc[j], -2.0f * d), xq) : -__fsub_rn(__fadd_rn(xq, xc[j]), 2.0f * d);
+            }
+            float* dst = keys + ((size_t)bl * Nq + row) * ldk + col;
+            if (col + 3 < Nt) *reinterpret_cast<float4*>(dst) = make_float4(kv[0], kv[1], kv[2], kv[3]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (col + j < Nt) dst[j] = kv[j];
+            }
+        }
+    }
+}
+
+#ifndef SEL_KO
+#define SEL_KO 0                       // timing experiments: 1 no bisection, 2 no compaction, 4 no sort (bit mask; results are garbage)
+#endif
+constexpr int SEL_R = 40;              // keys per lane and segment
+constexpr int SEL_SEG = 32 * SEL_R;    // 1280
+constexpr int SEL_CAP = 256;           // survivor buffer (64-bit words) per warp
+__device__ __forceinline__ unsigned knn_ord(float x) {      // monotone float -> unsigned (larger float <-> larger word); 0 is below every float
+    const unsigned u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+// Bitonic sort (descending) of 32*NPL words held NPL per lane, element index = lane + 32*j: partners closer than 32 are
+// another lane's register j (shuffles), partners 32*m apart are this lane's own registers.
+template <int NPL>
+__device__ __forceinline__ void warp_bitonic_desc(unsigned long long (&v)[NPL], int lane) {
+#pragma unroll
+    for (int sz = 2; sz <= 32 * NPL; sz <<= 1) {
+#pragma unroll
+        for (int st = sz >> 1; st > 0; st >>= 1) {
+            if (st >= 32) {
+                const int js = st >> 5;
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) {
+                    if ((j & js) == 0) {
+                        const bool desc = (((lane + 32 * j) & sz) == 0);
+                        const unsigned long long a = v[j], c = v[j | js];
+                        if ((a < c) == desc) { v[j] = c; v[j | js] = a; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) {
+                    const unsigned long long other = shfl_xor_u64(v[j], st);
+                    const bool desc = (((lane + 32 * j) & sz) == 0), lower = (lane & st) == 0;
+                    // the lower index of a pair keeps the larger word when the run is descending
+                    const bool keep_max = lower == desc;
+                    v[j] = keep_max ? (v[j] > other ? v[j] : other) : (v[j] < other ? v[j] : other);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+knn_select_kernel(const float* __restrict__ keys, int ldk, int n_rows, int Nt, int k, int32_t* __restrict__ idx32,
+                  int64_t* __restrict__ idx64, long long out_row0) {
+    __shared__ unsigned long long sbuf[8][SEL_CAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int row = blockIdx.x * 8 + wid;
+    if (row >= n_rows) return;
+    unsigned long long* sv = sbuf[wid];
+    const float* kr = keys + (size_t)row * ldk;
+    const unsigned lt = (1u << lane) - 1u;
+    int have = 0;                          // entries of the running list (sorted, sv[0 .. have))
+    for (int seg0 = 0; seg0 < Nt; seg0 += SEL_SEG) {
+        unsigned r[SEL_R];
+        unsigned m1 = 0u, m2 = 0u, m3 = 0u;   // this lane's three largest keys of the segment
+#pragma unroll
+        for (int i = 0; i < SEL_R; ++i) {
+            const int e = seg0 + i * 32 + lane;
+            const float x = kr[min(e, Nt - 1)];
+            r[i] = e < Nt ? knn_ord(x) : 0u;
+            const unsigned a = min(m1, r[i]);
+            m1 = max(m1, r[i]);
+            const unsigned c = min(m2, a);
+            m2 = max(m2, a);
+            m3 = max(m3, c);
+        }
+        // the running list's keys (two per lane; zero beyond `have`)
+        const unsigned long long w0 = lane < have ? sv[lane] : 0ull, w1 = 32 + lane < have ? sv[32 + lane] : 0ull;
+        const unsigned l0 = (unsigned)(w0 >> 32), l1 = (unsigned)(w1 >> 32);
+        // L = k-th largest of the 96 lane-local top-3 keys (a lower bound of the row's k-th best): bisection on the ordered words
+        unsigned L = 0u;
+        if (SEL_KO & 1) L = __reduce_max_sync(0xffffffffu, m3);
+        else
+        for (int bit = 31; bit >= 0; --bit) {
+            const unsigned cand = L | (1u << bit);
+            const unsigned cnt = __reduce_add_sync(0xffffffffu, (unsigned)(m1 >= cand) + (unsigned)(m2 >= cand) + (unsigned)(m3 >= cand));
+            if (cnt >= (unsigned)k) L = cand;
+        }
+        if (have >= k) { const unsigned lk = (unsigned)(sv[k - 1] >> 32); L = max(L, lk); }   // the list's k-th best is a lower bound too
+        unsigned thr_gt = L ? L - 1u : 0u;  // keys > thr_gt always survive
+        unsigned cnt_l = (unsigned)(l0 > thr_gt) + (unsigned)(l1 > thr_gt);
+#pragma unroll
+        for (int i = 0; i < SEL_R; ++i) cnt_l += (unsigned)(r[i] > thr_gt);
+        unsigned tot = __reduce_add_sync(0xffffffffu, cnt_l);
+        __syncwarp();
+        int base;
+        if (tot <= (unsigned)SEL_CAP) {
+            // every lane writes its own survivors at its own offset (order in the buffer is irrelevant: the sort below orders
+            // by (key, index)); exclusive prefix sum of the per-lane counts
+            unsigned off = cnt_l;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, off, d); if (lane >= d) off += n; }
+            off -= cnt_l;
+            if (l0 > thr_gt) sv[off++] = w0;
+            if (l1 > thr_gt) sv[off++] = w1;
+#pragma unroll
+            for (int i = 0; i < ((SEL_KO & 2) ? 2 : SEL_R); ++i) {
+                if (r[i] > thr_gt) sv[off++] = ((unsigned long long)r[i] << 32) | (unsigned)(~(unsigned)(seg0 + i * 32 + lane));
+            }
+            base = (int)tot;
+        } else {
+            // masses of equal keys: exact k-th largest T of (list + segment) by bisection, then everything above T plus the first
+            // equals in index order (the list entries precede the segment)
+            unsigned Tk = 0u;
+            for (int bit = 31; bit >= 0; --bit) {
+                const unsigned cand = Tk | (1u << bit);
+                unsigned cc = (unsigned)(l0 >= cand) + (unsigned)(l1 >= cand);
+#pragma unroll
+                for (int i = 0; i < SEL_R; ++i) cc += (unsigned)(r[i] >= cand);
+                if (__reduce_add_sync(0xffffffffu, cc) >= (unsigned)k) Tk = cand;
+            }
+            unsigned cg = (unsigned)(l0 > Tk) + (unsigned)(l1 > Tk);
+#pragma unroll
+            for (int i = 0; i < SEL_R; ++i) cg += (unsigned)(r[i] > Tk);
+            int need = k - (int)__reduce_add_sync(0xffffffffu, cg);
+            base = 0;
+            auto push = [&](bool gt, bool eq, unsigned long long word) {
+                const unsigned meq = __ballot_sync(0xffffffffu, eq);
+                const bool take = gt || (eq && __popc(meq & lt) < need);
+                need = max(0, need - __popc(meq));
+                const unsigned m = __ballot_sync(0xffffffffu, take);
+                if (take) sv[base + __popc(m & lt)] = word;
+                base += __popc(m);
+            };
+            push(l0 > Tk, l0 == Tk && lane < have, w0);
+            push(l1 > Tk, l1 == Tk && 32 + lane < have, w1);
+#pragma unroll 1
+            for (int i = 0; i < SEL_R; ++i) {
+                unsigned ri = 0u;
+#pragma unroll
+                for (int jj = 0; jj < SEL_R; ++jj) if (jj == i) ri = r[jj];
+                const int e = seg0 + i * 32 + lane;
+                push(ri > Tk, ri == Tk && e < Nt, ((unsigned long long)ri << 32) | (unsigned)(~(unsigned)e));
+            }
+        }
+        __syncwarp();
+        // sort the survivors (descending), padded with zeros: in registers, 2 / 4 / 8 words per lane
+        if (!(SEL_KO & 4)) {
+            if (base <= 64) {
+                unsigned long long v[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) v[j] = lane + 32 * j < base ? sv[lane + 32 * j] : 0ull;
+                warp_bitonic_desc<2>(v, lane);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 2; ++j) sv[lane + 32 * j] = v[j];
+            } else if (base <= 128) {
+                unsigned long long v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = lane + 32 * j < base ? sv[lane + 32 * j] : 0ull;
+                warp_bitonic_desc<4>(v, lane);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sv[lane + 32 * j] = v[j];
+            } else {
+                unsigned long long v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = lane + 32 * j < base ? sv[lane + 32 * j] : 0ull;
+                warp_bitonic_desc<8>(v, lane);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sv[lane + 32 * j] = v[j];
+            }
+        }
+        __syncwarp();
+        have = min(base, k);
+    }
+    const size_t o = (size_t)(out_row0 + row) * k;
+    for (int p = lane; p < k; p += 32) {
+        const int v = p < have ? (int)(~(unsigned)sv[p]) : 0;
+        if (idx32) idx32[o + p] = v;
+        if (idx64) idx64[o + p] = (int64_t)v;
+    }
+}
+
 template <int KCAP, typename... Args>
 cudaError_t launch_knn(int dev, dim3 grid, cudaStream_t stream, Args... args) {
     const size_t smem = sizeof(KnnSmem) + (size_t)TM * 2 * KCAP * 8;
@@ -241,8 +531,25 @@ cudaError_t launch_knn(int dev, dim3 grid, cudaStream_t stream, Args... args) {
 
 }  // namespace
 
+namespace {
+// clouds per chunk of the two-kernel form: up to 1 GB of keys at a time.  (L2-sized chunks of 100 MB were measured SLOWER, 5.58
+// vs 5.02 ms for the four layers at 128 clouds of 1250 points: eight short launches with their tails cost more than the HBM
+// round trip of 0.8 GB, which takes 0.25 ms.)
+int knn_chunk_clouds(int B, int Nq, int Nt) {
+    const long long per = (long long)Nq * fc_round_up(Nt, 4);
+    static long long budget = 0;       // floats of keys per chunk (FC_KNN_CHUNK_MB: A/B knob)
+    if (!budget) { const char* e = getenv("FC_KNN_CHUNK_MB"); budget = (e ? atoll(e) : 1024ll) << 18; if (budget < 1) budget = 256ll << 20; }
+    long long cb = budget / (per > 0 ? per : 1);
+    if (cb < 1) cb = 1;
+    if (cb > B) cb = B;
+    return (int)cb;
+}
+int64_t knn_norm_floats(int B, int Nq, int Nt, bool self) { return fc_round_up_ll((int64_t)B * (self ? Nt : Nq + Nt), 64); }
+}  // namespace
+
+// scratch of a kNN call: the squared norms of the points, then the keys of one chunk of clouds
 int64_t fc_knn_scratch_floats(int B, int Nq, int Nt, bool self) {
-    return (int64_t)B * (self ? Nt : Nq + Nt);
+    return knn_norm_floats(B, Nq, Nt, self) + (int64_t)knn_chunk_clouds(B, Nq, Nt) * Nq * fc_round_up(Nt, 4);
 }
 
 int fc_knn_launch(const float* q, int ldq, long long q_bstride, const float* t, int ldt, long long t_bstride,
@@ -260,6 +567,32 @@ int fc_knn_launch(const float* q, int ldq, long long q_bstride, const float* t, 
     norms_kernel<<<dim3((Nt + 255) / 256, B), 256, 0, stream>>>(t, ldt, t_bstride, Nt, C, tn);
     fc_count_launch();
     if (!self) { norms_kernel<<<dim3((Nq + 255) / 256, B), 256, 0, stream>>>(q, ldq, q_bstride, Nq, C, qn); fc_count_launch(); }
+    static int fused_env = -1;     // FC_KNN=fused: the one-kernel form (A/B runs)
+    if (fused_env < 0) { const char* e = getenv("FC_KNN"); fused_env = (e && e[0] == 'f') ? 1 : 0; }
+    if (!fused_env) {
+        float* keys = norms_scratch + knn_norm_floats(B, Nq, Nt, self);
+        const int ldk = fc_round_up(Nt, 4);
+        const int cb = knn_chunk_clouds(B, Nq, Nt);
+        static int skip = -1;          // FC_KNN_SKIP=d|s: timing experiments (results are garbage)
+        if (skip < 0) { const char* e = getenv("FC_KNN_SKIP"); skip = !e ? 0 : (e[0] == 'd' ? 1 : 2); }
+        for (int b0 = 0; b0 < B; b0 += cb) {
+            const int nb = B - b0 < cb ? B - b0 : cb;
+            if (skip != 1)
+            {
+                const dim3 grid((Nt + DT - 1) / DT, (Nq + DT - 1) / DT, nb);
+                const bool vec = (C & 3) == 0 && (ldq & 3) == 0 && (ldt & 3) == 0 && (q_bstride & 3) == 0 && (t_bstride & 3) == 0 &&
+                                 ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(t)) & 15) == 0;
+                if (vec) knn_dist_kernel<true><<<grid, 256, 0, stream>>>(q, ldq, q_bstride, t, ldt, t_bstride, qn, tn, Nq, Nt, C, mode, keys, ldk, b0);
+                else     knn_dist_kernel<false><<<grid, 256, 0, stream>>>(q, ldq, q_bstride, t, ldt, t_bstride, qn, tn, Nq, Nt, C, mode, keys, ldk, b0);
+            }
+            const long long rows = (long long)nb * Nq;
+            if (skip != 2)
+            knn_select_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(keys, ldk, (int)rows, Nt, k, idx32, idx64, (long long)b0 * Nq);
+            fc_count_launch(2);
+        }
+        FC_LAUNCH_OK();
+        return FC_OK;
+    }
     int dev = 0;
     FC_CUDA_OK(cudaGetDevice(&dev));
     dim3 grid((Nq + TM - 1) / TM, B);
