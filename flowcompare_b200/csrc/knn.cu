@@ -47,6 +47,29 @@ __global__ void norms_kernel(const float* __restrict__ x, int ld, long long bstr
     xx[(size_t)b * N + i] = s;
 }
 
+// The same sums for wide rows (C >= 32): a warp owns 32 points and moves their rows through shared memory 32 columns at a time, so
+// the global loads are coalesced (one 128-byte row segment per instruction) instead of 32 rows per instruction; each lane still adds
+// ITS point's squares in column order -- the result is bit-identical to norms_kernel.
+__global__ void __launch_bounds__(256) norms_wide_kernel(const float* __restrict__ x, int ld, long long bstride, int N, int C,
+                                                         float* __restrict__ xx) {
+    __shared__ float tile[8][32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, b = blockIdx.y;
+    const int p0 = (blockIdx.x * 8 + w) * 32;
+    if (p0 >= N) return;
+    const float* xb = x + (size_t)b * bstride;
+    float s = 0.f;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r)
+            tile[w][r][lane] = (p0 + r < N && c0 + lane < C) ? xb[(size_t)(p0 + r) * ld + c0 + lane] : 0.f;
+        __syncwarp();
+        const int cmax = min(32, C - c0);
+        for (int c = 0; c < cmax; ++c) { const float v = tile[w][lane][c]; s = fmaf(v, v, s); }
+        __syncwarp();
+    }
+    if (p0 + lane < N) xx[(size_t)b * N + p0 + lane] = s;
+}
+
 struct KnnSmem {
     float Qs[CK][TM];                 // query chunk, feature-major
     float Cs[CK][TN];                 // candidate chunk, feature-major
@@ -564,9 +587,13 @@ int fc_knn_launch(const float* q, int ldq, long long q_bstride, const float* t, 
     float* qn = self ? tn : norms_scratch + (size_t)B * Nt;
     FcProfScope prof(FC_CLS_KNN, 2.0 * B * (double)Nq * Nt * C,
                      4.0 * B * ((double)(self ? Nt : Nq + Nt) * C + (double)Nq * k), stream);
-    norms_kernel<<<dim3((Nt + 255) / 256, B), 256, 0, stream>>>(t, ldt, t_bstride, Nt, C, tn);
-    fc_count_launch();
-    if (!self) { norms_kernel<<<dim3((Nq + 255) / 256, B), 256, 0, stream>>>(q, ldq, q_bstride, Nq, C, qn); fc_count_launch(); }
+    auto norms = [&](const float* p, int ld, long long bs, int n, float* out) {
+        if (C >= 32) norms_wide_kernel<<<dim3((n + 255) / 256, B), 256, 0, stream>>>(p, ld, bs, n, C, out);
+        else         norms_kernel<<<dim3((n + 255) / 256, B), 256, 0, stream>>>(p, ld, bs, n, C, out);
+        fc_count_launch();
+    };
+    norms(t, ldt, t_bstride, Nt, tn);
+    if (!self) norms(q, ldq, q_bstride, Nq, qn);
     static int fused_env = -1;     // FC_KNN=fused: the one-kernel form (A/B runs)
     if (fused_env < 0) { const char* e = getenv("FC_KNN"); fused_env = (e && e[0] == 'f') ? 1 : 0; }
     if (!fused_env) {

@@ -380,3 +380,21 @@ def test_fps_oracle_is_furthest_point_sampling():
     for j in range(1, 40):
         d = ((x[:, None, :] - x[None, idx[:j], :]) ** 2).sum(-1).min(1)
         assert d[idx[j]] >= d.max() * (1 - 1e-6)
+
+
+@pytest.mark.parametrize("kind", ["LinearLU", "random_permute", "FullCombiner", "ExponentialCombiner"])
+def test_permuter_fold_and_its_inverse(kind):
+    """packing.permuter_matrix / permuter_inverse_matrix (the pack-time form of every permuter, reference model_initialization.py:
+    117-131): the matrix reproduces the port's forward transform and log-det, and inverse @ forward = I."""
+    cfg = configs.tiny_config("dgcnn_attn", permuter_type=kind, latent_dim=24, cif_latent_dim=24)
+    dcfg = configs.derive(cfg)
+    fsd, _ = spec.random_state_dicts(cfg, seed=5)
+    t = 3     # transforms.1 coupling, .2 ActNorm, .3 permuter
+    W, ldj = packing.permuter_matrix(fsd, t, dcfg)
+    Winv = packing.permuter_inverse_matrix(fsd, t, dcfg)
+    assert (Winv @ W - torch.eye(24, dtype=torch.float64)).abs().max().item() < 1e-9
+    x = torch.randn(2, 5, 24, generator=torch.Generator().manual_seed(1))
+    y, l = port.permuter_forward(fsd, t, x, dcfg)
+    assert (y.double() - x.double() @ W.t()).abs().max().item() < 1e-5
+    assert abs(float(l.reshape(-1)[0]) - ldj) < 1e-4
+    assert (port.permuter_inverse(fsd, t, y, dcfg) - x).abs().max().item() < 1e-4
