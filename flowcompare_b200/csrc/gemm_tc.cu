@@ -57,8 +57,11 @@ constexpr int TC_STAGES = 5;                   // shared-memory stages: a load i
 #ifndef TC_BN_CAP
 #define TC_BN_CAP 96                           // widest tile (accumulator width); 80 leaves room for 6 A stages (measured slower)
 #endif
+#ifndef TC_RES_PREFETCH
+#define TC_RES_PREFETCH 1                      // 3xFP16 mode: the residual of an epilogue chunk arrives by cp.async one chunk ahead (the first
+#endif                                         // chunk's before the accumulator wait) in a second per-warp staging tile; costs one pipeline stage
 #ifndef TC_STAGES_F16
-#define TC_STAGES_F16 7                        // 3xFP16 mode: a stage is 16 KB of A + 2 x 6 KB of W, tensor time per k-block is halved
+#define TC_STAGES_F16 (TC_RES_PREFETCH ? 6 : 7)                        // 3xFP16 mode: a stage is 16 KB of A + 2 x 6 KB of W, tensor time per k-block is halved
 #endif
 // Knock-out switches for bottleneck hunting (scripts/build_variant.sh ... "-DTC_KO_MMA=1"): the pipeline keeps its shape and
 // barrier traffic, one stage of work is skipped; the RESULTS ARE GARBAGE, only the timing is meaningful.
@@ -131,7 +134,9 @@ template <bool F16> struct TcCfg {
     static constexpr int TS_COLS = F16 ? 16 : 32;                     // TMEM columns of one A stage (HALF a k-block: hi | lo)
     static constexpr int TSTAGES = (512 - 4 * TC_BN_CAP) / TS_COLS;   // TMEM stages of the A operand
     // stages x (16 KB A + Whi + Wlo at BN = 96) + 8 staging tiles of the epilogue + 1 KB alignment slack
-    static constexpr int SMEM_BYTES = STAGES * (TC_BM * TC_BK * 4 + 2 * 96 * TC_BK * W_ELT) + 8 * 32 * 20 * 4 + 1024;
+    static constexpr bool RES_PF = F16 && TC_RES_PREFETCH;            // residual prefetch (two 2 KB swizzled tiles per epilogue warp)
+    static constexpr int STG_FLOATS = RES_PF ? 1024 : 32 * 20;        // per-warp staging floats
+    static constexpr int SMEM_BYTES = STAGES * (TC_BM * TC_BK * 4 + 2 * 96 * TC_BK * W_ELT) + 8 * STG_FLOATS * 4 + 1024;
 };
 // phase timers (scripts/tc_phases.py): compiled out by default, build a variant with -DTC_PHASE_TIMERS=1
 #ifndef TC_PHASE_TIMERS
@@ -615,7 +620,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         const GemmArgs& a = p.g;
         // per-warp staging tile [32 rows][16 + 4 pad] (rows 16-byte aligned; a thread's own-row float4 accesses are
         // conflict free, the transposed ones 2-way at worst)
-        float* stg = stage_out + ew * (32 * 20);
+        float* stg = stage_out + ew * TcCfg<F16>::STG_FLOATS;
         int it = 0;
         long long e_wait = 0;
         bool tma_pending = false;
@@ -640,6 +645,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 }
                 if (etid == 0) bias_in_smem2[buf] = (one_group && m0 < a.M) ? 1 : 0;
             }
+            // The residual of a chunk does not depend on the accumulator: its (L2-latency) loads are issued one chunk ahead,
+            // and the first chunk's before the wait for the tensor core, so they overlap the mainloop / the previous chunk.
+            const int row0 = m0 + quad * 32;
+            const bool vec_base = row0 + 32 <= a.M && (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0;
+            const bool vec_res = RES && (a.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0 &&
+                                 (!a.res_scale || (reinterpret_cast<uintptr_t>(a.res_scale) & 15) == 0);
+            // Prefetch (3xFP16, TMA-store launches): chunk c's residual is copied by cp.async into the staging tile the chunk's
+            // output will later be written to (64B-swizzle layout, thread (r, q) -> row r, 16-byte slot q ^ ((r >> 1) & 3));
+            // the two tiles alternate, so the copy for chunk c+1 runs while chunk c is computed and stored.
+            const bool res_pf = TcCfg<F16>::RES_PF && RES && p.tma_store && vec_base && vec_res;
+            int pb = 0;
+            auto res_prefetch = [&](int c0n, int which) {
+                const int coln = tile_n0 + c0n;
+                if (c0n < tile_bn && coln + 16 <= a.N) {
+                    const float* rp = a.res + (size_t)(row0 + (lane >> 2)) * a.ldres + coln + (lane & 3) * 4;
+                    const uint32_t dst0 = smem_u32(stg + which * 512);
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = (lane >> 2) + 8 * i;
+                        const uint32_t dst = dst0 + (uint32_t)(rr * 64 + ((((lane & 3) ^ ((rr >> 1) & 3))) << 4));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(rp + (size_t)(8 * i) * a.ldres) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            if (res_pf) {
+                if (tma_pending) {       // the last chunk of the previous tile may still be read by its TMA store
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    tma_pending = false;
+                    __syncwarp();
+                }
+                res_prefetch(half * 16, pb);
+            }
+            // Same for the coupling epilogue's latent values (8 per row and chunk): copied ahead into a compact [32][12] tile
+            // behind the [32][20] staging tile.
+            const bool cpl_pf = TcCfg<F16>::RES_PF && EPI == FC_EPI_COUPLING && !TC_KO_CPLMEM && TC_CPL_STAGED && row0 + 32 <= a.M &&
+                                ((a.ldx | a.col0) & 1) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 7) == 0;
+            auto cpl_prefetch = [&](int c0n) {
+                const int coln = tile_n0 + c0n;
+                if (c0n < tile_bn && coln + 16 <= a.N) {
+                    const float* gx = a.x + (size_t)(row0 + (lane >> 2)) * a.ldx + a.col0 + (coln >> 1) + (lane & 3) * 2;
+                    const uint32_t dst0 = smem_u32(stg + 640 + (lane >> 2) * 12 + (lane & 3) * 2);
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst0 + (uint32_t)(8 * i * 12 * 4)), "l"(gx + (size_t)(8 * i) * a.ldx) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            if (cpl_pf) cpl_prefetch(half * 16);
+            float mu = 0.f, rstd = 0.f;
+            if (EPI == FC_EPI_LNQ && m0 + row_in_tile < a.M) { mu = a.row_mu[m0 + row_in_tile]; rstd = a.row_rstd[m0 + row_in_tile]; }
             TC_T(ea0);
             mbar_wait(&acc_full[buf], (it >> 1) & 1, 500);
             TC_T(ea1);
@@ -652,14 +708,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             const bool row_ok = row < a.M;
             const int n0 = tile_n0;
             float ldj = 0.f;
-            float mu = 0.f, rstd = 0.f;
-            if (EPI == FC_EPI_LNQ && row_ok) { mu = a.row_mu[row]; rstd = a.row_rstd[row]; }
             const float* bias_row = a.bias;
             if (a.bias && a.bias_group > 0 && row_ok) bias_row = a.bias + (size_t)(row / a.bias_group) * a.bias_ld;
-            const int row0 = m0 + quad * 32;
-            const bool vec_base = row0 + 32 <= a.M && (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0;
-            const bool vec_res = RES && (a.ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0 &&
-                                 (!a.res_scale || (reinterpret_cast<uintptr_t>(a.res_scale) & 15) == 0);
             // the accumulator loads of chunk c+1 are in flight while chunk c goes through its bias / activation / stores
             uint32_t r[16], rc[16];
             if (half * 16 < tile_bn) tmem_ld16x2_issue(acc_main + (uint32_t)(half * 16), acc_corr + (uint32_t)(half * 16), r, rc);
@@ -715,7 +765,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     const int r8 = lane >> 2, c4 = (lane & 3) * 4;
                     float4* my_row4 = reinterpret_cast<float4*>(stg + lane * 20);
                     if (RES) {
-                        if (vec && vec_res) {
+                        if (vec && res_pf) {
+                            asm volatile("cp.async.wait_group 0;" ::: "memory");
+                            __syncwarp();
+                            const unsigned char* rb = reinterpret_cast<const unsigned char*>(stg + pb * 512) + lane * 64;
+                            const int sw = (lane >> 1) & 3;
+    #pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 rv = *reinterpret_cast<const float4*>(rb + ((q ^ sw) << 4));
+                                if (a.res_scale) {
+                                    const float4 rs = *reinterpret_cast<const float4*>(a.res_scale + col + 4 * q);
+                                    v[4 * q] = fmaf(rs.x, rv.x, v[4 * q]); v[4 * q + 1] = fmaf(rs.y, rv.y, v[4 * q + 1]);
+                                    v[4 * q + 2] = fmaf(rs.z, rv.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(rs.w, rv.w, v[4 * q + 3]);
+                                } else {
+                                    v[4 * q] += rv.x; v[4 * q + 1] += rv.y; v[4 * q + 2] += rv.z; v[4 * q + 3] += rv.w;
+                                }
+                            }
+                            res_prefetch(c0 + 32, pb ^ 1);   // the other tile: its last TMA store was waited for at the top of this chunk
+                        } else if (vec && vec_res) {
                             const float* rp = a.res + (size_t)(row0 + r8) * a.ldres + col + c4;
                             float4 rx4[4];
     #pragma unroll
@@ -767,7 +834,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         // The chunk as a 32-row x 64-byte tile in the 64B-swizzle layout (16-byte chunk q of row r at q ^ ((r >> 1) & 3):
                         // every thread writes its own row conflict free), handed to the TMA unit by one lane: no transposed
                         // shared-memory reads, no per-thread global stores or address arithmetic (UTMASTG).
-                        unsigned char* sb = reinterpret_cast<unsigned char*>(stg) + lane * 64;
+                        float* stile = stg + (res_pf ? pb * 512 : 0);
+                        unsigned char* sb = reinterpret_cast<unsigned char*>(stile) + lane * 64;
                         const int sw = (lane >> 1) & 3;
     #pragma unroll
                         for (int q = 0; q < 4; ++q)
@@ -775,10 +843,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&mapC, stg, col, row0);
+                            tma_store_2d(&mapC, stile, col, row0);
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                         tma_pending = true;
+                        pb ^= 1;
                         continue;
                     }
     #pragma unroll
@@ -892,13 +961,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     const int r8 = lane >> 2, c2 = (lane & 3) * 2;
                     float* gx = a.x + (size_t)(row0 + r8) * a.ldx + a.col0 + (col >> 1) + c2;
                     float2 lx[4];
-    #pragma unroll
-                    for (int i = 0; i < 4; ++i) lx[i] = *reinterpret_cast<const float2*>(gx + (size_t)(8 * i) * a.ldx);
-    #pragma unroll
-                    for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(stg + (r8 + 8 * i) * 20 + c2) = lx[i];
-                    __syncwarp();
                     float4* my4 = reinterpret_cast<float4*>(stg + lane * 20);
-                    const float4 xa = my4[0], xb = my4[1];
+                    float4 xa, xb;
+                    if (cpl_pf) {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        __syncwarp();
+                        const float4* pf4 = reinterpret_cast<const float4*>(stg + 640 + lane * 12);
+                        xa = pf4[0]; xb = pf4[1];
+                        __syncwarp();
+                        cpl_prefetch(c0 + 32);
+                    } else {
+    #pragma unroll
+                        for (int i = 0; i < 4; ++i) lx[i] = *reinterpret_cast<const float2*>(gx + (size_t)(8 * i) * a.ldx);
+    #pragma unroll
+                        for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(stg + (r8 + 8 * i) * 20 + c2) = lx[i];
+                        __syncwarp();
+                        xa = my4[0]; xb = my4[1];
+                    }
                     float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
     #pragma unroll
                     for (int q = 0; q < 8; ++q) {

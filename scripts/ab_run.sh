@@ -1,3 +1,6 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; python -c "import json; d=json.load(open('gpurun_out/r02_bench_final.json')); print('bench', d['value'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'], d['clocks']['sm_mhz'], {k:(v['ms'],v['tflops']) for k,v in d['kernel_classes'].items()}); print(d['sweep_one_gpu']); print(d['per_config'])"
+python -m pytest tests/test_gpu_parity.py tests/test_transforms_gpu.py -m gpu -x -q 2>&1 | tail -2
+for i in 1 2; do
+for v in flowcompare_b200/libflowcompare_b200.so flowcompare_b200/libfc_np.so flowcompare_b200/libfc_np6.so; do
+FLOWCOMPARE_B200_LIB=$PWD/$v python bench.py --no-extras > gpurun_out/ab.json 2>/dev/null; python -c "import json; d=json.load(open('gpurun_out/ab.json')); print('$v', d['value'], d['e2e']['value'], d['roofline']['achieved'], d['clocks']['sm_mhz'], {k:(v['ms'],v['tflops']) for k,v in d['kernel_classes'].items()})"
+done; done
