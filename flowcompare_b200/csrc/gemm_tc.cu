@@ -57,6 +57,15 @@ constexpr int TC_STAGES = 5;                   // shared-memory stages: a load i
 #ifndef TC_BN_CAP
 #define TC_BN_CAP 96                           // widest tile (accumulator width); 80 leaves room for 6 A stages (measured slower)
 #endif
+#ifndef TC_HINT_EPI
+#define TC_HINT_EPI 0                          // suspend-time hints (ns) of the epilogue's accumulator wait / the converters' waits
+#endif
+#ifndef TC_HINT_CONV
+#define TC_HINT_CONV 0
+#endif
+#ifndef TC_EARLY_ACC_FREE
+#define TC_EARLY_ACC_FREE 0                    // 1: accumulator buffer released after a warp's last tcgen05.ld of the tile (measured: no gain, 516.7 vs 517.6 pairs/s)
+#endif
 #ifndef TC_RES_PREFETCH
 #define TC_RES_PREFETCH 1                      // 3xFP16 mode: the residual of an epilogue chunk arrives by cp.async one chunk ahead (the first
 #endif                                         // chunk's before the accumulator wait) in a second per-warp staging tile; costs one pipeline stage
@@ -193,10 +202,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 4];
     __shared__ __align__(8) uint64_t turn_bar;   // ping-pong issuers: phase g completes when k-block g has been issued
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float ldj_sm[TC_BM];
-    __shared__ __align__(16) float bias_sm2[2][96];   // the tile's bias (and LayerNorm-q column sums), by accumulator buffer
-    __shared__ __align__(16) float csum_sm2[2][96];
-    __shared__ int bias_in_smem2[2];
+    __shared__ float ldj_sm[2][TC_BM];        // by tile parity: the only barrier between the two halves is the one inside a tile
+    // the bias (and LayerNorm-q column sums) of the columns each epilogue warp handles in the current tile: chunk i of the warp
+    // (columns half*16 + 32*i ..+15 of the tile) at [16*i ..+15].  Per warp, so the epilogue needs no CTA-wide barrier.
+    __shared__ __align__(16) float bias_w[8][48];
+    __shared__ __align__(16) float csum_w[8][48];
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024 B alignment
@@ -492,7 +502,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                             pending = -1;
                         }
                         TC_T(cf0);
-                        mbar_wait(&full[s], sph, 400 + t);
+                        mbar_wait_hint(&full[s], sph, 400 + t, TC_HINT_CONV);
                         TC_T(cf1);
                         TC_ACC(c_full, cf0, cf1);
                         const float4* rowp = reinterpret_cast<const float4*>(a_raw(s) + row_in_tile * 128);
@@ -513,7 +523,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         }
                         if (!TC_NO_AFREE) warp_arrive(&a_free[s]);
                         TC_T(ct0);
-                        mbar_wait(&tfree[ks], kph ^ 1, 450 + t);
+                        mbar_wait_hint(&tfree[ks], kph ^ 1, 450 + t, TC_HINT_CONV);
                         TC_T(ct1);
                         TC_ACC(c_tfree, ct0, ct1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -536,7 +546,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     pending = -1;
                 }
                 TC_T(cf0);
-                mbar_wait(&full[s], sph, 400 + t);
+                mbar_wait_hint(&full[s], sph, 400 + t, TC_HINT_CONV);
                 TC_T(cf1);
                 TC_ACC(c_full, cf0, cf1);
                 const float4* rowp = reinterpret_cast<const float4*>(a_raw(s) + row_in_tile * 128);
@@ -582,7 +592,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     }
                     if (h == 0 || TC_CONV_WARPS_N == 8) {   // once per k-block: the MMAs that read this TMEM stage have retired
                         TC_T(ct0);
-                        mbar_wait(&tfree[ks], kph ^ 1, 450 + t);
+                        mbar_wait_hint(&tfree[ks], kph ^ 1, 450 + t, TC_HINT_CONV);
                         TC_T(ct1);
                         TC_ACC(c_tfree, ct0, ct1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -629,21 +639,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             const int n_tile = L % n_tiles, m0 = (L / n_tiles) * TC_BM;
             const int tile_n0 = tile_n0_of(n_tile), tile_bn = tile_bn_of(n_tile);
             const int buf = it & 1;
-            float* bias_sm = bias_sm2[buf];
-            float* csum_sm = csum_sm2[buf];
+            float* bias_sm = bias_w[ew];
+            float* csum_sm = csum_w[ew];
+            // while the tensor core is still on this tile: fetch its bias row (a cold L2 miss per 16-column chunk
+            // otherwise -- measured ~600 cycles each) into shared memory
+            const int last_row = min(m0 + TC_BM, a.M) - 1;
+            const bool one_group = a.bias_group <= 0 || (m0 / a.bias_group) == (last_row / a.bias_group);
+            const bool bias_smem = one_group && m0 < a.M;
             {
-                // while the tensor core is still on this tile: fetch its bias row (a cold L2 miss per 16-column chunk
-                // otherwise -- measured ~600 cycles each) into shared memory
-                const int last_row = min(m0 + TC_BM, a.M) - 1;
-                const bool one_group = a.bias_group <= 0 || (m0 / a.bias_group) == (last_row / a.bias_group);
                 const float* brow = a.bias;
                 if (a.bias && a.bias_group > 0) brow = a.bias + (size_t)(m0 / a.bias_group) * a.bias_ld;
-                for (int i = etid; i < tile_bn; i += 256) {
-                    const int col = tile_n0 + i;
-                    bias_sm[i] = (brow && one_group && col < a.N) ? brow[col] : 0.f;
-                    csum_sm[i] = (EPI == FC_EPI_LNQ && col < a.N) ? a.csum[col] : 0.f;
+                __syncwarp();            // every lane is done with the previous tile's values
+                for (int i = lane; i < 48; i += 32) {
+                    const int ct = half * 16 + 32 * (i >> 4) + (i & 15);     // column within the tile
+                    const int col = tile_n0 + ct;
+                    const bool ok = ct < tile_bn && col < a.N;
+                    bias_sm[i] = (brow && one_group && ok) ? brow[col] : 0.f;
+                    csum_sm[i] = (EPI == FC_EPI_LNQ && ok) ? a.csum[col] : 0.f;
                 }
-                if (etid == 0) bias_in_smem2[buf] = (one_group && m0 < a.M) ? 1 : 0;
             }
             // The residual of a chunk does not depend on the accumulator: its (L2-latency) loads are issued one chunk ahead,
             // and the first chunk's before the wait for the tensor core, so they overlap the mainloop / the previous chunk.
@@ -697,12 +710,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             float mu = 0.f, rstd = 0.f;
             if (EPI == FC_EPI_LNQ && m0 + row_in_tile < a.M) { mu = a.row_mu[m0 + row_in_tile]; rstd = a.row_rstd[m0 + row_in_tile]; }
             TC_T(ea0);
-            mbar_wait(&acc_full[buf], (it >> 1) & 1, 500);
+            mbar_wait_hint(&acc_full[buf], (it >> 1) & 1, 500, TC_HINT_EPI);
             TC_T(ea1);
             TC_ACC(e_wait, ea0, ea1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            asm volatile("bar.sync 2, 256;" ::: "memory");    // bias_sm / csum_sm visible to all 8 epilogue warps
-            const bool bias_smem = bias_in_smem2[buf] != 0;
+            __syncwarp();                                      // bias_sm / csum_sm visible to the whole warp
             const uint32_t acc_main = tmem + lane_addr + TC_COL_ACC * buf, acc_corr = acc_main + TC_COL_CORR;
             const int row = m0 + row_in_tile;
             const bool row_ok = row < a.M;
@@ -712,6 +724,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             if (a.bias && a.bias_group > 0 && row_ok) bias_row = a.bias + (size_t)(row / a.bias_group) * a.bias_ld;
             // the accumulator loads of chunk c+1 are in flight while chunk c goes through its bias / activation / stores
             uint32_t r[16], rc[16];
+            bool acc_released = false;
             if (half * 16 < tile_bn) tmem_ld16x2_issue(acc_main + (uint32_t)(half * 16), acc_corr + (uint32_t)(half * 16), r, rc);
             for (int c0 = half * 16; c0 < tile_bn; c0 += 32) {
                 float v[16];
@@ -725,18 +738,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 for (int j = 0; j < 16; ++j)
                     v[j] = F16 ? fmaf(__uint_as_float(rc[j]), 4.8828125e-4f, __uint_as_float(r[j])) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
                 if (c0 + 32 < tile_bn) tmem_ld16x2_issue(acc_main + (uint32_t)(c0 + 32), acc_corr + (uint32_t)(c0 + 32), r, rc);
+                else if (TC_EARLY_ACC_FREE) {
+                    // that was this warp's last read of the accumulator: hand the buffer back to the MMA issuer now, not after the
+                    // chunk's arithmetic and stores
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    warp_arrive(&acc_free[buf]);
+                    acc_released = true;
+                }
                 const int col = n0 + c0;
                 if (col >= a.N) continue;                     // warp-uniform
                 if (TC_KO_EPI) { if (v[0] == 123.456f) a.C[0] = v[1]; continue; }
                 if (EPI == FC_EPI_LNQ) {
     #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (col + j < a.N) v[j] = rstd * (v[j] - mu * csum_sm[c0 + j]) + bias_sm[c0 + j];
+                        if (col + j < a.N) v[j] = rstd * (v[j] - mu * csum_sm[(c0 >> 5) * 16 + j]) + bias_sm[(c0 >> 5) * 16 + j];
                 } else if (bias_row && bias_smem) {
                     // four 16-byte broadcast loads (bias_sm is 16-byte aligned and c0 a multiple of 16); zero beyond N
     #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_sm + c0 + 4 * q);
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_sm + (c0 >> 5) * 16 + 4 * q);
                         v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
                     }
                 } else if (bias_row) {
@@ -1058,17 +1078,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             }
             if (EPI == FC_EPI_COUPLING || EPI == FC_EPI_AUGMENT) {
                 // the two threads that share a row combine their partial log-dets in a fixed order (deterministic)
-                if (half == 1) ldj_sm[row_in_tile] = ldj;
+                if (half == 1) ldj_sm[buf][row_in_tile] = ldj;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (half == 0 && row_ok) {
-                    const float tot = ldj + ldj_sm[row_in_tile];
+                    const float tot = ldj + ldj_sm[buf][row_in_tile];
                     float* pp = a.part + (size_t)n_tile * a.M + row;
                     if (EPI == FC_EPI_COUPLING) *pp += tot; else *pp = tot;
                 }
             }
             // this thread's TMEM reads of the tile are complete (every tcgen05.ld above is followed by its wait)
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            warp_arrive(&acc_free[buf]);
+            if (!acc_released) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                warp_arrive(&acc_free[buf]);
+            }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // this warp's TMA stores have landed
 #if TC_PHASE_TIMERS

@@ -40,6 +40,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     }
     mbar_timeout(tag, parity);
 }
+// same, with a suspend-time hint (ns): the hardware may park the waiting thread for up to that long per try instead of
+// returning after its short default limit, so long waits do not fill issue slots with the spin loop
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, int tag, uint32_t hint_ns) {
+    if (hint_ns == 0) { mbar_wait(bar, parity, tag); return; }
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+        if (done) return;
+    }
+    mbar_timeout(tag, parity);
+}
 // non-blocking probe of a phase: lets an issuing warp check the NEXT stage before it blocks on the tensor queue
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     uint32_t done;
