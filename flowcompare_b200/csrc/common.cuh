@@ -50,6 +50,25 @@ __device__ __forceinline__ float fc_gelu_erf_fast(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(r, u, -1.0f)));
     return fmaf(-fabsf(x), e, fmaxf(x, 0.f));
 }
+// Two values at a time with Blackwell's packed fp32 instructions (FFMA2: one issue slot for two fmas).  Every component goes
+// through the same operation sequence as fc_gelu_erf_fast, so the results are bit-identical to it.
+__device__ __forceinline__ float2 fc_gelu_erf_fast2(float2 x) {
+    const float2 na = make_float2(-fabsf(x.x), -fabsf(x.y));
+    const float2 u = make_float2(fminf(fabsf(x.x), 6.6f), fminf(fabsf(x.y), 6.6f));
+    float2 r = make_float2(-2.107304487601092e-06f, -2.107304487601092e-06f);
+    r = __ffma2_rn(r, u, make_float2(3.082007880290574e-05f, 3.082007880290574e-05f));
+    r = __ffma2_rn(r, u, make_float2(-0.00014644312103818846f, -0.00014644312103818846f));
+    r = __ffma2_rn(r, u, make_float2(-0.0002300897957034123f, -0.0002300897957034123f));
+    r = __ffma2_rn(r, u, make_float2(0.007180221614911477f, 0.007180221614911477f));
+    r = __ffma2_rn(r, u, make_float2(-0.052572273431757154f, -0.052572273431757154f));
+    r = __ffma2_rn(r, u, make_float2(-0.4591854841684466f, -0.4591854841684466f));
+    r = __ffma2_rn(r, u, make_float2(-1.1511073739593443f, -1.1511073739593443f));
+    const float2 t = __ffma2_rn(r, u, make_float2(-1.0f, -1.0f));
+    float2 e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+    return __ffma2_rn(na, e, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
 __device__ __forceinline__ float fc_leaky_relu02(float x) { return x > 0.f ? x : 0.2f * x; }
 
 __device__ __forceinline__ float fc_warp_sum(float v) {

@@ -518,7 +518,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                                 float h0, h1;
                                 unpack_f16x2(hp, h0, h1);
                                 hl[base + (e >> 1)] = hp;
-                                hl[base + 8 + (e >> 1)] = pack_f16x2((xv[e] - h0) * 2048.0f, (xv[e + 1] - h1) * 2048.0f);
+                                const float2 d2 = __fmul2_rn(__fadd2_rn(make_float2(xv[e], xv[e + 1]), make_float2(-h0, -h1)), make_float2(2048.0f, 2048.0f));
+                                hl[base + 8 + (e >> 1)] = pack_f16x2(d2.x, d2.y);
                             }
                         }
                         if (!TC_NO_AFREE) warp_arrive(&a_free[s]);
@@ -571,7 +572,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                                 float h0, h1;
                                 unpack_f16x2(hp, h0, h1);
                                 hl[2 * jj + (e >> 1)] = hp;
-                                hl[TS_COLS / 2 + 2 * jj + (e >> 1)] = pack_f16x2((xv[e] - h0) * 2048.0f, (xv[e + 1] - h1) * 2048.0f);
+                                const float2 d2 = __fmul2_rn(__fadd2_rn(make_float2(xv[e], xv[e + 1]), make_float2(-h0, -h1)), make_float2(2048.0f, 2048.0f));
+                                hl[TS_COLS / 2 + 2 * jj + (e >> 1)] = pack_f16x2(d2.x, d2.y);
                             }
                         } else {
 #pragma unroll
@@ -735,8 +737,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 __syncwarp();
                 tmem_ld16x2_wait(r, rc);
     #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    v[j] = F16 ? fmaf(__uint_as_float(rc[j]), 4.8828125e-4f, __uint_as_float(r[j])) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+                for (int j = 0; j < 16; j += 2) {
+                    const float2 m2 = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                    const float2 c2 = make_float2(__uint_as_float(rc[j]), __uint_as_float(rc[j + 1]));
+                    const float2 o2 = F16 ? __ffma2_rn(c2, make_float2(4.8828125e-4f, 4.8828125e-4f), m2) : __fadd2_rn(m2, c2);
+                    v[j] = o2.x; v[j + 1] = o2.y;
+                }
                 if (c0 + 32 < tile_bn) tmem_ld16x2_issue(acc_main + (uint32_t)(c0 + 32), acc_corr + (uint32_t)(c0 + 32), r, rc);
                 else if (TC_EARLY_ACC_FREE) {
                     // that was this warp's last read of the accumulator: hand the buffer back to the MMA issuer now, not after the
@@ -757,7 +763,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bias_sm + (c0 >> 5) * 16 + 4 * q);
-                        v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+                        const float2 s0 = __fadd2_rn(make_float2(v[4 * q], v[4 * q + 1]), make_float2(b4.x, b4.y));
+                        const float2 s1 = __fadd2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(b4.z, b4.w));
+                        v[4 * q] = s0.x; v[4 * q + 1] = s0.y; v[4 * q + 2] = s1.x; v[4 * q + 3] = s1.y;
                     }
                 } else if (bias_row) {
                     if (col + 15 < a.N && ((reinterpret_cast<uintptr_t>(bias_row + col) & 15) == 0)) {
@@ -798,7 +806,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                                     v[4 * q] = fmaf(rs.x, rv.x, v[4 * q]); v[4 * q + 1] = fmaf(rs.y, rv.y, v[4 * q + 1]);
                                     v[4 * q + 2] = fmaf(rs.z, rv.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(rs.w, rv.w, v[4 * q + 3]);
                                 } else {
-                                    v[4 * q] += rv.x; v[4 * q + 1] += rv.y; v[4 * q + 2] += rv.z; v[4 * q + 3] += rv.w;
+                                    const float2 s0 = __fadd2_rn(make_float2(v[4 * q], v[4 * q + 1]), make_float2(rv.x, rv.y));
+                                    const float2 s1 = __fadd2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(rv.z, rv.w));
+                                    v[4 * q] = s0.x; v[4 * q + 1] = s0.y; v[4 * q + 2] = s1.x; v[4 * q + 3] = s1.y;
                                 }
                             }
                             res_prefetch(c0 + 32, pb ^ 1);   // the other tile: its last TMA store was waited for at the top of this chunk
@@ -842,7 +852,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     }
                     if (ACT == FC_ACT_GELU) {
     #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fc_gelu_erf_fast(v[j]);
+                        for (int j = 0; j < 16; j += 2) {
+                            const float2 g2 = fc_gelu_erf_fast2(make_float2(v[j], v[j + 1]));
+                            v[j] = g2.x; v[j + 1] = g2.y;
+                        }
                     } else if (ACT == FC_ACT_LRELU) {
     #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = fc_leaky_relu02(v[j]);
