@@ -19,13 +19,13 @@ void fc_set_last_cuda_error(int code, const char* file, int line) {
 void fc_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 namespace {
-struct ProfRec { int cls; double flops, bytes; cudaEvent_t a, b; };
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t a, b; long long tag; };
 std::atomic<bool> g_prof_on{false};
 std::vector<ProfRec> g_prof;
 }  // namespace
 bool fc_prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
-void fc_prof_open(int cls, double flops, double bytes, cudaStream_t s) {
-    ProfRec r{cls, flops, bytes, nullptr, nullptr};
+void fc_prof_open(int cls, double flops, double bytes, cudaStream_t s, long long tag) {
+    ProfRec r{cls, flops, bytes, nullptr, nullptr, tag};
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     cudaEventRecord(r.a, s);
     g_prof.push_back(r);
@@ -43,14 +43,19 @@ extern "C" int fc_profile_end(double* ms, double* flops, double* bytes, int64_t*
     FC_REQUIRE(ms && flops && bytes && launches && n_classes >= FC_N_CLASSES);
     for (int i = 0; i < n_classes; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
     FC_CUDA_OK(cudaDeviceSynchronize());
+    // FC_PROFILE_DUMP=<path>: one line per instrumented launch (class, shape tag, flops, ms) for per-shape breakdowns
+    const char* dump = getenv("FC_PROFILE_DUMP");
+    FILE* df = dump && dump[0] ? fopen(dump, "w") : nullptr;
     for (auto& r : g_prof) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            if (df) fprintf(df, "%d %lld %.0f %.6f\n", r.cls, r.tag, r.flops, (double)t);
             ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1;
         }
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
     g_prof.clear();
+    if (df) fclose(df);
     return FC_OK;
 }
 

@@ -66,6 +66,9 @@ constexpr int TC_STAGES = 5;                   // shared-memory stages: a load i
 #ifndef TC_EARLY_ACC_FREE
 #define TC_EARLY_ACC_FREE 0                    // 1: accumulator buffer released after a warp's last tcgen05.ld of the tile (measured: no gain, 516.7 vs 517.6 pairs/s)
 #endif
+#ifndef TC_CONV_FLAGS
+#define TC_CONV_FLAGS 0                        // 3xFP16 parity converters publish a k-block through shared-memory sequence flags (st.release /
+#endif                                         // ld.acquire, ~30 cycles a poll) instead of the conv[] mbarrier (~100 cycles per wait even when complete)
 #ifndef TC_RES_PREFETCH
 #define TC_RES_PREFETCH 1                      // 3xFP16 mode: the residual of an epilogue chunk arrives by cp.async one chunk ahead (the first
 #endif                                         // chunk's before the accumulator wait) in a second per-warp staging tile; costs one pipeline stage
@@ -202,6 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 2 * TC_TSTAGES + 4];
     __shared__ __align__(8) uint64_t turn_bar;   // ping-pong issuers: phase g completes when k-block g has been issued
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) uint32_t conv_flag[8][4];   // [TMEM A stage][converter warp of the group]: use count of the stage
     __shared__ float ldj_sm[2][TC_BM];        // by tile parity: the only barrier between the two halves is the one inside a tile
     // the bias (and LayerNorm-q column sums) of the columns each epilogue warp handles in the current tile: chunk i of the warp
     // (columns half*16 + 32*i ..+15 of the tile) at [16*i ..+15].  Per warp, so the epilogue needs no CTA-wide barrier.
@@ -240,6 +244,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     auto tile_n0_of = [&](int nt) { return 16 * (nt * n_base + min(nt, n_rem)); };
     auto tile_bn_of = [&](int nt) { return 16 * (n_base + (nt < n_rem ? 1 : 0)); };
 
+    constexpr bool CFLAGS = PARITY && TC_CONV_FLAGS && !TC_SPLIT_ISSUE && !TC_PINGPONG && TC_ISSUE_KBLOCK == 1;
+    if (threadIdx.x < 32) conv_flag[threadIdx.x >> 2][threadIdx.x & 3] = 0u;
     if (threadIdx.x == 0) {
         constexpr int PER_WARP = TC_WARP_ARRIVE ? 1 : 32;   // arrivals a warp contributes per event
         constexpr int CONV_GROUPS = PARITY ? 2 : 1;         // converter groups that take turns on k-blocks
@@ -386,6 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
 #endif
         } else {
         bool conv_seen = false;   // the next k-block's barrier was seen complete by the probe
+        uint32_t kuse = 1;        // use count of the current TMEM A stage (flag value the converters publish)
         int s = 0;                // shared-memory stage of the next k-block
         int ks = 0; uint32_t kph = 0;   // tensor-memory A stage (one per k-block) of the next k-block and its barrier phase
         TC_T(m_t0);
@@ -404,12 +411,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             for (int t = 0; t < T;) {
                 const int nb = min(KBI, T - t);
                 TC_T(mc0);
+                if constexpr (CFLAGS) {
+                    // the four converter warps of the k-block's group have each stored the stage's use count (release) after
+                    // their tcgen05.st completed; one 16-byte acquire load reads all four
+                    const uint32_t fa = smem_u32(&conv_flag[ks][0]);
+                    uint32_t f0, f1, f2, f3, spin = 0;
+                    for (;;) {
+                        asm volatile("ld.acquire.cta.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f0), "=r"(f1), "=r"(f2), "=r"(f3) : "r"(fa) : "memory");
+                        if (min(min(f0, f1), min(f2, f3)) >= kuse) break;
+                        if (++spin > (1u << 24)) mbar_timeout(300 + t, kuse);
+                    }
+                } else {
                 if (!conv_seen) mbar_wait(&conv[ks], kph, 300 + t);
                 if (nb > 1) { const int k2 = ks + 1 == TC_TSTAGES / 2 ? 0 : ks + 1; mbar_wait(&conv[k2], k2 ? kph : kph ^ 1, 350 + t); }
+                }
                 TC_T(mc1);
                 TC_ACC(m_conv, mc0, mc1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                {   // probe the NEXT group's first k-block now: a wait after the issue is dead time for the tensor pipe
+                if constexpr (!CFLAGS) {   // probe the NEXT group's first k-block now: a wait after the issue is dead time for the tensor pipe
                     int kn = ks + nb; uint32_t pn = kph;
                     if (kn >= TC_TSTAGES / 2) { kn -= TC_TSTAGES / 2; pn ^= 1; }
                     conv_seen = TC_PROBE ? mbar_test(&conv[kn], pn) : false;
@@ -458,7 +477,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                 __syncwarp();
                 t += nb;
                 s += nb; if (s >= TC_STAGES) s -= TC_STAGES;
-                ks += nb; if (ks >= TC_TSTAGES / 2) { ks -= TC_TSTAGES / 2; kph ^= 1; }
+                ks += nb; if (ks >= TC_TSTAGES / 2) { ks -= TC_TSTAGES / 2; kph ^= 1; ++kuse; }
             }
             if (elect_one()) umma_commit(&acc_full[buf]);        // accumulators of this tile complete
             __syncwarp();
@@ -491,16 +510,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             // chain per k-block (knock-out builds: the pipeline ran at that pace with all the work removed).  A thread converts
             // its whole 32-float row of the k-block and writes it with one 32-column tcgen05.st.
             const int grp = (warp - TC_CONV_WARP0) >> 2;
-            uint32_t g = 0;
+            uint32_t g = 0, cuse = 1, pend_use = 0;
+            auto publish = [&]() {
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if constexpr (CFLAGS) {
+                    __syncwarp();
+                    if (lane == 0)
+                        asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"(smem_u32(&conv_flag[pending][(warp - TC_CONV_WARP0) & 3])), "r"(pend_use) : "memory");
+                } else {
+                    warp_arrive(&conv[pending]);
+                }
+                pending = -1;
+            };
             for (int L = blockIdx.x; L < total_tiles; L += gridDim.x) {
                 for (int t = 0; t < T; ++t, ++g) {
                     if ((int)(g & 1) == grp) {
-                        if (pending >= 0) {
-                            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                            warp_arrive(&conv[pending]);
-                            pending = -1;
-                        }
+                        if (pending >= 0) publish();
                         TC_T(cf0);
                         mbar_wait_hint(&full[s], sph, 400 + t, TC_HINT_CONV);
                         TC_T(cf1);
@@ -531,12 +557,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                         const uint32_t dst = tmem + lane_addr + TC_COL_A + TS_COLS * (2 * ks);
                         if constexpr (TC_KO_CONV) { (void)hl; (void)dst; }
                         else tmem_st32(dst, hl);
-                        pending = ks;
+                        pending = ks; pend_use = cuse;
                     }
                     s = s + 1 == TC_STAGES ? 0 : s + 1; if (s == 0) sph ^= 1;
-                    ks = ks + 1 == TC_TSTAGES / 2 ? 0 : ks + 1; if (ks == 0) kph ^= 1;
+                    ks = ks + 1 == TC_TSTAGES / 2 ? 0 : ks + 1; if (ks == 0) { kph ^= 1; ++cuse; }
                 }
             }
+            if (pending >= 0) publish();
         } else
         for (int L = blockIdx.x; L < total_tiles; L += gridDim.x) {
             for (int t = 0; t < T; ++t) {
@@ -673,14 +700,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             int pb = 0;
             auto res_prefetch = [&](int c0n, int which) {
                 const int coln = tile_n0 + c0n;
-                if (c0n < tile_bn && coln + 16 <= a.N) {
+                // a chunk that straddles N (N a multiple of 4) is prefetched too: its 16-byte pieces beyond N are zero-filled
+                // (src-size 0, nothing is read) and the TMA store clips them
+                if (c0n < tile_bn && coln < a.N && (coln + 16 <= a.N || (a.N & 3) == 0)) {
                     const float* rp = a.res + (size_t)(row0 + (lane >> 2)) * a.ldres + coln + (lane & 3) * 4;
                     const uint32_t dst0 = smem_u32(stg + which * 512);
+                    const uint32_t nbytes = coln + (lane & 3) * 4 < a.N ? 16u : 0u;
+                    if (nbytes == 0u) rp = a.res;     // keep the (unused) address in bounds
     #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rr = (lane >> 2) + 8 * i;
                         const uint32_t dst = dst0 + (uint32_t)(rr * 64 + ((((lane & 3) ^ ((rr >> 1) & 3))) << 4));
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(rp + (size_t)(8 * i) * a.ldres) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(rp + (nbytes ? (size_t)(8 * i) * a.ldres : (size_t)0)), "r"(nbytes) : "memory");
                     }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
@@ -790,10 +821,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     // per-element predicates or address arithmetic -- the scalar form below cost ~19 instructions per
                     // element, more than the GELU
                     const bool vec = vec_base && col + 16 <= a.N;
+                    // TMA-store launches also take a chunk that straddles N through the fast path (the store clips it)
+                    const bool vect = vec || (vec_base && p.tma_store && (a.N & 3) == 0 && (!RES || res_pf));
                     const int r8 = lane >> 2, c4 = (lane & 3) * 4;
                     float4* my_row4 = reinterpret_cast<float4*>(stg + lane * 20);
                     if (RES) {
-                        if (vec && res_pf) {
+                        if (vect && res_pf) {
                             asm volatile("cp.async.wait_group 0;" ::: "memory");
                             __syncwarp();
                             const unsigned char* rb = reinterpret_cast<const unsigned char*>(stg + pb * 512) + lane * 64;
@@ -802,7 +835,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                             for (int q = 0; q < 4; ++q) {
                                 const float4 rv = *reinterpret_cast<const float4*>(rb + ((q ^ sw) << 4));
                                 if (a.res_scale) {
-                                    const float4 rs = *reinterpret_cast<const float4*>(a.res_scale + col + 4 * q);
+                                    const float4 rs = col + 4 * q < a.N ? *reinterpret_cast<const float4*>(a.res_scale + col + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
                                     v[4 * q] = fmaf(rs.x, rv.x, v[4 * q]); v[4 * q + 1] = fmaf(rs.y, rv.y, v[4 * q + 1]);
                                     v[4 * q + 2] = fmaf(rs.z, rv.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(rs.w, rv.w, v[4 * q + 3]);
                                 } else {
@@ -863,7 +896,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
-                    if (vec && p.tma_store) {
+                    if (vect && p.tma_store) {
                         // The chunk as a 32-row x 64-byte tile in the 64B-swizzle layout (16-byte chunk q of row r at q ^ ((r >> 1) & 3):
                         // every thread writes its own row conflict free), handed to the TMA unit by one lane: no transposed
                         // shared-memory reads, no per-thread global stores or address arithmetic (UTMASTG).
@@ -1091,6 +1124,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             }
             if (EPI == FC_EPI_COUPLING || EPI == FC_EPI_AUGMENT) {
                 // the two threads that share a row combine their partial log-dets in a fixed order (deterministic)
+                // (measured: reading the old partial before the accumulator wait, a per-quadrant barrier and releasing the
+                // accumulator before this tail made the coupling launches 7 % SLOWER, 300 vs 281 us)
                 if (half == 1) ldj_sm[buf][row_in_tile] = ldj;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (half == 0 && row_ok) {
@@ -1254,7 +1289,9 @@ int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     FC_REQUIRE(nsm > 0);
     const int total_tiles = p.n_tiles * p.m_tiles;
     FcProfScope prof(FC_CLS_GEMM_TC, 2.0 * a.M * a.N * (a.K1 + a.K2),
-                     4.0 * ((double)a.M * (a.K1 + a.K2) + (double)a.N * (a.K1 + a.K2) + (double)a.M * a.N), stream);
+                     4.0 * ((double)a.M * (a.K1 + a.K2) + (double)a.N * (a.K1 + a.K2) + (double)a.M * a.N), stream,
+                     (long long)(a.K1 + a.K2) | ((long long)a.N << 16) | ((long long)a.epi << 32) | ((long long)a.act << 36) |
+                         ((long long)(a.res != nullptr) << 40));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(total_tiles < nsm ? total_tiles : nsm);      // persistent: one CTA per SM
     cfg.blockDim = dim3(TC_THREADS);

@@ -9,7 +9,7 @@ from flowcompare_b200 import lib as fclib, packing
 
 lib = fclib.load()
 lib.fc_debug_tc_phases.argtypes = [ctypes.c_void_p]
-shapes = [(32768, 512, 512, 1), (32768, 512, 512, 0), (32768, 256, 256, 1), (32768, 256, 150, 1), (32768, 64, 256, 0), (32768, 300, 300, 0)]
+shapes = [(65536, 512, 512, 1), (65536, 512, 512, 0), (65536, 256, 256, 1), (65536, 256, 256, 0), (65536, 256, 150, 1), (65536, 256, 150, 0), (65536, 300, 300, 0)]
 for (M, N, K, act) in shapes:
     g = torch.Generator().manual_seed(0)
     A = torch.randn(M, (K + 3) // 4 * 4, generator=g).cuda()
