@@ -540,7 +540,7 @@ def main():
         d = (lp_tc - lp_32).abs()
         precision_check = {"pairs": 2, "max_abs_diff_nats": float(d.max().item()), "median_abs_diff_nats": float(d.median().item()),
                            "mean_rel_diff": float(abs(lp_tc.mean().item() - lp_32.mean().item()) / abs(lp_32.mean().item())),
-                           "note": "tf32x3 (timed) vs exact-fp32 FFMA path, 115 layers; the reference's own fp32-vs-fp64 noise at "
+                           "note": precision + " (timed) vs exact-fp32 FFMA path, 115 layers; the reference's own fp32-vs-fp64 noise at "
                                    "this depth is 2e-3 max / 2.4e-4 mean nats (DESIGN.md section 2)"}
         eng32.close()
         del eng32
