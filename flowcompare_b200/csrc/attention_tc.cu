@@ -383,7 +383,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             const float mc = F16 ? fmaf(m_new, LOG2E, -10.0f) : m_new * LOG2E;
             float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < KS; ++j) { sv[j] = ex2_approx(fmaf(sv[j], LOG2E, -mc)); sum4[j & 3] += sv[j]; }
+            for (int j = 0; j < KS; j += 4) {
+                // packed fp32 (FFMA2 / FADD2): two scores per instruction, per component the same operations as the scalar form
+                const float2 t0 = __ffma2_rn(make_float2(sv[j], sv[j + 1]), make_float2(LOG2E, LOG2E), make_float2(-mc, -mc));
+                const float2 t1 = __ffma2_rn(make_float2(sv[j + 2], sv[j + 3]), make_float2(LOG2E, LOG2E), make_float2(-mc, -mc));
+                sv[j] = ex2_approx(t0.x); sv[j + 1] = ex2_approx(t0.y); sv[j + 2] = ex2_approx(t1.x); sv[j + 3] = ex2_approx(t1.y);
+                const float2 s01 = __fadd2_rn(make_float2(sum4[0], sum4[1]), make_float2(sv[j], sv[j + 1]));
+                const float2 s23 = __fadd2_rn(make_float2(sum4[2], sum4[3]), make_float2(sv[j + 2], sv[j + 3]));
+                sum4[0] = s01.x; sum4[1] = s01.y; sum4[2] = s23.x; sum4[3] = s23.y;
+            }
             l = fmaf(l, alpha, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
             m = m_new;
 
@@ -403,7 +411,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                     float h0, h1;
                     unpack_f16x2(hp, h0, h1);
                     hi[j] = hp;
-                    lo[j] = pack_f16x2(p0 - h0, p1 - h1);
+                    const float2 d2 = __fadd2_rn(make_float2(p0, p1), make_float2(-h0, -h1));
+                    lo[j] = pack_f16x2(d2.x, d2.y);
                 }
                 if constexpr (KS == 32) { tmem_st16(tmem + lane_addr + C_PHI + 64 * pb + (off >> 1), hi); tmem_st16(tmem + lane_addr + C_PLO + 64 * pb + (off >> 1), lo); }
                 else                    { tmem_st8(tmem + lane_addr + C_PHI + 64 * pb + (off >> 1), hi);  tmem_st8(tmem + lane_addr + C_PLO + 64 * pb + (off >> 1), lo); }
@@ -436,7 +445,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(&o_free[ob]);
 #pragma unroll
-                for (int j = 0; j < KS; ++j) o[j] = fmaf(o[j], alpha_prev, ov[j]);
+                for (int j = 0; j < KS; j += 2) {
+                    const float2 o2 = __ffma2_rn(make_float2(o[j], o[j + 1]), make_float2(alpha_prev, alpha_prev), make_float2(ov[j], ov[j + 1]));
+                    o[j] = o2.x; o[j + 1] = o2.y;
+                }
             }
             alpha_prev = alpha;
         }
