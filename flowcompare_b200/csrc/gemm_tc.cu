@@ -69,6 +69,9 @@ constexpr int TC_STAGES = 5;                   // shared-memory stages: a load i
 #ifndef TC_CONV_FLAGS
 #define TC_CONV_FLAGS 0                        // 3xFP16 parity converters publish a k-block through shared-memory sequence flags (st.release /
 #endif                                         // ld.acquire, ~30 cycles a poll) instead of the conv[] mbarrier (~100 cycles per wait even when complete)
+#ifndef TC_FUSE_WLO
+#define TC_FUSE_WLO 1                          // 3xFP16: Ahi.Whi and Ahi.Wlo as one MMA of N = 96 + tile_bn over the adjacent [Whi; Wlo] boxes
+#endif
 #ifndef TC_RES_PREFETCH
 #define TC_RES_PREFETCH 1                      // 3xFP16 mode: the residual of an epilogue chunk arrives by cp.async one chunk ahead (the first
 #endif                                         // chunk's before the accumulator wait) in a second per-warp staging tile; costs one pipeline stage
@@ -215,7 +218,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024 B alignment
     const int BN = p.BN;                    // widest tile of this launch: shared-memory layout and TMA box
-    const int w_bytes = BN * TC_BK * TcCfg<F16>::W_ELT;
+    const int w_box_bytes = BN * TC_BK * TcCfg<F16>::W_ELT;          // what one weight TMA box brings
+    // 3xFP16: the Wlo box always sits 96 rows behind the Whi box (rows BN..95 of the slot are never written: they only feed
+    // accumulator columns nobody reads), so that one MMA can run over [Whi; Wlo] whatever BN is (TC_FUSE_WLO)
+    const int w_bytes = (F16 && TC_FUSE_WLO) ? TC_BN_CAP * TC_BK * TcCfg<F16>::W_ELT : w_box_bytes;
     const int stage_bytes = TC_A_BYTES + 2 * w_bytes;
     auto a_raw = [&](int s) { return smem + s * stage_bytes; };
     auto w_hi = [&](int s) { return smem + s * stage_bytes + TC_A_BYTES; };
@@ -283,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                     const uint32_t ph = (g / TC_STAGES) & 1;
                     if (!TC_NO_AFREE) mbar_wait(&a_free[s], ph ^ 1, 100 + t);
                     mbar_wait(&w_free[s], ph ^ 1, 150 + t);
-                    mbar_expect_tx(&full[s], (uint32_t)((TC_KO_ATMA ? 0 : TC_A_BYTES) + (TC_KO_WTMA ? 0 : 2 * w_bytes)));
+                    mbar_expect_tx(&full[s], (uint32_t)((TC_KO_ATMA ? 0 : TC_A_BYTES) + (TC_KO_WTMA ? 0 : 2 * w_box_bytes)));
                     if (!TC_KO_ATMA) {
                         if (t < p.T1) tma_load_2d(&mapA1, a_raw(s), &full[s], t * TC_BK, m0);
                         else          tma_load_2d(&mapA2, a_raw(s), &full[s], (t - p.T1) * TC_BK, m0);
@@ -404,6 +410,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             // (kind::f16: A = B = fp16 is format 0)
             const uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(tile_bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             const uint32_t d_main = tmem + TC_COL_ACC * buf, d_corr = d_main + TC_COL_CORR;
+            const bool fuse_wlo = F16 && TC_FUSE_WLO && !TC_SPLIT_ISSUE;   // the Wlo box sits 96 rows behind the Whi box
+            const uint32_t idesc_wide = (idesc & ~(0x3fu << 17)) | ((uint32_t)((TC_BN_CAP + tile_bn) >> 3) << 17);
             TC_T(ma0);
             mbar_wait(&acc_free[buf], ((it >> 1) & 1) ^ 1, 190);     // the epilogue of tile it-2 has drained this buffer
             TC_T(ma1);
@@ -448,11 +456,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                             if (F16) {
                                 // one kind::f16 MMA covers the half k-block (16 k = 32 bytes of the 64-byte weight row)
                                 const uint64_t adv = (uint64_t)(h * 32 >> 4);
+                                if (fuse_wlo) {
+                                    // Whi and Wlo are adjacent 96-row boxes of the stage and the two accumulators adjacent 96-column
+                                    // blocks of TMEM: ONE MMA of N = 96 + tile_bn computes Ahi.[Whi; Wlo] -> [main | compensation].
+                                    // A TS-form kind::f16 MMA costs ~100-160 cycles to issue whatever its N up to ~200
+                                    // (scripts/micro/peaks.cu), so two instructions per half k-block instead of three.
+                                    // (Columns tile_bn..95 of main receive the next tile's weight rows: never read.)
+                                    umma_f16_ts(d_main, t_hi, dbh + adv, idesc_wide, (tt | h) != 0);
+                                    umma_f16_ts(d_corr, t_lo, dbh + adv, idesc, 1);               // (A - Ahi) 2^11 . Whi
+                                } else {
                                 if (role != 1) {
                                     umma_f16_ts(d_corr, t_lo, dbh + adv, idesc, (tt | h) != 0);   // (A - Ahi) 2^11 . Whi
                                     umma_f16_ts(d_corr, t_hi, dbl + adv, idesc, 1);               // Ahi . (W - Whi) 2^11
                                 }
                                 if (role != 2) umma_f16_ts(d_main, t_hi, dbh + adv, idesc, (tt | h) != 0);
+                                }
                             } else {
 #pragma unroll
                                 for (int kk = 0; kk < 2; ++kk) {

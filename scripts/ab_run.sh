@@ -1,4 +1,9 @@
+# Same-box A/B of two builds of the library (FLOWCOMPARE_B200_LIB picks the .so): A = TC_FUSE_WLO=0, B = TC_FUSE_WLO=1 (default build)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 300 python bench.py --no-extras > gpurun_out/ab.json 2>/dev/null; python -c "import json; d=json.load(open('gpurun_out/ab.json')); print('bench', d['value'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['traffic'], d['clocks']['sm_mhz'])"
+A=$PWD/flowcompare_b200/libfc_fuse0.so; B=$PWD/flowcompare_b200/libflowcompare_b200.so
+i=0
+for L in $A $B $B $A $A $B; do
+  i=$((i+1))
+  FLOWCOMPARE_B200_LIB=$L timeout 40 python bench.py --no-extras --no-cpu-baseline --steps 4 --warmup 3 > gpurun_out/abx_$i.json 2>/dev/null
+  python -c "import json; d=json.load(open('gpurun_out/abx_$i.json')); print('$i', '$(basename $L)', d['value'], d['ms_per_step'], d['kernel_classes']['gemm_tcgen05_3x']['ms'], d['kernel_classes']['cross_attention']['ms'], d['clocks']['sm_mhz'])" | tee -a gpurun_out/abx.log
+done
