@@ -4,6 +4,7 @@ There is no CPU path."""
 import torch
 
 from . import lib as _lib
+from .engine import get_knn
 
 
 def _stream():
@@ -47,3 +48,30 @@ def co_unit_sphere(points_0, points_1, return_inverse=False):
     else:
         inverse = {"furthest_distance": inv[:, 3], "mean": inv[:, :3]}
     return (a, b, inverse) if return_inverse else (a, b)
+
+
+def voxel_centers(start, end, size):
+    """The centre grid of `voxelize` (reference utils.py:448-451): per axis `arange(start + size/2, end + size/2, size)`, all
+    combinations with the FIRST axis running fastest, [m, D] fp32.  Host-side like the reference's (its `torch.arange` lands on
+    the CPU whatever device the bounds live on): a few hundred rows, built once per cluster."""
+    start, end, size = (torch.as_tensor(v, dtype=torch.float32).cpu() for v in (start, end, size))
+    lo, hi = start + size / 2, end + size / 2                     # fp32, as the reference's per-axis tensor arithmetic
+    axes = [torch.arange(lo[d].item(), hi[d].item(), size[d].item()) for d in range(size.numel())]
+    cols, inner = [], 1
+    total = 1
+    for a in axes:
+        total *= a.numel()
+    for a in axes:
+        cols.append(a.repeat_interleave(inner).repeat(total // (inner * a.numel())))
+        inner *= a.numel()
+    return torch.stack(cols, dim=1)
+
+
+def voxelize(pos, start, end, size):
+    """`voxelize(pos, start, end, size)` (reference utils.py:446-454, called by dataloaders/ams_voxel_loader.py:204): the voxel
+    centres of the box and, for every point of `pos` [n, D] (CUDA), the index of its nearest centre -- the reference's
+    `get_knn(pos, centers, 1)`, here one launch of the bit-exact kNN query (csrc/knn.cu, fc_knn_query) instead of an n x m
+    distance matrix and a top-k.  Returns (labels [n, 1] int64, centers [m, D]) on pos.device."""
+    assert pos.is_cuda, "flowcompare_b200.dataops works on CUDA tensors only (no CPU fallback)"
+    centers = voxel_centers(start, end, size).to(pos.device)
+    return get_knn(pos, centers, 1), centers

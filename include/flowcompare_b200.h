@@ -63,7 +63,9 @@ FC_API int fc_knn_self(const float* x, int ldx, int B, int N, int C, int k,
 
 /* fc_knn_query replaces `get_knn(samples, context_cloud, n_neighbors)` / `KNN_torch_fun` of
  * reference knn.py:40-52,79-90: queries q [Nq, D], train t [Nt, D] -> idx64 [Nq, k], ascending
- * diss_ij = (qq_i + tt_j) - 2*dot_ij, ties by lower index.  1 <= k <= 64, k <= Nt.            */
+ * diss_ij = (qq_i + tt_j) - 2*dot_ij, ties by lower index.  1 <= k <= 64, k <= Nt.
+ * With k = 1 and t = the voxel-centre grid it is also the label pass of `voxelize(pos, start, end, size)`
+ * (reference utils.py:446-454, called by dataloaders/ams_voxel_loader.py:204).                 */
 FC_API int fc_knn_query(const float* q, const float* t, int Nq, int Nt, int D, int k,
                  int64_t* idx64, fc_stream_t stream);
 

@@ -7,7 +7,11 @@ first maximum) as called by reference dataloaders/ams_voxel_loader.py:298-307.  
 restatement only ("parity unpinned" against torch_cluster itself).
 
 `co_unit_sphere` is not restated: the tests import the reference's own utils.co_unit_sphere when /root/reference is present
-and otherwise use the golden file made from it (tests/golden/dataops.pt, oracle/make_dataops_golden.py)."""
+and otherwise use the golden file made from it (tests/golden/dataops.pt, oracle/make_dataops_golden.py).
+
+`voxelize` restates reference utils.py:446-454 (voxel centres of a box + the nearest centre of every point through
+knn.get_knn, knn.py:79-90) and is pinned to the unmodified reference's output (tests/golden/voxelize.pt,
+oracle/make_voxelize_golden.py; tests/test_oracle.py::test_voxelize_oracle_matches_reference)."""
 import numpy as np
 
 
@@ -28,3 +32,22 @@ def fps(points, m):
         cur = int(np.argmax(dist))          # first maximum
         idx[j] = cur
     return idx
+
+
+def voxelize(pos, start, end, size):
+    """reference utils.py:446-454.  pos [n, D], start / end / size [D] (CPU fp32 tensors) -> (labels [n, 1] int64, centers [m, D]).
+    Centres: per axis `arange(start + size/2, end + size/2, size)` (fp32 tensor arithmetic for the bounds, torch's own arange
+    for the steps), enumerated with the first axis fastest.  Labels: index of the nearest centre with the reference's kNN
+    arithmetic and tie order (oracle/knn_ref.c mode 1 = knn.py:40-52)."""
+    import torch
+    from oracle import knn_ref
+    D = len(size)
+    axes = [torch.arange(start[i] + size[i] / 2, end[i] + size[i] / 2, size[i]) for i in range(D)]
+    centers = torch.empty(int(np.prod([len(a) for a in axes])), D)
+    row = 0
+    for multi in np.ndindex(*[len(a) for a in axes[::-1]]):      # last axis slowest, first axis fastest
+        for d in range(D):
+            centers[row, d] = axes[d][multi[D - 1 - d]]
+        row += 1
+    labels = knn_ref.knn_query(pos, centers, 1)
+    return labels, centers

@@ -9,7 +9,7 @@ from flowcompare_b200 import configs, packing, spec
 from oracle import knn_ref, port, refload
 from oracle.make_golden import FIXTURES, fixture_inputs
 from tests import arena_sim
-from tests.conftest import load_golden
+from tests.conftest import load_golden, voxel_label_mismatch
 
 torch.set_grad_enabled(False)
 
@@ -380,6 +380,28 @@ def test_fps_oracle_is_furthest_point_sampling():
     for j in range(1, 40):
         d = ((x[:, None, :] - x[None, idx[:j], :]) ** 2).sum(-1).min(1)
         assert d[idx[j]] >= d.max() * (1 - 1e-6)
+
+
+@pytest.mark.parametrize("case", ["loader_default", "fine", "single_layer", "planar"])
+def test_voxelize_oracle_matches_reference(case):
+    """oracle/dataops_ref.voxelize (centres + nearest-centre labels through the canonical kNN oracle) and the product's host-side
+    centre grid (flowcompare_b200.dataops.voxel_centers) against the UNMODIFIED reference's utils.voxelize (utils.py:446-454;
+    tests/golden/voxelize.pt): centres bit-exact incl. their order; labels equal except where the two candidate centres are
+    equidistant within the rounding noise of the reference's own fp32 formula (see tests/conftest.voxel_label_mismatch)."""
+    from flowcompare_b200 import dataops
+    from oracle import dataops_ref
+    from oracle.make_voxelize_golden import inputs
+    gold = load_golden("voxelize")[case]
+    pos, start, end, size = inputs(case)
+    labels, centers = dataops_ref.voxelize(pos, start, end, size)
+    assert torch.equal(centers, gold["centers"])
+    assert torch.equal(dataops.voxel_centers(start, end, size), gold["centers"])
+    assert voxel_label_mismatch(pos, centers, labels, gold["labels"]) <= 5e-3
+    if refload.available():
+        refload.load()
+        import utils
+        l2, c2 = utils.voxelize(pos, start=start, end=end, size=size)
+        assert torch.equal(l2, gold["labels"]) and torch.equal(c2, gold["centers"])
 
 
 @pytest.mark.parametrize("kind", ["LinearLU", "random_permute", "FullCombiner", "ExponentialCombiner"])
