@@ -403,7 +403,10 @@ def test_change_maps_equals_the_four_separate_passes():
 
 
 def test_drop_in_adapters_follow_reference_call_signature():
-    """The reference's inner_loop body (model_initialization.py:206-228) re-stated against the adapters."""
+    """The reference's inner_loop body (model_initialization.py:206-228) re-stated against the adapters on the GPU (the
+    reference tree does not travel to the GPU box).  Its CPU twin, tests/test_oracle.py::
+    test_reference_callers_run_unmodified_on_the_adapters, hands the same adapter classes to the reference's own imported
+    `inner_loop` / `make_sample`."""
     import einops
     cfg, fsd, esd, batch, _ = _engine("tiny_dgcnn_attn_extra")
     md = eng.accelerate({"flow": _SD(fsd), "input_embedder": _SD(esd)}, cfg, device=DEV)

@@ -382,6 +382,65 @@ def test_fps_oracle_is_furthest_point_sampling():
         assert d[idx[j]] >= d.max() * (1 - 1e-6)
 
 
+class _PortEngine:
+    """Stands in for FlowCompareB200 UNDER the product's drop-in adapters (engine._FlowAdapter / _EmbedderAdapter) on a machine
+    without a GPU: same method signatures, the product's own argument normalisation (`FlowCompareB200._prep_context`), the CPU
+    port doing the arithmetic.  Test infrastructure: lets the reference's unmodified callers be run on the adapters here."""
+
+    def __init__(self, fsd, esd, dcfg):
+        self.fsd, self.esd, self.cfg = fsd, esd, dcfg
+        self.device = torch.device("cpu")
+        self.is_global, self.has_extra = bool(dcfg["global"]), bool(dcfg["extra_z_value_context"])
+        self.d_in = dcfg["input_dim"]
+
+    def embed(self, extract_0):
+        f = port.dgcnn_embed_global if self.is_global else port.dgcnn_embed
+        return f(self.esd, extract_0[:, :, :self.d_in], self.cfg["n_neighbors"])[0]
+
+    def _expand(self, context, extra_context, B, P):
+        from flowcompare_b200.engine import FlowCompareB200
+        ctx, _, extra = FlowCompareB200._prep_context(self, context, extra_context, B)
+        if self.is_global:
+            ctx = ctx.unsqueeze(1).expand(-1, P, -1)
+        return ctx, (None if extra is None else extra.reshape(B, 1, 1).expand(-1, P, -1))
+
+    def log_prob(self, x, context, extra_context=None, eps=None, eps_cif=None):
+        ctx, ex = self._expand(context, extra_context, x.shape[0], x.shape[1])
+        return port.flow_log_prob(self.fsd, self.cfg, x[..., :self.d_in], ctx, ex, eps, eps_cif=eps_cif)
+
+    def sample(self, n_points, context, extra_context=None, z=None, seed=None, eps_cif=None):
+        ctx, ex = self._expand(context, extra_context, context.shape[0], n_points)
+        return port.flow_sample(self.fsd, self.cfg, z, ctx, ex, eps_cif=eps_cif)
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", TINY)
+def test_reference_callers_run_unmodified_on_the_adapters(name):
+    """The reference's OWN `inner_loop` and `make_sample` (model_initialization.py:206-245), imported unmodified, are handed a
+    models_dict made of the product's adapter classes (what `accelerate` returns; the engine under them is the CPU stand-in
+    above because there is no GPU here): the calls they make -- `input_embedder(extract_0)`,
+    `flow.log_prob(x, context=, extra_context=)` with the einops-repeated [B,N,1] extra context and [B,P,E] global embedding,
+    `flow.sample(num_samples=1, n_points=, context=, sample_distrib=, extra_context=)` -- bind to the adapters' signatures and
+    give the goldens the same functions produced on the reference's own modules."""
+    from flowcompare_b200.engine import _EmbedderAdapter, _FlowAdapter
+    from oracle.make_sample_golden import Injected, base_draw
+    _, mi = refload.load()
+    cfg, fsd, esd, batch = fixture_inputs(name)
+    dcfg = configs.derive(cfg)
+    eng = _PortEngine(fsd, esd, dcfg)
+    md = {"parameters": [], "flow": _FlowAdapter(eng), "input_embedder": _EmbedderAdapter(eng)}
+    md["flow"].eps = batch["eps"]
+    loss, lp, bpd = mi.inner_loop((batch["extract_0"], batch["extract_1"], batch["extra_context"]), md, dcfg)
+    gold = load_golden(name)
+    assert (lp - gold["log_prob"]).abs().max().item() < 1e-3
+    assert abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-4
+    assert abs(bpd.item() - gold["bpd"].item()) / abs(gold["bpd"].item()) < 1e-4
+    gs = load_golden("sample_" + name)
+    z = base_draw(name, cfg, batch["extract_0"].shape[0])
+    x = mi.make_sample(gs["n_points"], batch["extract_0"], md, dcfg, sample_distrib=Injected(z), extra_context=batch["extra_context"])
+    assert x.shape == gs["x"].shape and (x - gs["x"]).abs().max().item() < 1e-4
+
+
 @pytest.mark.parametrize("case", ["loader_default", "fine", "single_layer", "planar"])
 def test_voxelize_oracle_matches_reference(case):
     """oracle/dataops_ref.voxelize (centres + nearest-centre labels through the canonical kNN oracle) and the product's host-side
