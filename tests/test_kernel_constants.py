@@ -56,3 +56,43 @@ def test_gemm_tile_partition_covers_n_without_padding_columns():
         assert n0[-1] + bn[-1] == (N + 15) // 16 * 16                    # exactly N rounded up to 16: no padded tile columns
         # the TMA box is tc_bn(N) rows from n0: it must stay inside the packed weight rows (n_tiles * tc_bn)
         assert n0[-1] + packing.tc_bn(N) <= packing.tc_n_tiles(N) * packing.tc_bn(N)
+
+
+def _tc_define(name):
+    src = open(os.path.join(ROOT, "flowcompare_b200", "csrc", "gemm_tc.cu")).read()
+    m = re.search(r"#define\s+%s\s+(\d+)" % name, src) or re.search(r"constexpr int %s\s*=\s*([^;]+);" % name, src)
+    assert m, name
+    return m.group(1).strip()
+
+
+def test_fused_whi_wlo_mma_layout_invariants():
+    """TC_FUSE_WLO (gemm_tc.cu): ONE tcgen05.mma of N = TC_BN_CAP + tile_bn runs over the adjacent [Whi; Wlo] boxes of a stage and
+    lands in the adjacent [main | compensation] accumulators.  The layout facts that makes legal, checked against the source's
+    constants: the compensation accumulator sits exactly TC_BN_CAP columns behind the main one, every wide N is a legal UMMA
+    shape for M = 128 (multiple of 16, <= 256) and fits the 6-bit N field of the instruction descriptor, the wide write stays
+    inside its own accumulator buffer (below the next buffer and the A-operand stages), and the Wlo slot starts on a whole
+    8-row swizzle atom of the 64-byte fp16 weight rows so that one descriptor walks both boxes."""
+    cap = int(_tc_define("TC_BN_CAP"))
+    bk = int(_tc_define("TC_BK"))
+    assert _tc_define("TC_FUSE_WLO") == "1"
+    assert _tc_define("TC_COL_CORR").replace(" ", "") == "TC_BN_CAP"
+    assert _tc_define("TC_COL_ACC").replace(" ", "") == "2*TC_BN_CAP"
+    assert _tc_define("TC_COL_A").replace(" ", "") == "4*TC_BN_CAP"
+    col_acc, col_a = 2 * cap, 4 * cap
+    assert col_a <= 512 - 4 * 16                       # at least four 16-column A stages remain in the 512 TMEM columns
+    for N in (64, 128, 256, 300, 512, 588):
+        _, bn = _tiles(N, cap)
+        for b in bn:
+            wide = cap + b
+            assert wide % 16 == 0 and 16 <= wide <= 256
+            assert (wide >> 3) < 64
+            assert wide <= col_acc                      # [main | compensation[0:b)] never reaches accumulator buffer 1 or the A stages
+    row_bytes = bk * 2                                  # fp16 weights: 64-byte rows, SWIZZLE_64B atoms of 8 rows = 512 B
+    assert (cap * row_bytes) % (8 * row_bytes) == 0
+    # shared memory of the launch (TcCfg<true>::SMEM_BYTES: stages sized for 96-row boxes whatever BN is) fits the 227 KB opt-in
+    src = open(os.path.join(ROOT, "flowcompare_b200", "csrc", "gemm_tc.cu")).read()
+    m = re.search(r"#define TC_STAGES_F16 \(TC_RES_PREFETCH \? (\d+) : (\d+)\)", src)
+    stages = int(m.group(1)) if _tc_define("TC_RES_PREFETCH") == "1" else int(m.group(2))
+    stg_floats = 1024 if _tc_define("TC_RES_PREFETCH") == "1" else 32 * 20
+    smem = stages * (128 * bk * 4 + 2 * cap * bk * 2) + 8 * stg_floats * 4 + 1024
+    assert smem <= 227 * 1024
