@@ -28,10 +28,10 @@ def test_shard_bounds_cover_everything_once():
             assert max(sizes) - min(sizes) <= 1
 
 
-def _setup():
-    cfg = configs.get_config("dgcnn_attn_extra", n_flow_layers=2, sample_size=48, n_samples_context=64)
+def _setup(label="dgcnn_attn_extra", pairs=5):
+    cfg = configs.get_config(label, n_flow_layers=2, sample_size=48, n_samples_context=64)
     fsd, esd = spec.random_state_dicts(cfg, seed=3)
-    batch = spec.synthetic_batch(cfg, 5, seed=4)   # 5 pairs over 2 ranks: ragged 3 + 2
+    batch = spec.synthetic_batch(cfg, pairs, seed=4)   # 5 pairs over 2 ranks: ragged 3 + 2; 2 pairs over 3 ranks: an empty block
     dcfg = configs.derive(cfg)
 
     def score(args, eps):
@@ -40,14 +40,14 @@ def _setup():
     return cfg, batch, score
 
 
-def _worker(rank, world, port_no, q):
+def _worker(rank, world, port_no, q, label="dgcnn_attn_extra", pairs=5):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
     torch.set_grad_enabled(False)
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        cfg, batch, score = _setup()
+        cfg, batch, score = _setup(label, pairs)
         per_cloud, nats = sharding.evaluate_sharded(score, batch["extract_0"], batch["extract_1"], batch["extra_context"],
                                                     batch["eps"], input_dim=cfg["input_dim"])
         q.put((rank, per_cloud.tolist(), nats))
@@ -56,8 +56,11 @@ def _worker(rank, world, port_no, q):
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_gloo_matches_single_process():
-    cfg, batch, score = _setup()
+@pytest.mark.parametrize("world,label,pairs", [(2, "dgcnn_attn_extra", 5), (3, "dgcnn_attn", 2)])
+def test_multi_rank_gloo_matches_single_process(world, label, pairs):
+    """world 2: ragged blocks (3 + 2 pairs) with extra context; world 3 with 2 pairs: the last rank's block is EMPTY (it still
+    takes part in the gather) and the config has no extra context."""
+    cfg, batch, score = _setup(label, pairs)
     want, want_nats = sharding.evaluate_sharded(score, batch["extract_0"], batch["extract_1"], batch["extra_context"],
                                                 batch["eps"], input_dim=cfg["input_dim"])
     with socket.socket() as s:
@@ -65,10 +68,10 @@ def test_two_rank_gloo_matches_single_process():
         port_no = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port_no, q, label, pairs)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=240) for _ in range(2)]
+    results = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
