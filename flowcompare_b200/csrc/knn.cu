@@ -663,6 +663,40 @@ extern "C" int fc_knn_self(const float* x, int ldx, int B, int N, int C, int k, 
                          (cudaStream_t)stream);
 }
 
+// Workspace forms of the two entry points above: nothing is allocated and no per-device state is touched, so calls on different
+// streams (or host threads) of one device are independent.  The workspace holds the norms and the keys of one chunk of clouds.
+extern "C" int64_t fc_knn_workspace_bytes(int B, int Nq, int Nt, int self) {
+    if (B < 1 || Nq < 1 || Nt < 1) return 0;
+    return fc_knn_scratch_floats(B, Nq, Nt, self != 0) * 4 + 256;
+}
+
+namespace {
+float* knn_ws_base(void* workspace, int64_t workspace_bytes, int64_t need_floats) {
+    if (!workspace) return nullptr;
+    const uintptr_t p = reinterpret_cast<uintptr_t>(workspace);
+    const uintptr_t a = (p + 255) & ~(uintptr_t)255;
+    if ((int64_t)(a - p) + need_floats * 4 > workspace_bytes) return nullptr;
+    return reinterpret_cast<float*>(a);
+}
+}  // namespace
+
+extern "C" int fc_knn_self_ws(const float* x, int ldx, int B, int N, int C, int k, int32_t* idx32, int64_t* idx64,
+                              void* workspace, int64_t workspace_bytes, fc_stream_t stream) {
+    FC_REQUIRE(x && ldx >= C && B > 0 && N > 0 && C > 0 && k >= 1 && k <= KNN_KMAX && k <= N && (idx32 || idx64));   // before any GPU work
+    float* scratch = knn_ws_base(workspace, workspace_bytes, fc_knn_scratch_floats(B, N, N, true));
+    if (!scratch) return FC_ERR_WORKSPACE;   // missing, or smaller than fc_knn_workspace_bytes says
+    return fc_knn_launch(x, ldx, (long long)N * ldx, x, ldx, (long long)N * ldx, B, N, N, C, k, 0, idx32, idx64, scratch,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int fc_knn_query_ws(const float* q, const float* t, int Nq, int Nt, int D, int k, int64_t* idx64,
+                               void* workspace, int64_t workspace_bytes, fc_stream_t stream) {
+    FC_REQUIRE(q && t && idx64 && Nq > 0 && Nt > 0 && D > 0 && k >= 1 && k <= KNN_KMAX && k <= Nt);   // before any GPU work
+    float* scratch = knn_ws_base(workspace, workspace_bytes, fc_knn_scratch_floats(1, Nq, Nt, false));
+    if (!scratch) return FC_ERR_WORKSPACE;   // missing, or smaller than fc_knn_workspace_bytes says
+    return fc_knn_launch(q, D, 0, t, D, 0, 1, Nq, Nt, D, k, 1, nullptr, idx64, scratch, (cudaStream_t)stream);
+}
+
 extern "C" int fc_knn_query(const float* q, const float* t, int Nq, int Nt, int D, int k, int64_t* idx64,
                             fc_stream_t stream) {
     FC_REQUIRE(q && t && idx64 && Nq > 0 && Nt > 0 && D > 0 && k >= 1 && k <= KNN_KMAX && k <= Nt);   // before any GPU work

@@ -30,6 +30,9 @@ SIGNATURES = {
     "fc_launch_count": (c_i64, []),
     "fc_knn_self": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "fc_knn_query": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "fc_knn_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
+    "fc_knn_self_ws": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "fc_knn_query_ws": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp]),
     "fc_fps": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "fc_knn_heap": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "fc_three_nn": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),

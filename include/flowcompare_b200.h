@@ -69,6 +69,18 @@ FC_API int fc_knn_self(const float* x, int ldx, int B, int N, int C, int k,
 FC_API int fc_knn_query(const float* q, const float* t, int Nq, int Nt, int D, int k,
                  int64_t* idx64, fc_stream_t stream);
 
+/* Workspace forms of the two entry points above.  fc_knn_self / fc_knn_query keep the round-1 signatures (no workspace
+ * argument) and are the ONE exception to "never allocate": they use a per-device scratch (norms + distance keys) that
+ * grows on demand, so two calls on different streams of the same device must not overlap.  The _ws forms take the
+ * scratch from the caller (fc_knn_workspace_bytes(B, Nq, Nt, self): B clouds, self = 1 for fc_knn_self_ws with
+ * Nq = Nt = N, self = 0 and B = 1 for fc_knn_query_ws), touch no global state and are independent per stream.
+ * FC_ERR_WORKSPACE if the workspace is NULL or too small.  Results are identical to the forms above.            */
+FC_API int64_t fc_knn_workspace_bytes(int B, int Nq, int Nt, int self);
+FC_API int fc_knn_self_ws(const float* x, int ldx, int B, int N, int C, int k, int32_t* idx32, int64_t* idx64,
+                   void* workspace, int64_t workspace_bytes, fc_stream_t stream);
+FC_API int fc_knn_query_ws(const float* q, const float* t, int Nq, int Nt, int D, int k, int64_t* idx64,
+                    void* workspace, int64_t workspace_bytes, fc_stream_t stream);
+
 /* ------------------------------------------------------------------ pointops (PAConv embedder, data side) ----
  * Op-level entry points for the reference's `pointops` kernels (models/scene_seg_PAConv/lib/pointops; python wrappers
  * lib/pointops/functions/pointops.py), point-major layouts, int32 indices, bit-exact INDICES against the reference's

@@ -57,6 +57,16 @@ def test_argument_validation_happens_before_any_gpu_work():
     lib = fclib.load()
     INVALID, UNSUPPORTED = -1, -5
     assert lib.fc_knn_self(0, 6, 1, 10, 6, 4, 0, 0, 0) == INVALID                       # null input
+    assert lib.fc_knn_self_ws(0, 6, 1, 10, 6, 4, 0, 0, 0, 0, 0) == INVALID               # null input (workspace form)
+    assert lib.fc_knn_self_ws(8, 6, 1, 10, 6, 11, 8, 0, 8, 1 << 20, 0) == INVALID         # k > N
+    assert lib.fc_knn_self_ws(8, 6, 1, 10, 6, 4, 8, 0, 0, 0, 0) == -4                     # FC_ERR_WORKSPACE: no workspace
+    assert lib.fc_knn_self_ws(8, 6, 1, 10, 6, 4, 8, 0, 256, 16, 0) == -4                  # FC_ERR_WORKSPACE: too small
+    assert lib.fc_knn_query_ws(8, 8, 10, 5, 3, 6, 8, 8, 1 << 20, 0) == INVALID            # k > Nt
+    assert lib.fc_knn_query_ws(8, 8, 10, 5, 3, 2, 8, 0, 0, 0) == -4
+    # the workspace covers the norms and the keys of one chunk of clouds, 256-byte slack for alignment
+    assert lib.fc_knn_workspace_bytes(1, 1000, 315, 0) >= 4 * (1000 + 315 + 1000 * 316)
+    assert lib.fc_knn_workspace_bytes(2, 1250, 1250, 1) >= 4 * (2 * 1250 + 2 * 1250 * 1252)
+    assert lib.fc_knn_workspace_bytes(0, 10, 10, 1) == 0
     assert lib.fc_cross_attention(0, 64, 0, 128, 0, 64, 1, 8, 8, 64, 0.125, 0) == INVALID
     assert lib.fc_cross_attention_tf32x3(0, 64, 0, 128, 0, 64, 1, 8, 8, 64, 0.125, 0) == INVALID
     assert lib.fc_cross_attention_tc(0, 64, 0, 128, 0, 64, 1, 8, 8, 64, 0.125, 0, 0, 0) == INVALID   # no scratch
