@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 int fc_launch_gemm_tc(const GemmArgs& a, cudaStream_t stream);  // gemm_tc.cu
@@ -21,18 +22,29 @@ void fc_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed)
 namespace {
 struct ProfRec { int cls; double flops, bytes; cudaEvent_t a, b; long long tag; };
 std::atomic<bool> g_prof_on{false};
-std::vector<ProfRec> g_prof;
+std::vector<ProfRec> g_prof;      // guarded by g_prof_mu: launchers on several host threads may record concurrently
+std::mutex g_prof_mu;
 }  // namespace
 bool fc_prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
-void fc_prof_open(int cls, double flops, double bytes, cudaStream_t s, long long tag) {
+int fc_prof_open(int cls, double flops, double bytes, cudaStream_t s, long long tag) {
     ProfRec r{cls, flops, bytes, nullptr, nullptr, tag};
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     cudaEventRecord(r.a, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(r);
+    return (int)g_prof.size() - 1;
 }
-void fc_prof_close(cudaStream_t s) { if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, s); }
+void fc_prof_close(int id, cudaStream_t s) {     // each scope closes ITS record (not whatever was opened last)
+    cudaEvent_t b = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (id >= 0 && id < (int)g_prof.size()) b = g_prof[(size_t)id].b;
+    }
+    if (b) cudaEventRecord(b, s);
+}
 
 extern "C" int fc_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_prof.clear();
     g_prof_on.store(true);
@@ -43,6 +55,7 @@ extern "C" int fc_profile_end(double* ms, double* flops, double* bytes, int64_t*
     FC_REQUIRE(ms && flops && bytes && launches && n_classes >= FC_N_CLASSES);
     for (int i = 0; i < n_classes; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
     FC_CUDA_OK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     // FC_PROFILE_DUMP=<path>: one line per instrumented launch (class, shape tag, flops, ms) for per-shape breakdowns
     const char* dump = getenv("FC_PROFILE_DUMP");
     FILE* df = dump && dump[0] ? fopen(dump, "w") : nullptr;

@@ -89,12 +89,12 @@ __device__ __forceinline__ float fc_warp_max(float v) {
 enum { FC_CLS_GEMM_FFMA = 0, FC_CLS_GEMM_TC = 1, FC_CLS_ATTENTION = 2, FC_CLS_KNN = 3, FC_CLS_EDGECONV = 4,
        FC_CLS_OTHER = 5, FC_N_CLASSES = 6 };
 bool fc_prof_enabled();
-void fc_prof_open(int cls, double flops, double bytes, cudaStream_t s, long long tag = 0);
-void fc_prof_close(cudaStream_t s);
+int fc_prof_open(int cls, double flops, double bytes, cudaStream_t s, long long tag = 0);   // returns the record's id
+void fc_prof_close(int id, cudaStream_t s);
 struct FcProfScope {
-    cudaStream_t s; bool on;
+    cudaStream_t s; bool on; int id = -1;
     FcProfScope(int cls, double flops, double bytes, cudaStream_t st, long long tag = 0) : s(st), on(fc_prof_enabled()) {
-        if (on) fc_prof_open(cls, flops, bytes, s, tag);
+        if (on) id = fc_prof_open(cls, flops, bytes, s, tag);
     }
-    ~FcProfScope() { if (on) fc_prof_close(s); }
+    ~FcProfScope() { if (on) fc_prof_close(id, s); }
 };
