@@ -1,6 +1,7 @@
-# Same-box A/B of two builds of the library (FLOWCOMPARE_B200_LIB picks the .so): A = TC_FUSE_WLO=0, B = TC_FUSE_WLO=1 (default build)
+# Same-box A/B of two builds of the library (FLOWCOMPARE_B200_LIB picks the .so): A = TC_FUSE_WLO=0, B = TC_FUSE_WLO=1 (default build).
+# Build A first:  scripts/build_variant.sh fuse0 gemm_tc "-DTC_FUSE_WLO=0"   (output of the last run: profiles/r02_fuse_wlo_ab.txt)
 mkdir -p gpurun_out
-A=$PWD/flowcompare_b200/libfc_fuse0.so; B=$PWD/flowcompare_b200/libflowcompare_b200.so
+A=$PWD/flowcompare_b200/variants/lib_fuse0.so; B=$PWD/flowcompare_b200/libflowcompare_b200.so
 i=0
 for L in $A $B $B $A $A $B; do
   i=$((i+1))
