@@ -463,6 +463,28 @@ def test_voxelize_oracle_matches_reference(case):
         assert torch.equal(l2, gold["labels"]) and torch.equal(c2, gold["centers"])
 
 
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_voxel_centers_equal_live_reference_on_random_boxes():
+    """flowcompare_b200.dataops.voxel_centers against the centres the UNMODIFIED utils.voxelize builds (utils.py:448-451), 60 random
+    boxes in 2 and 3 dimensions incl. extents that are exact multiples of the voxel size and boxes thinner than one voxel:
+    bit-identical values in the same order."""
+    from flowcompare_b200 import dataops
+    refload.load()
+    import utils
+    g = torch.Generator().manual_seed(99)
+    for case in range(60):
+        D = 2 + case % 2
+        size = torch.rand(D, generator=g) * 3 + 0.25
+        start = (torch.rand(D, generator=g) - 0.5) * 200
+        n = torch.randint(0, 7, (D,), generator=g).float()
+        extent = (n + 1) * size if case % 3 == 0 else (n + torch.rand(D, generator=g)) * size   # exact multiples every third case
+        end = start + extent
+        pos = start + torch.rand(5, D, generator=g) * extent.clamp_min(1e-3)
+        _, want = utils.voxelize(pos, start=start, end=end, size=size)
+        got = dataops.voxel_centers(start, end, size)
+        assert got.shape == want.shape and torch.equal(got, want), (case, start, end, size)
+
+
 @pytest.mark.parametrize("kind", ["LinearLU", "random_permute", "FullCombiner", "ExponentialCombiner"])
 def test_permuter_fold_and_its_inverse(kind):
     """packing.permuter_matrix / permuter_inverse_matrix (the pack-time form of every permuter, reference model_initialization.py:
