@@ -414,6 +414,32 @@ class FlowCompareB200:
         out["change_0_1"] = log_prob_to_change(out["log_prob_0_1"], out["log_prob_1_1"], multiple, hard_cutoff)
         return out
 
+    def evaluate_on_batches(self, batches, multiple=5.4, hard_cutoff=None, eps=None):
+        """The evaluation loop of `evaluate_on_test` (reference test_flow.py:147-226) over an iterable of
+        `(batch_1_0, batch_0_0)` pairs, each batch `(extract_0, extract_1, extra_context)` as the reference assembles them
+        (test_flow.py:155-158): the two passes run as ONE stacked pass, then `log_prob_to_change(lp_1_0, lp_0_0, multiple)`,
+        the per-cloud change means `(change > 0).float().mean(-1)` (:172) and the running average of the 1|0 pass's nats
+        (:224-226).  eps: optional iterable of [2B, N, latent-input_dim] noise per batch (1|0 rows first).
+        Returns `(nats_avg, change_mean_list)` as Python floats, like the reference."""
+        nats_avg, change_mean_list = 0.0, []
+        eps_it = iter(eps) if eps is not None else None
+        for batch_ind, (b10, b00) in enumerate(batches):
+            B = b10[0].shape[0]
+            e0 = torch.cat([b[0][:, :, :self.d_in].to(self.device, torch.float32) for b in (b10, b00)], dim=0)
+            e1 = torch.cat([b[1][:, :, :self.d_in].to(self.device, torch.float32) for b in (b10, b00)], dim=0)
+            extra = None
+            if self.has_extra:
+                if b10[2] is None or b00[2] is None:
+                    raise _lib.FlowCompareError("this config uses extra context but a batch has none")
+                extra = torch.cat([b[2].reshape(-1).to(self.device, torch.float32) for b in (b10, b00)], dim=0)
+            _, lp, _ = self.inner_loop((e0, e1, extra), eps=None if eps_it is None else next(eps_it))
+            lp10, lp00 = lp[:B], lp[B:]
+            change = log_prob_to_change(lp10, lp00, multiple, hard_cutoff)
+            change_mean_list.extend((change > 0).float().mean(dim=-1).tolist())
+            nats = (-lp10.mean() * math.log2(math.e) / self.d_in).item()
+            nats_avg = (nats_avg * batch_ind + nats) / (batch_ind + 1)
+        return nats_avg, change_mean_list
+
     def log_prob_to_change(self, log_prob_1_given_0, log_prob_0_given_0, multiple, hard_cutoff=None):
         """`log_prob_to_change` (+ `clamp_infs`), reference test_flow.py:241-275."""
         return log_prob_to_change(log_prob_1_given_0, log_prob_0_given_0, multiple, hard_cutoff)

@@ -79,37 +79,6 @@ def test_knn_query_bit_exact(lib):
     assert torch.equal(got, want)
 
 
-def test_knn_workspace_forms_equal_the_scratch_forms(lib):
-    """fc_knn_self_ws / fc_knn_query_ws (caller-provided workspace, no global state) give the indices of fc_knn_self / fc_knn_query,
-    also from a misaligned workspace base and when two calls run on different streams with their own workspaces."""
-    g = torch.Generator().manual_seed(11)
-    pts = torch.randn(2, 700, 64, generator=g).to(DEV)
-    want = eng.knn(pts.permute(0, 2, 1), 40)
-    assert torch.equal(want.cpu(), knn_ref.knn_self(pts.cpu(), 40))
-    nbytes = lib.fc_knn_workspace_bytes(2, 700, 700, 1)
-    assert nbytes > 0
-    ws = [torch.empty(nbytes + 8, dtype=torch.uint8, device=DEV) for _ in range(2)]
-    got = [torch.full((2, 700, 40), -7, dtype=torch.int64, device=DEV) for _ in range(2)]
-    streams = [torch.cuda.Stream(device=DEV) for _ in range(2)]
-    torch.cuda.synchronize()
-    for i in range(2):
-        with torch.cuda.stream(streams[i]):
-            rc = lib.fc_knn_self_ws(pts.data_ptr(), 64, 2, 700, 64, 40, 0, got[i].data_ptr(), ws[i].data_ptr() + 8 * i, nbytes,
-                                    streams[i].cuda_stream)
-            fclib.check(rc, "fc_knn_self_ws")
-    torch.cuda.synchronize()
-    assert torch.equal(got[0], want) and torch.equal(got[1], want)
-    q, t = torch.randn(900, 3, generator=g).to(DEV), torch.randn(315, 3, generator=g).to(DEV)
-    want_q = eng.get_knn(q, t, 1)
-    nb = lib.fc_knn_workspace_bytes(1, 900, 315, 0)
-    wq = torch.empty(nb, dtype=torch.uint8, device=DEV)
-    got_q = torch.empty(900, 1, dtype=torch.int64, device=DEV)
-    assert lib.fc_knn_query_ws(q.data_ptr(), t.data_ptr(), 900, 315, 3, 1, got_q.data_ptr(), wq.data_ptr(), nb, _stream()) == 0
-    torch.cuda.synchronize()
-    assert torch.equal(got_q, want_q) and torch.equal(got_q.cpu(), knn_ref.knn_query(q.cpu(), t.cpu(), 1))
-    assert lib.fc_knn_query_ws(q.data_ptr(), t.data_ptr(), 900, 315, 3, 1, got_q.data_ptr(), wq.data_ptr(), nb - 512, _stream()) == -4
-
-
 def test_knn_rejects_bad_k(lib):
     x = torch.randn(1, 10, 3, device=DEV)
     idx = torch.empty(1, 10, 65, dtype=torch.int64, device=DEV)

@@ -441,6 +441,40 @@ def test_reference_callers_run_unmodified_on_the_adapters(name):
     assert x.shape == gs["x"].shape and (x - gs["x"]).abs().max().item() < 1e-4
 
 
+def test_evaluate_on_batches_host_logic(monkeypatch):
+    """engine.FlowCompareB200.evaluate_on_batches (the loop of reference test_flow.py:147-226) with the CUDA calls under it
+    replaced by the CPU port: stacking the 1|0 and 0|0 passes, the change means and the running nats equal the reference's loop
+    written out with separate port calls."""
+    from flowcompare_b200 import engine as eng_mod
+    cfg, fsd, esd, batch = fixture_inputs("tiny_dgcnn_attn_extra")
+    dcfg = configs.derive(cfg)
+    e = object.__new__(eng_mod.FlowCompareB200)             # no device, no library: only the host logic is exercised
+    e.d_in, e.device, e.has_extra = dcfg["input_dim"], torch.device("cpu"), True
+    e.inner_loop = lambda b, eps=None: port.inner_loop((b[0], b[1], b[2].reshape(-1, 1)), fsd, esd, dcfg, eps)
+    monkeypatch.setattr(eng_mod, "log_prob_to_change", port.log_prob_to_change)
+    B = batch["extract_0"].shape[0]
+    data, epss = [], []
+    for i in range(2):
+        pair, ee = [], []
+        for j in range(2):
+            b = spec.synthetic_batch(cfg, B, seed=60 + 2 * i + j)
+            pair.append((b["extract_0"], b["extract_1"], b["extra_context"]))
+            ee.append(b["eps"])
+        data.append(tuple(pair))
+        epss.append(torch.cat(ee, dim=0))
+    nats_avg, means = e.evaluate_on_batches(data, multiple=1.0, eps=epss)
+    want_nats, want_means = 0.0, []
+    for i, (b10, b00) in enumerate(data):
+        _, lp10, nats = port.inner_loop(b10, fsd, esd, dcfg, epss[i][:B])
+        _, lp00, _ = port.inner_loop(b00, fsd, esd, dcfg, epss[i][B:])
+        change = port.log_prob_to_change(lp10, lp00, 1.0)
+        want_means.extend((change > 0).float().mean(dim=-1).tolist())
+        want_nats = (want_nats * i + nats.item()) / (i + 1)
+    assert len(means) == 2 * B and any(m > 0 for m in means)
+    assert all(abs(a - b) <= 2.0 / batch["extract_1"].shape[1] for a, b in zip(means, want_means))   # CPU BLAS is not batch invariant to the bit
+    assert abs(nats_avg - want_nats) < 1e-5 * abs(want_nats)
+
+
 @pytest.mark.parametrize("case", ["loader_default", "fine", "single_layer", "planar"])
 def test_voxelize_oracle_matches_reference(case):
     """oracle/dataops_ref.voxelize (centres + nearest-centre labels through the canonical kNN oracle) and the product's host-side
