@@ -459,7 +459,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                                 if (fuse_wlo) {
                                     // Whi and Wlo are adjacent 96-row boxes of the stage and the two accumulators adjacent 96-column
                                     // blocks of TMEM: ONE MMA of N = 96 + tile_bn computes Ahi.[Whi; Wlo] -> [main | compensation].
-                                    // A TS-form kind::f16 MMA costs ~100-160 cycles to issue whatever its N up to ~200
+                                    // A TS-form kind::f16 MMA costs the same issue time at N = 192 as at N = 96
                                     // (scripts/micro/peaks.cu), so two instructions per half k-block instead of three.
                                     // (Columns tile_bn..95 of main receive the next tile's weight rows: never read.)
                                     umma_f16_ts(d_main, t_hi, dbh + adv, idesc_wide, (tt | h) != 0);
