@@ -77,3 +77,46 @@ def test_argument_validation_happens_before_any_gpu_work():
     assert lib.fc_gemm(0, 0, 0, 0, 0, 0, 0, 4, 4, 4, 0, 0, 0) == INVALID
     msg = lib.fc_last_error()
     assert isinstance(msg, bytes)
+
+
+def _header_prototypes():
+    """{name: (return C type, [parameter C types])} parsed from the FC_API prototypes of the header."""
+    src = open(os.path.join(ROOT, "include", "flowcompare_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"FC_API\s+([\w\s\*]+?)\b(fc_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        ret, name, params = m.group(1).strip(), m.group(2), m.group(3).strip()
+        types = []
+        if params and params != "void":
+            for p in params.split(","):
+                p = " ".join(p.split())
+                p = re.sub(r"\s*\b\w+$", "", p) if not p.endswith("*") else p      # drop the parameter name
+                types.append(p.replace(" *", "*"))
+        out[name] = (ret, types)
+    return out
+
+
+def _ctype_of(c_type):
+    import ctypes
+    t = c_type.replace("const ", "").strip()
+    if t.endswith("*") and t.replace(" ", "") == "char*":
+        return ctypes.c_char_p
+    if t.endswith("**"):
+        return ctypes.POINTER(ctypes.c_void_p)      # out-handles (fc_flow**, fc_embedder**)
+    if t.endswith("*") or t in ("fc_stream_t",):
+        return ctypes.c_void_p
+    return {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "double": ctypes.c_double,
+            "uint64_t": ctypes.c_uint64, "unsigned long long": ctypes.c_uint64, "long long": ctypes.c_int64}[t]
+
+
+def test_ctypes_argument_types_match_the_header_one_by_one():
+    """Every entry of lib.SIGNATURES has the header prototype's return type and, position by position, its parameter types
+    (pointers and fc_stream_t -> c_void_p, int -> c_int, int64_t -> c_int64, float -> c_float ...): a drifted binding would
+    pass wrong-sized arguments without any error on the GPU box."""
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(fclib.SIGNATURES)
+    for name, (res, args) in fclib.SIGNATURES.items():
+        ret, types = protos[name]
+        assert (res is None) if ret == "void" else (_ctype_of(ret) is res), (name, ret, res)
+        want = [_ctype_of(t) for t in types]
+        assert want == list(args), (name, types, args)
