@@ -96,3 +96,37 @@ def test_fused_whi_wlo_mma_layout_invariants():
     stg_floats = 1024 if _tc_define("TC_RES_PREFETCH") == "1" else 32 * 20
     smem = stages * (128 * bk * 4 + 2 * cap * bk * 2) + 8 * stg_floats * 4 + 1024
     assert smem <= 227 * 1024
+
+
+def test_error_compensated_operand_schemes_reach_fp32_accuracy():
+    """The arithmetic the tensor-core GEMM relies on, with the product's own pack-time splits (packing.f16_split / tf32_round):
+    D = Ahi.Whi + 2^-11 (Alo.Whi + Ahi.Wlo) for 3xFP16 (hi = fp16(x), lo = fp16((x - hi) 2^11)) and
+    D = Ahi.Whi + Alo.Whi + Ahi.Wlo for 3xTF32, products and sums taken exactly (fp64) so that only the OPERAND scheme is
+    measured: both must be as close to the exact product as an fp32 GEMM is (~K^0.5 2^-24 relative to |a||w| per term; the
+    dropped Alo.Wlo term is 2^-22 of a term).  A plain single fp16 / TF32 product is shown to be 1000x worse."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 64, 48, 512
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / math.sqrt(K)
+    exact = A.double() @ W.double().t()
+    fp32 = (A @ W.t()).double()
+    e_fp32 = (fp32 - exact).abs().max().item()
+    ah, al = packing.f16_split(A)
+    wh, wl = packing.f16_split(W)
+    d16 = ah.double() @ wh.double().t() + (al.double() @ wh.double().t() + ah.double() @ wl.double().t()) / 2048.0
+    e16 = (d16 - exact).abs().max().item()
+    single16 = (ah.double() @ wh.double().t() - exact).abs().max().item()
+    a_hi = packing.tf32_round(A); a_lo = packing.tf32_round(A - a_hi)
+    w_hi = packing.tf32_round(W); w_lo = packing.tf32_round(W - w_hi)
+    d32 = a_hi.double() @ w_hi.double().t() + a_lo.double() @ w_hi.double().t() + a_hi.double() @ w_lo.double().t()
+    e32 = (d32 - exact).abs().max().item()
+    assert e16 < 2e-6 and e32 < 2e-6, (e16, e32)
+    assert e16 < 4 * e_fp32 + 1e-7 and e32 < 4 * e_fp32 + 1e-7, (e16, e32, e_fp32)        # as good as an fp32 GEMM
+    assert single16 > 200 * e16                                                           # what the compensation buys
+    # range: the hi part overflows exactly where the docs say (|x| >= 65520 -> inf), lo stays clear of fp16 subnormals for normal x
+    assert torch.isinf(packing.f16_split(torch.tensor([65520.0]))[0]).all()
+    x = torch.tensor([1.0 + 2.0 ** -12, 3.14159265, 1e-3])
+    hi, lo = packing.f16_split(x)
+    rec = hi.double() + lo.double() / 2048.0
+    assert ((rec - x.double()).abs() / x.double()).max().item() < 2.0 ** -21
