@@ -194,6 +194,18 @@ def ncu_traffic():
         return None, f"no committed ncu capture readable: {exc}"
 
 
+def ffma_peak():
+    """Measured fp32 FFMA rate of a B200 of this pool in TFLOP/s (profiles/r02_unit_peaks.txt, scripts/micro/peaks.cu; CUDA
+    events, no profiler): the denominator of the FMA-bound kernel classes.  None if the file is not readable."""
+    try:
+        import re
+        with open(os.path.join(ROOT, "profiles", "r02_unit_peaks.txt")) as f:
+            m = re.search(r"fp32 FFMA\s*:\s*([0-9.]+) TFLOP/s", f.read())
+        return float(m.group(1)) if m else None
+    except Exception:
+        return None
+
+
 def _timed(fn, steps, warmup=2):
     """pairs-agnostic device timing of fn(): CUDA events on the current stream, after warm-up."""
     for _ in range(warmup):
@@ -507,6 +519,10 @@ def main():
             if ln_c[i]:
                 classes[nm] = {"launches": int(ln_c[i]), "ms": round(ms_c[i], 3), "share": round(ms_c[i] / total_ms, 4),
                                "tflops": round(fl_c[i] / ms_c[i] / 1e9, 2), "gbs": round(by_c[i] / ms_c[i] / 1e6, 1)}
+        fpk = ffma_peak()
+        for nm in ("knn", "gemm_fp32_ffma"):      # FMA-bound classes against the measured FFMA rate (profiles/r02_unit_peaks.txt)
+            if fpk and nm in classes:
+                classes[nm]["frac_of_measured_ffma_peak"] = round(classes[nm]["tflops"] / fpk, 4)
         pk = peaks()
         top = 1 if ln_c[1] and ms_c[1] >= ms_c[0] else 0
         achieved = fl_c[top] / ms_c[top] / 1e9

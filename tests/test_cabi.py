@@ -51,6 +51,12 @@ def test_bench_reads_traffic_from_committed_profile():
     assert isinstance(traffic, int) and traffic > 0, note
 
 
+def test_bench_reads_the_measured_ffma_peak():
+    import bench
+    v = bench.ffma_peak()
+    assert isinstance(v, float) and 50.0 < v < 80.0      # 148 SMs x 128 lanes x 2 flop x <= 1.965 GHz = 74.5 TFLOP/s nominal
+
+
 def test_argument_validation_happens_before_any_gpu_work():
     """Invalid arguments are rejected with FC_ERR_INVALID_ARG / FC_ERR_UNSUPPORTED on the host, before a single CUDA
     call: these run without a GPU."""
