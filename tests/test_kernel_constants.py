@@ -130,3 +130,31 @@ def test_error_compensated_operand_schemes_reach_fp32_accuracy():
     hi, lo = packing.f16_split(x)
     rec = hi.double() + lo.double() / 2048.0
     assert ((rec - x.double()).abs() / x.double()).max().item() < 2.0 ** -21
+
+
+def test_knn_select_algorithm_model_matches_plain_sort_incl_masses_of_ties():
+    """tests/knn_select_sim.py (a lane-by-lane model of knn_select_kernel) against a plain (key desc, index asc) sort: random
+    rows of one and several segments, k = 1 / 40 / 64, rows shorter than a warp, exact pairs of duplicates, and MASSES of equal
+    keys -- the exact-bisection path of the kernel (more than SEL_CAP survivors), incl. ties that straddle segments and the
+    carried list, whose index order no GPU test compares with the oracle on more than pairs."""
+    from tests import knn_select_sim as sim
+    rng = np.random.RandomState(0)
+    stats = {}
+    cases = []
+    for nt, k in [(33, 1), (40, 40), (100, 7), (1250, 40), (1280, 64), (1281, 40), (3000, 40), (2048, 64)]:
+        cases.append((rng.randn(nt).astype(np.float32), k))
+    dup = rng.randn(625).astype(np.float32)
+    cases.append((np.concatenate([dup, dup]), 40))                                   # every key twice
+    cases.append((np.zeros(1500, np.float32), 64))                                   # all equal
+    cases.append((rng.choice(np.array([-1.0, 0.5, 2.0], np.float32), 2000), 40))     # three values: masses of ties at the threshold
+    few = rng.randn(3000).astype(np.float32); few[rng.rand(3000) < 0.6] = 7.0         # 60 % share the LARGEST key, 3 segments
+    cases.append((few, 64))
+    low = rng.randn(2600).astype(np.float32); low[rng.rand(2600) < 0.9] = -3.0        # 90 % share a key BELOW the top-k
+    cases.append((low, 40))
+    mix = np.round(rng.randn(4000) * 2).astype(np.float32)                           # ~15 distinct values, 4 segments
+    cases.append((mix, 40))
+    for keys, k in cases:
+        got = sim.select(keys, k, stats)
+        want = sim.reference(keys, k)
+        assert np.array_equal(got, want), (len(keys), k, got[:8], want[:8])
+    assert stats.get("compaction", 0) > 0 and stats.get("bisection", 0) > 0          # both paths of the kernel were exercised

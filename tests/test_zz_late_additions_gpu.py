@@ -103,3 +103,19 @@ def test_evaluate_on_batches_equals_the_reference_loop_composed_by_hand():
     assert change_means == want_means
     assert abs(nats_avg - want_nats) <= 1e-5 * max(1.0, abs(want_nats))
     e.close()
+
+
+@pytest.mark.parametrize("n,k,sites", [(1500, 40, 1), (2000, 40, 3), (3000, 64, 2)])
+def test_knn_masses_of_duplicate_points_follow_the_tie_rule(n, k, sites):
+    """Hundreds of IDENTICAL points (the dataset's oversampling produces exact duplicates, reference utils.py:362-370): more than
+    256 keys tie at or above a query's k-th best, which takes knn_select_kernel's exact-bisection path (ties in index order,
+    across segments and the carried list).  Bit-exact against the canonical oracle; the algorithm itself is also checked on CPU
+    by a lane-by-lane model (tests/knn_select_sim.py)."""
+    g = torch.Generator().manual_seed(n + k)
+    x = torch.rand(1, n, 6, generator=g)
+    site = torch.rand(sites, 6, generator=g)
+    pick = torch.rand(n, generator=g) < 0.6                      # 60 % of the points sit exactly on one of the sites
+    x[0, pick] = site[torch.randint(0, sites, (int(pick.sum()),), generator=g)]
+    want = knn_ref.knn_self(x, k)
+    got = eng.knn(x.permute(0, 2, 1).to(DEV), k).cpu()
+    assert torch.equal(got, want)
